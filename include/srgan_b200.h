@@ -1,0 +1,218 @@
+/*
+ * srgan_b200.h -- C ABI of the B200-native SRGAN training-step kernels.
+ *
+ * This is the drop-in boundary underneath the Python surface of the reference's
+ * pyfiles/ (model.py, util.py, util_notebook.py).  The reference has no FFI of its
+ * own: every entry point below replaces a PyTorch library call that the reference
+ * issues on the hot path; the call site it replaces is cited as
+ * "ref: <file>:<line>" (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     name starts with h_;
+ *   - activations are fp32, NHWC ("channels last"): x[n][h][w][c];
+ *   - convolution filters are fp32, KRSC: w[k][r][s][c] (== torch channels_last of a
+ *     [K,C,R,S] parameter);
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates; scratch is passed in (query the size first);
+ *   - return value: 0 = ok, <0 = invalid argument (SRGAN_E_*), >0 = cudaError_t.
+ *     Nothing throws across this boundary.  srgan_last_error() gives a message.
+ */
+#ifndef SRGAN_B200_H_
+#define SRGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRGAN_ABI_VERSION 1
+
+/* status codes */
+#define SRGAN_OK            0
+#define SRGAN_E_BADARG     -1
+#define SRGAN_E_UNSUPPORTED -2
+#define SRGAN_E_WORKSPACE  -3
+
+/* activation ids (epilogues / fused norm) */
+#define SRGAN_ACT_NONE  0
+#define SRGAN_ACT_RELU  1
+#define SRGAN_ACT_LRELU 2
+#define SRGAN_ACT_TANH  3
+
+/* convolution engine selection */
+#define SRGAN_CONV_AUTO 0   /* tcgen05 (TF32 in, fp32 accumulate) where the shape qualifies, else FFMA */
+#define SRGAN_CONV_FP32 1   /* fp32 FFMA implicit GEMM: exact-fp32 parity path and odd shapes */
+#define SRGAN_CONV_TF32 2   /* force the tcgen05 path; SRGAN_E_UNSUPPORTED when the shape does not qualify */
+
+typedef struct srgan_conv_desc {
+  int32_t N, H, W, C;   /* input activation x[N][H][W][C] */
+  int32_t K, R, S;      /* filter w[K][R][S][C] */
+  int32_t P, Q;         /* output y[N][P][Q][K]; P = (H + 2*pad - R)/stride + 1 */
+  int32_t stride, pad;  /* symmetric, zero padding (reflect padding = srgan_reflect_pad_* + pad 0) */
+  /* element strides of x for fprop/wgrad; all 0 means dense NHWC.  Lets the stem read an
+     NCHW image batch in place. */
+  int64_t xs_n, xs_h, xs_w, xs_c;
+} srgan_conv_desc;
+
+const char* srgan_last_error(void);
+int  srgan_abi_version(void);
+/* 1 when the library was built with the tcgen05 convolution kernels */
+int  srgan_has_tcgen05(void);
+
+/* ---------------------------------------------------------------- convolutions
+ * ref: nn.Conv2d forward  pyfiles/model.py:191,193,212,215,232,262,269,274,302,309,328-331,
+ *      358,364,369,385,419,425,430,445 ; nn.ConvTranspose2d pyfiles/model.py:227,230
+ *      (a transposed convolution's forward is srgan_conv2d_dgrad of the mirrored conv,
+ *      its input gradient is srgan_conv2d_fprop, its filter gradient srgan_conv2d_wgrad
+ *      with x and dy swapped).
+ * fprop : y = act(conv(x, w) + bias)
+ * dgrad : dx = conv_transpose(dy, w)            (overwrites dx)
+ * wgrad : dw = sum_pixels x (*) dy ; dbias = sum_pixels dy (either may be NULL)
+ */
+size_t srgan_conv2d_workspace(const srgan_conv_desc* d, int pass /*0 fprop,1 dgrad,2 wgrad*/, int engine);
+int srgan_conv2d_fprop(const srgan_conv_desc* d, const float* x, const float* w, const float* bias,
+                       float* y, int act, float slope, int engine,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int srgan_conv2d_dgrad(const srgan_conv_desc* d, const float* dy, const float* w, float* dx,
+                       int engine, void* workspace, size_t workspace_bytes, void* stream);
+int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, const float* dy, float* dw,
+                       float* dbias, int engine, void* workspace, size_t workspace_bytes, void* stream);
+/* which engine AUTO resolves to for this shape/pass: SRGAN_CONV_FP32 or SRGAN_CONV_TF32 */
+int srgan_conv2d_engine(const srgan_conv_desc* d, int pass);
+
+/* ---------------------------------------------------------------- layout / padding
+ * ref: images arrive NCHW from the DataLoader (notebook/03-train... cell 24:16-18);
+ *      padding_mode="reflect" pyfiles/model.py:358,364,419,425 */
+int srgan_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, void* stream);
+int srgan_nhwc_to_nchw(const float* x, float* y, int N, int C, int H, int W, void* stream);
+int srgan_reflect_pad_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream);
+int srgan_reflect_pad_bwd(const float* dy, float* dx, int N, int H, int W, int C, int pad, void* stream);
+
+/* ---------------------------------------------------------------- fused instance norm
+ * ref: CBINorm2d.forward pyfiles/model.py:54-67 (F.instance_norm + ConBias + affine),
+ *      nn.InstanceNorm2d(affine=False) pyfiles/model.py:178, followed by ReLU
+ *      (:199,240,246) / LeakyReLU(0.2) (:357,361,417,422) / residual add (:201).
+ *   xh = (x - mean_hw) * rstd_hw ; v = (xh + cbias[n][c]) * gamma[c] + beta[c]
+ *   y  = act(v) (+ residual)
+ * gamma/beta/cbias/residual may be NULL.  mean/rstd [N*C] are written by fwd and read by bwd.
+ * bwd writes dx and the per-(n,c) sums s1 = sum dv, s2 = sum dv*xh  (dv = dy*act'(v));
+ * srgan_inorm_param_grads turns (s1,s2) into dgamma, dbeta (accumulated over n in a fixed
+ * order, overwritten) and dcbias[n][c].
+ */
+int srgan_inorm_fwd(const float* x, float* y, float* mean, float* rstd,
+                    const float* gamma, const float* beta, const float* cbias, const float* residual,
+                    int N, int HW, int C, float eps, int act, float slope, void* stream);
+int srgan_inorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, const float* cbias,
+                    float* dx, float* s1, float* s2,
+                    int N, int HW, int C, int act, float slope, void* stream);
+int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma, const float* cbias,
+                            float* dgamma, float* dbeta, float* dcbias, int N, int C, void* stream);
+
+/* ---------------------------------------------------------------- conditional bias
+ * ref: ConBias = nn.Sequential(nn.Linear(num_con, C), nn.Tanh()) pyfiles/model.py:16-19,57
+ *   t[n][c] = tanh(sum_j con[n][j] * w[c][j] + b[c])
+ * bwd: dpre = dt * (1 - t^2); dw[c][j] = sum_n dpre*con ; db[c] = sum_n dpre ;
+ *      dcon[n][j] = sum_c dpre * w[c][j]   (any output may be NULL) */
+int srgan_condbias_fwd(const float* con, const float* w, const float* b, float* t,
+                       int N, int J, int C, void* stream);
+int srgan_condbias_bwd(const float* dt, const float* t, const float* con, const float* w,
+                       float* dw, float* db, float* dcon, int N, int J, int C, void* stream);
+
+/* ---------------------------------------------------------------- pooling / elementwise
+ * ref: nn.AvgPool2d(2,2) pyfiles/model.py:365,368,426,429 ; nn.AvgPool2d(3, stride=2, padding=1,
+ *      count_include_pad=False) :286,324 ; LeakyReLU(0.2)+AdaptiveAvgPool2d(1) :394,454 ;
+ *      LeakyReLU(0.01) :263,270,303,310 ; Tanh :248 ; residual/shortcut adds :201,375,436 */
+int srgan_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int srgan_avgpool2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+/* y = avgpool2(a) + b  (encoder block tail: cmp-conv pooled + shortcut) */
+int srgan_avgpool2_add_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C, void* stream);
+int srgan_avgpool3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int srgan_avgpool3s2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+/* f[n][c] = mean_hw lrelu(x[n][hw][c]) */
+int srgan_lrelu_gap_fwd(const float* x, float* f, int N, int HW, int C, float slope, void* stream);
+int srgan_lrelu_gap_bwd(const float* df, const float* x, float* dx, int N, int HW, int C, float slope, void* stream);
+/* dx = dy * act'(.) evaluated from the saved OUTPUT y of the activation */
+int srgan_act_bwd(const float* dy, const float* y, float* dx, size_t n, int act, float slope, void* stream);
+int srgan_add(const float* a, const float* b, float* y, size_t n, void* stream);
+/* column sums of a [rows][C] matrix (bias gradients): out[c] = sum_r x[r][c] */
+int srgan_colsum(const float* x, float* out, size_t rows, int C, void* stream);
+
+/* ---------------------------------------------------------------- encoder head
+ * ref: softmax over the class dimension, nn.Softmax() pyfiles/model.py:333-334 ;
+ *      reparametrize pyfiles/model.py:398-402,459-463 : z = eps*exp(0.5*logvar) + mu */
+int srgan_softmax_fwd(const float* x, float* y, int N, int J, void* stream);
+int srgan_softmax_bwd(const float* dy, const float* y, float* dx, int N, int J, void* stream);
+int srgan_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, size_t n, void* stream);
+int srgan_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu, float* dlogvar,
+                      size_t n, void* stream);
+
+/* ---------------------------------------------------------------- image / patch losses
+ * ref: torch.mean(torch.abs(a-b)) pyfiles/util_notebook.py:295,309,348,359,625,639,676,686 ;
+ *      get_loss_D (MSE against a constant) pyfiles/util.py:457-462 ;
+ *      get_domainloss_D (MSE between two tensors) pyfiles/util.py:464-468
+ * fwd kernels write ONE fp32 scalar to out (overwrite); reductions use a fixed order
+ * (bit-reproducible run to run).  scratch: srgan_reduce_scratch_bytes(n).          */
+size_t srgan_reduce_scratch_bytes(size_t n);
+int srgan_l1_mean_fwd(const float* a, const float* b, size_t n, float* out, void* scratch, void* stream);
+/* da = g[0]*sign(a-b)/n ; db = -da  (either may be NULL); g is a device scalar */
+int srgan_l1_mean_bwd(const float* a, const float* b, const float* g, float* da, float* db, size_t n, void* stream);
+int srgan_mse_const_fwd(const float* x, float target, size_t n, float* out, void* scratch, void* stream);
+int srgan_mse_const_bwd(const float* x, float target, const float* g, float* dx, size_t n, void* stream);
+int srgan_mse_fwd(const float* a, const float* b, size_t n, float* out, void* scratch, void* stream);
+int srgan_mse_bwd(const float* a, const float* b, const float* g, float* da, float* db, size_t n, void* stream);
+
+/* ---------------------------------------------------------------- latent batch losses
+ * ref: conventional KL pyfiles/util_notebook.py:300-304,630-634 ; batch-KL :314-320,644-650 ;
+ *      corrcoef / corrcoef_loss pyfiles/util.py:470-517 ; GaussianHistogram /
+ *      histogram_imitation pyfiles/util.py:521-553.
+ * mu is [n][D] (row = sample), D <= 32, bins <= 64.
+ * out (fp32) layout, SRGAN_LATENT_OUT_FLOATS(D,bins) floats:
+ *   [0] batch-KL  [1] corr loss  [2] hist loss  [3] conventional KL
+ *   [4 .. 4+D)        mean_d
+ *   [.. +D)           var_d   (unbiased * n_cfg/(n_cfg-1))
+ *   [.. +D)           unbiased variance c_dd (diagonal of the covariance)
+ *   [.. +D*D)         corrcoef matrix (clamped)
+ *   [.. +D*bins)      soft histogram h[d][b]
+ *   [.. +D)           histogram mass S_d = sum_b h[d][b]
+ * flags: bit0 batch-KL, bit1 corr, bit2 hist, bit3 conventional KL (needs logvar).
+ * One CTA, fixed summation order: results are bit-identical for a given (mu, n).
+ */
+#define SRGAN_LATENT_BKL  1
+#define SRGAN_LATENT_CORR 2
+#define SRGAN_LATENT_HIST 4
+#define SRGAN_LATENT_KL   8
+#define SRGAN_LATENT_OUT_FLOATS(D, bins) (4 + 4 * (D) + (D) * (D) + (D) * (bins))
+int srgan_latent_losses_fwd(const float* mu, const float* logvar, int n, int D, float n_cfg,
+                            const float* hist_target, int bins, float hist_min, float hist_max, float sigma,
+                            int flags, float* out, void* stream);
+/* dmu[n][D] = sum_k g4[k] * dLoss_k/dmu, g4 = DEVICE pointer to the 4 upstream gradients (same
+ * order as out[0..4)); dlogvar likewise for the KL term (may be NULL).  Reads the statistics fwd
+ * left in `out`.  Only rows [row0,row0+rows) of the batch are differentiated and written to
+ * dmu[rows][D] / dlogvar[rows][D] (a data-parallel rank's slice of an all-gathered batch).   */
+int srgan_latent_losses_bwd(const float* mu, const float* logvar, int n, int D, float n_cfg,
+                            const float* hist_target, int bins, float hist_min, float hist_max, float sigma,
+                            int flags, const float* out, const float* g4,
+                            float* dmu, float* dlogvar, int row0, int rows, void* stream);
+/* stats = the `out` blob of srgan_latent_losses_fwd(flags with SRGAN_LATENT_CORR) */
+int srgan_corrcoef_bwd(const float* mu, int n, int D, const float* stats, const float* dcorr,
+                       float* dmu, void* stream);
+int srgan_softhist_fwd(const float* x, int n, int bins, float hist_min, float hist_max, float sigma,
+                       float* h, void* stream);
+int srgan_softhist_bwd(const float* x, const float* dh, int n, int bins, float hist_min, float hist_max,
+                       float sigma, float* dx, void* stream);
+
+/* ---------------------------------------------------------------- optimizer
+ * ref: optim.Adam(..., betas=(0.5,0.999)) pyfiles/util_notebook.py:117-131,500-507 (torch.optim.Adam
+ *      semantics: bias-corrected, eps added to sqrt(v_hat), no weight decay, no amsgrad).
+ * One launch updates a whole flat parameter buffer.                                  */
+int srgan_adam_step(float* p, const float* g, float* m, float* v, size_t n,
+                    float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGAN_B200_H_ */

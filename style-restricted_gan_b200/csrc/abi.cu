@@ -1,0 +1,119 @@
+// C-ABI front door: error reporting, convolution engine dispatch, small wrappers.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace srgan {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// conv_ffma.cu
+size_t conv_ffma_workspace(const srgan_conv_desc* d, int pass);
+int conv_fprop_ffma_launch(const srgan_conv_desc*, const float*, const float*, const float*, float*, int, float,
+                           cudaStream_t);
+int conv_dgrad_ffma_launch(const srgan_conv_desc*, const float*, const float*, float*, cudaStream_t);
+int conv_wgrad_ffma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
+                           cudaStream_t);
+int colsum_launch(const float*, float*, long long, int, cudaStream_t);
+
+// conv_umma.cu (tcgen05 engine)
+bool conv_umma_supported(const srgan_conv_desc* d, int pass);
+size_t conv_umma_workspace(const srgan_conv_desc* d, int pass);
+int conv_fprop_umma_launch(const srgan_conv_desc*, const float*, const float*, const float*, float*, int, float,
+                           void*, size_t, cudaStream_t);
+int conv_dgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, void*, size_t,
+                           cudaStream_t);
+int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
+                           cudaStream_t);
+
+static int check_desc(const srgan_conv_desc* d) {
+  if (!d) { set_error("conv: null descriptor"); return SRGAN_E_BADARG; }
+  if (d->N < 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->K <= 0 || d->R <= 0 || d->S <= 0 || d->stride <= 0 ||
+      d->pad < 0) {
+    set_error("conv: non-positive dimension"); return SRGAN_E_BADARG;
+  }
+  int P = (d->H + 2 * d->pad - d->R) / d->stride + 1, Q = (d->W + 2 * d->pad - d->S) / d->stride + 1;
+  if (d->H + 2 * d->pad < d->R || d->W + 2 * d->pad < d->S || P != d->P || Q != d->Q) {
+    set_error("conv: output size mismatch (expected %dx%d, got %dx%d)", P, Q, d->P, d->Q);
+    return SRGAN_E_BADARG;
+  }
+  return SRGAN_OK;
+}
+
+static bool dense_x(const srgan_conv_desc* d) {
+  if (d->xs_n == 0 && d->xs_h == 0 && d->xs_w == 0 && d->xs_c == 0) return true;
+  return d->xs_c == 1 && d->xs_w == d->C && d->xs_h == (int64_t)d->W * d->C &&
+         d->xs_n == (int64_t)d->H * d->W * d->C;
+}
+
+static int resolve_engine(const srgan_conv_desc* d, int pass, int engine) {
+  bool ok = (pass == 1 || dense_x(d)) && conv_umma_supported(d, pass);
+  if (engine == SRGAN_CONV_FP32) return SRGAN_CONV_FP32;
+  if (engine == SRGAN_CONV_TF32) return ok ? SRGAN_CONV_TF32 : SRGAN_E_UNSUPPORTED;
+  return ok ? SRGAN_CONV_TF32 : SRGAN_CONV_FP32;
+}
+
+}  // namespace srgan
+
+using namespace srgan;
+
+extern "C" const char* srgan_last_error(void) { return g_err; }
+extern "C" int srgan_abi_version(void) { return SRGAN_ABI_VERSION; }
+
+extern "C" int srgan_conv2d_engine(const srgan_conv_desc* d, int pass) {
+  if (int e = check_desc(d)) return e;
+  return resolve_engine(d, pass, SRGAN_CONV_AUTO);
+}
+
+extern "C" size_t srgan_conv2d_workspace(const srgan_conv_desc* d, int pass, int engine) {
+  if (check_desc(d)) return 0;
+  int e = resolve_engine(d, pass, engine);
+  if (e == SRGAN_CONV_TF32) return conv_umma_workspace(d, pass);
+  if (e == SRGAN_CONV_FP32) return conv_ffma_workspace(d, pass);
+  return 0;
+}
+
+extern "C" int srgan_conv2d_fprop(const srgan_conv_desc* d, const float* x, const float* w, const float* bias,
+                                  float* y, int act, float slope, int engine, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(x && w && y, "null pointer");
+  int e = resolve_engine(d, 0, engine);
+  if (e < 0) { set_error("conv fprop: shape not supported by the tcgen05 engine"); return e; }
+  if (e == SRGAN_CONV_TF32)
+    return conv_fprop_umma_launch(d, x, w, bias, y, act, slope, ws, ws_bytes, (cudaStream_t)stream);
+  return conv_fprop_ffma_launch(d, x, w, bias, y, act, slope, (cudaStream_t)stream);
+}
+
+extern "C" int srgan_conv2d_dgrad(const srgan_conv_desc* d, const float* dy, const float* w, float* dx,
+                                  int engine, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
+  int e = resolve_engine(d, 1, engine);
+  if (e < 0) { set_error("conv dgrad: shape not supported by the tcgen05 engine"); return e; }
+  if (e == SRGAN_CONV_TF32) return conv_dgrad_umma_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream);
+  return conv_dgrad_ffma_launch(d, dy, w, dx, (cudaStream_t)stream);
+}
+
+extern "C" int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, const float* dy, float* dw,
+                                  float* dbias, int engine, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(x && dy && (dw || dbias), "null pointer");
+  int e = resolve_engine(d, 2, engine);
+  if (e < 0) { set_error("conv wgrad: shape not supported by the tcgen05 engine"); return e; }
+  if (e == SRGAN_CONV_TF32)
+    return conv_wgrad_umma_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
+  return conv_wgrad_ffma_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srgan_colsum(const float* x, float* out, size_t rows, int C, void* stream) {
+  SRGAN_CHECK_ARG(x && out && C >= 0, "bad argument");
+  return colsum_launch(x, out, (long long)rows, C, (cudaStream_t)stream);
+}

@@ -1,0 +1,464 @@
+// Memory-bound glue kernels: layout changes, reflect padding, pooling, activations,
+// conditional bias, softmax, reparametrisation.  NHWC fp32; vectorised (float4) where the
+// channel count allows, grid-stride loops sized to a multiple of the SM count.
+#include "common.cuh"
+
+namespace srgan {
+
+static inline unsigned grid_for(size_t work, int threads) {
+  size_t blocks = (work + threads - 1) / threads;
+  size_t cap = (size_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+#define GRID_STRIDE(i, n) \
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+
+// ------------------------------------------------------------------ NCHW <-> NHWC (smem transpose)
+// One block transposes a [C x 32 pixels] panel; coalesced on both sides.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xs = x + (size_t)n * C * HW;
+  float* ys = y + (size_t)n * C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? xs[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    if (c < C && p < HW) ys[(size_t)p * C + c] = tile[threadIdx.x][j];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xs = x + (size_t)n * C * HW;
+  float* ys = y + (size_t)n * C * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? xs[(size_t)p * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) ys[(size_t)c * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------ reflect padding
+__device__ __forceinline__ int reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+// y[N][H+2p][W+2p][C]
+__global__ void reflect_pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W,
+                                       int C, int pad) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const size_t total = (size_t)N * Hp * Wp * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    size_t t = i / C;
+    int w = (int)(t % Wp); t /= Wp;
+    int h = (int)(t % Hp);
+    int n = (int)(t / Hp);
+    int sh = reflect(h - pad, H), sw = reflect(w - pad, W);
+    y[i] = __ldg(x + (((size_t)n * H + sh) * W + sw) * C + c);
+  }
+}
+// dx[n][h][w][c] = sum over padded positions that mirror onto (h,w); gather form, fixed order
+__global__ void reflect_pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
+                                       int C, int pad) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const size_t total = (size_t)N * H * W * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    size_t t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    // candidate padded rows: h+pad (interior), pad-h (top mirror, 1<=h<=pad), 2(H-1)-h+pad (bottom mirror)
+    int hs[3], ws[3], nh = 0, nw = 0;
+    hs[nh++] = h + pad;
+    if (h >= 1 && h <= pad) hs[nh++] = pad - h;
+    if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h + pad;
+    ws[nw++] = w + pad;
+    if (w >= 1 && w <= pad) ws[nw++] = pad - w;
+    if (w <= W - 2 && w >= W - 1 - pad) ws[nw++] = 2 * (W - 1) - w + pad;
+    float s = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) s += __ldg(dy + (((size_t)n * Hp + hs[a]) * Wp + ws[b]) * C + c);
+    dx[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------ pooling
+// AvgPool2d(2,2): floor output size, trailing row/col dropped.
+__global__ void avgpool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ addend,
+                                    float* __restrict__ y, int N, int H, int W, int C) {
+  const int P = H / 2, Q = W / 2;
+  const size_t total = (size_t)N * P * Q * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    size_t t = i / C;
+    int q = (int)(t % Q); t /= Q;
+    int p = (int)(t % P);
+    int n = (int)(t / P);
+    const float* b = x + (((size_t)n * H + 2 * p) * W + 2 * q) * C + c;
+    float v = 0.25f * ((__ldg(b) + __ldg(b + C)) + (__ldg(b + (size_t)W * C) + __ldg(b + (size_t)W * C + C)));
+    if (addend) v += __ldg(addend + i);
+    y[i] = v;
+  }
+}
+__global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
+                                    int C) {
+  const int P = H / 2, Q = W / 2;
+  const size_t total = (size_t)N * H * W * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    size_t t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    int p = h >> 1, q = w >> 1;
+    dx[i] = (p < P && q < Q) ? 0.25f * __ldg(dy + (((size_t)n * P + p) * Q + q) * C + c) : 0.f;
+  }
+}
+// AvgPool2d(3, stride 2, padding 1, count_include_pad=False)
+__global__ void avgpool3s2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W,
+                                      int C) {
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)N * P * Q * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    size_t t = i / C;
+    int q = (int)(t % Q); t /= Q;
+    int p = (int)(t % P);
+    int n = (int)(t / P);
+    int h0 = max(2 * p - 1, 0), h1 = min(2 * p + 2, H), w0 = max(2 * q - 1, 0), w1 = min(2 * q + 2, W);
+    float s = 0.f;
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) s += __ldg(x + (((size_t)n * H + h) * W + w) * C + c);
+    y[i] = s / (float)((h1 - h0) * (w1 - w0));
+  }
+}
+__global__ void avgpool3s2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
+                                      int C) {
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)N * H * W * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    size_t t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    // windows p with 2p-1 <= h <= 2p+1
+    float s = 0.f;
+    for (int p = max((h - 1 + 1) / 2, 0); p <= min((h + 1) / 2, P - 1); ++p) {
+      int h0 = max(2 * p - 1, 0), h1 = min(2 * p + 2, H);
+      if (h < h0 || h >= h1) continue;
+      for (int q = max(w / 2, 0); q <= min((w + 1) / 2, Q - 1); ++q) {
+        int w0 = max(2 * q - 1, 0), w1 = min(2 * q + 2, W);
+        if (w < w0 || w >= w1) continue;
+        s += __ldg(dy + (((size_t)n * P + p) * Q + q) * C + c) / (float)((h1 - h0) * (w1 - w0));
+      }
+    }
+    dx[i] = s;
+  }
+}
+
+// f[n][c] = mean_hw lrelu(x).  One warp-row per (n, 32 channels); block (32, 8) strides pixels.
+__global__ void lrelu_gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ f, int HW, int C,
+                                     float slope) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < C)
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      float v = __ldg(x + ((size_t)n * HW + p) * C + c);
+      s += v > 0.f ? v : v * slope;
+    }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    f[(size_t)n * C + c] = t / (float)HW;
+  }
+}
+__global__ void lrelu_gap_bwd_kernel(const float* __restrict__ df, const float* __restrict__ x,
+                                     float* __restrict__ dx, int N, int HW, int C, float slope) {
+  const size_t total = (size_t)N * HW * C;
+  const float inv = 1.f / (float)HW;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C);
+    int n = (int)(i / ((size_t)HW * C));
+    float v = __ldg(x + i);
+    dx[i] = __ldg(df + (size_t)n * C + c) * inv * (v > 0.f ? 1.f : slope);
+  }
+}
+
+// ------------------------------------------------------------------ elementwise
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                               size_t n, int act, float slope) {
+  size_t n4 = n / 4;
+  const float4* d4 = reinterpret_cast<const float4*>(dy);
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  float4* o4 = reinterpret_cast<float4*>(dx);
+  GRID_STRIDE(i, n4) {
+    float4 a = __ldg(d4 + i), b = __ldg(y4 + i), o;
+    o.x = a.x * act_grad_out(b.x, act, slope);
+    o.y = a.y * act_grad_out(b.y, act, slope);
+    o.z = a.z * act_grad_out(b.z, act, slope);
+    o.w = a.w * act_grad_out(b.w, act, slope);
+    o4[i] = o;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * act_grad_out(y[i], act, slope);
+}
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                           size_t n) {
+  size_t n4 = n / 4;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* o4 = reinterpret_cast<float4*>(y);
+  GRID_STRIDE(i, n4) {
+    float4 p = __ldg(a4 + i), q = __ldg(b4 + i);
+    o4[i] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = a[i] + b[i];
+}
+
+// ------------------------------------------------------------------ conditional bias
+// t[n][c] = tanh(b[c] + sum_j con[n][j] w[c][j]); J is small (<= 64).
+__global__ void condbias_fwd_kernel(const float* __restrict__ con, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ t, int N, int J, int C) {
+  const size_t total = (size_t)N * C;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % C), n = (int)(i / C);
+    float s = b ? __ldg(b + c) : 0.f;
+    for (int j = 0; j < J; ++j) s = fmaf(__ldg(con + (size_t)n * J + j), __ldg(w + (size_t)c * J + j), s);
+    t[i] = tanhf(s);
+  }
+}
+// one block per channel tile is overkill at these sizes: one thread per (c,j) for dw, per c for db,
+// per (n,j) for dcon; all loops run in a fixed order.
+__global__ void condbias_bwd_kernel(const float* __restrict__ dt, const float* __restrict__ t,
+                                    const float* __restrict__ con, const float* __restrict__ w,
+                                    float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dcon,
+                                    int N, int J, int C) {
+  const size_t nw = (size_t)C * J, nb = C, nc = (size_t)N * J;
+  const size_t total = nw + nb + nc;
+  GRID_STRIDE(i, total) {
+    if (i < nw) {
+      if (!dw) continue;
+      int c = (int)(i / J), j = (int)(i % J);
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) {
+        float tv = __ldg(t + (size_t)n * C + c);
+        s = fmaf(__ldg(dt + (size_t)n * C + c) * (1.f - tv * tv), __ldg(con + (size_t)n * J + j), s);
+      }
+      dw[i] = s;
+    } else if (i < nw + nb) {
+      if (!db) continue;
+      int c = (int)(i - nw);
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) {
+        float tv = __ldg(t + (size_t)n * C + c);
+        s += __ldg(dt + (size_t)n * C + c) * (1.f - tv * tv);
+      }
+      db[c] = s;
+    } else {
+      if (!dcon) continue;
+      size_t k = i - nw - nb;
+      int n = (int)(k / J), j = (int)(k % J);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) {
+        float tv = __ldg(t + (size_t)n * C + c);
+        s = fmaf(__ldg(dt + (size_t)n * C + c) * (1.f - tv * tv), __ldg(w + (size_t)c * J + j), s);
+      }
+      dcon[k] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ softmax over the last dim (J small)
+__global__ void softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int J) {
+  GRID_STRIDE(n, (size_t)N) {
+    const float* r = x + n * J;
+    float m = r[0];
+    for (int j = 1; j < J; ++j) m = fmaxf(m, r[j]);
+    float s = 0.f;
+    for (int j = 0; j < J; ++j) s += expf(r[j] - m);
+    for (int j = 0; j < J; ++j) y[n * J + j] = expf(r[j] - m) / s;
+  }
+}
+__global__ void softmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                   float* __restrict__ dx, int N, int J) {
+  GRID_STRIDE(n, (size_t)N) {
+    float dot = 0.f;
+    for (int j = 0; j < J; ++j) dot += dy[n * J + j] * y[n * J + j];
+    for (int j = 0; j < J; ++j) dx[n * J + j] = y[n * J + j] * (dy[n * J + j] - dot);
+  }
+}
+
+// ------------------------------------------------------------------ reparametrisation
+__global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                   const float* __restrict__ eps, float* __restrict__ z, size_t n) {
+  GRID_STRIDE(i, n) z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
+}
+__global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ lv,
+                                   const float* __restrict__ eps, float* __restrict__ dmu,
+                                   float* __restrict__ dlv, size_t n) {
+  GRID_STRIDE(i, n) {
+    float g = dz[i];
+    if (dmu) dmu[i] = g;
+    if (dlv) dlv[i] = g * eps[i] * 0.5f * expf(0.5f * lv[i]);
+  }
+}
+
+}  // namespace srgan
+
+using namespace srgan;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int srgan_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, void* stream) {
+  SRGAN_CHECK_ARG(x && y && N >= 0 && C > 0 && H > 0 && W > 0, "bad argument");
+  if (N == 0) return SRGAN_OK;
+  dim3 g(ceil_div(H * W, 32), ceil_div(C, 32), N);
+  nchw_to_nhwc_kernel<<<g, dim3(32, 8), 0, ST>>>(x, y, C, H * W);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_nhwc_to_nchw(const float* x, float* y, int N, int C, int H, int W, void* stream) {
+  SRGAN_CHECK_ARG(x && y && N >= 0 && C > 0 && H > 0 && W > 0, "bad argument");
+  if (N == 0) return SRGAN_OK;
+  dim3 g(ceil_div(H * W, 32), ceil_div(C, 32), N);
+  nhwc_to_nchw_kernel<<<g, dim3(32, 8), 0, ST>>>(x, y, C, H * W);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_reflect_pad_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream) {
+  SRGAN_CHECK_ARG(x && y && pad >= 0 && pad < H && pad < W, "reflect pad needs pad < H,W");
+  size_t total = (size_t)N * (H + 2 * pad) * (W + 2 * pad) * C;
+  if (total == 0) return SRGAN_OK;
+  reflect_pad_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, y, N, H, W, C, pad);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_reflect_pad_bwd(const float* dy, float* dx, int N, int H, int W, int C, int pad, void* stream) {
+  SRGAN_CHECK_ARG(dy && dx && pad >= 0 && pad < H && pad < W, "reflect pad needs pad < H,W");
+  size_t total = (size_t)N * H * W * C;
+  if (total == 0) return SRGAN_OK;
+  reflect_pad_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C, pad);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  SRGAN_CHECK_ARG(x && y, "null pointer");
+  size_t total = (size_t)N * (H / 2) * (W / 2) * C;
+  if (total == 0) return SRGAN_OK;
+  avgpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, nullptr, y, N, H, W, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool2_add_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C,
+                                      void* stream) {
+  SRGAN_CHECK_ARG(a && b && y, "null pointer");
+  size_t total = (size_t)N * (H / 2) * (W / 2) * C;
+  if (total == 0) return SRGAN_OK;
+  avgpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(a, b, y, N, H, W, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
+  SRGAN_CHECK_ARG(dy && dx, "null pointer");
+  size_t total = (size_t)N * H * W * C;
+  if (total == 0) return SRGAN_OK;
+  avgpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  SRGAN_CHECK_ARG(x && y, "null pointer");
+  size_t total = (size_t)N * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * C;
+  if (total == 0) return SRGAN_OK;
+  avgpool3s2_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, y, N, H, W, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool3s2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
+  SRGAN_CHECK_ARG(dy && dx, "null pointer");
+  size_t total = (size_t)N * H * W * C;
+  if (total == 0) return SRGAN_OK;
+  avgpool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_lrelu_gap_fwd(const float* x, float* f, int N, int HW, int C, float slope, void* stream) {
+  SRGAN_CHECK_ARG(x && f && HW > 0 && N <= 65535, "bad argument");
+  if (N == 0 || C == 0) return SRGAN_OK;
+  lrelu_gap_fwd_kernel<<<dim3(ceil_div(C, 32), N), dim3(32, 8), 0, ST>>>(x, f, HW, C, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_lrelu_gap_bwd(const float* df, const float* x, float* dx, int N, int HW, int C, float slope,
+                                   void* stream) {
+  SRGAN_CHECK_ARG(df && x && dx && HW > 0, "bad argument");
+  size_t total = (size_t)N * HW * C;
+  if (total == 0) return SRGAN_OK;
+  lrelu_gap_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(df, x, dx, N, HW, C, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_act_bwd(const float* dy, const float* y, float* dx, size_t n, int act, float slope,
+                             void* stream) {
+  SRGAN_CHECK_ARG(dy && y && dx, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) % 16 == 0, "pointers must be 16-byte aligned");
+  if (n == 0) return SRGAN_OK;
+  act_bwd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(dy, y, dx, n, act, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_add(const float* a, const float* b, float* y, size_t n, void* stream) {
+  SRGAN_CHECK_ARG(a && b && y, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) % 16 == 0, "pointers must be 16-byte aligned");
+  if (n == 0) return SRGAN_OK;
+  add_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(a, b, y, n);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_condbias_fwd(const float* con, const float* w, const float* b, float* t, int N, int J, int C,
+                                  void* stream) {
+  SRGAN_CHECK_ARG(con && w && t && J > 0 && C > 0, "bad argument");
+  if (N == 0) return SRGAN_OK;
+  condbias_fwd_kernel<<<grid_for((size_t)N * C, 128), 128, 0, ST>>>(con, w, b, t, N, J, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_condbias_bwd(const float* dt, const float* t, const float* con, const float* w, float* dw,
+                                  float* db, float* dcon, int N, int J, int C, void* stream) {
+  SRGAN_CHECK_ARG(dt && t && con && w && J > 0 && C > 0, "bad argument");
+  size_t total = (size_t)C * J + C + (size_t)N * J;
+  condbias_bwd_kernel<<<grid_for(total, 128), 128, 0, ST>>>(dt, t, con, w, dw, db, dcon, N, J, C);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_softmax_fwd(const float* x, float* y, int N, int J, void* stream) {
+  SRGAN_CHECK_ARG(x && y && J > 0, "bad argument");
+  if (N == 0) return SRGAN_OK;
+  softmax_fwd_kernel<<<grid_for(N, 128), 128, 0, ST>>>(x, y, N, J);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_softmax_bwd(const float* dy, const float* y, float* dx, int N, int J, void* stream) {
+  SRGAN_CHECK_ARG(dy && y && dx && J > 0, "bad argument");
+  if (N == 0) return SRGAN_OK;
+  softmax_bwd_kernel<<<grid_for(N, 128), 128, 0, ST>>>(dy, y, dx, N, J);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_reparam_fwd(const float* mu, const float* logvar, const float* eps, float* z, size_t n,
+                                 void* stream) {
+  SRGAN_CHECK_ARG(mu && logvar && eps && z, "null pointer");
+  if (n == 0) return SRGAN_OK;
+  reparam_fwd_kernel<<<grid_for(n, 128), 128, 0, ST>>>(mu, logvar, eps, z, n);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_reparam_bwd(const float* dz, const float* logvar, const float* eps, float* dmu,
+                                 float* dlogvar, size_t n, void* stream) {
+  SRGAN_CHECK_ARG(dz && logvar && eps, "null pointer");
+  if (n == 0) return SRGAN_OK;
+  reparam_bwd_kernel<<<grid_for(n, 128), 128, 0, ST>>>(dz, logvar, eps, dmu, dlogvar, n);
+  SRGAN_RETURN_LAUNCH();
+}

@@ -1,0 +1,928 @@
+"""Differentiable operators of the SRGAN training step, backed by libsrgan_b200.so.
+
+Every function here launches hand-written sm_100a kernels through the C ABI
+(include/srgan_b200.h); PyTorch supplies device memory, streams and the autograd tape only.
+CUDA fp32 tensors are required -- there is no CPU path.
+
+Activations are handled as logical NCHW tensors stored channels-last (NHWC); convolution
+filters as logical [K,C,R,S] parameters stored channels-last (KRSC).
+
+Backward passes read parameters LIVE (they are not saved on the tape).  This reproduces the
+torch-1.4 semantics the reference was trained with: `optG.step()` between the two backward
+passes of `update_GandE` (ref: pyfiles/util_notebook.py:666 then :689) mutates the weights in
+place, and the second backward uses the updated weights with the activations saved earlier.
+"""
+import os
+
+import torch
+
+import _srgan_lib as L
+from _srgan_lib import ConvDesc, SrganKernelError, check
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TF32 = 0, 1, 2
+_ENGINE_NAMES = {"auto": ENGINE_AUTO, "fp32": ENGINE_FP32, "tf32": ENGINE_TF32}
+_engine = _ENGINE_NAMES[os.environ.get("SRGAN_CONV_ENGINE", "auto").lower()]
+
+CL = torch.channels_last
+abi_calls = 0          # number of C-ABI kernel entry points invoked (bench: gpu_launches)
+
+
+def set_conv_engine(name):
+    """'auto' (tcgen05 where the shape qualifies), 'fp32' (exact FFMA) or 'tf32' (force tcgen05)."""
+    global _engine
+    _engine = _ENGINE_NAMES[name]
+
+
+def get_conv_engine():
+    return {v: k for k, v in _ENGINE_NAMES.items()}[_engine]
+
+
+def _lib():
+    return L.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise SrganKernelError(
+                "srgan_b200 operators need CUDA float32 tensors (got %s on %s); there is no CPU fallback"
+                % (t.dtype, t.device))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    global abi_calls
+    abi_calls += 1
+    check(getattr(_lib(), name)(*args), name)
+
+
+_ws = {}
+
+
+def _workspace(dev, nbytes):
+    buf = _ws.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _ws[dev] = buf
+    return buf
+
+
+_scratch = {}
+
+
+def _red_scratch(dev):
+    s = _scratch.get(dev)
+    if s is None:
+        s = torch.zeros(_lib().srgan_reduce_scratch_bytes(0) // 4, dtype=torch.float32, device=dev)
+        _scratch[dev] = s
+    return s
+
+
+# ----------------------------------------------------------------------------- host RNG
+def dp_rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def host_normal(rows, dim, device):
+    """Standard-normal [rows, dim] from the CPU default generator, moved to `device` (the reference draws all
+    of its noise this way: pyfiles/util_notebook.py:179,554, pyfiles/model.py:400,461).
+    Data parallel: every rank draws the noise of the GLOBAL batch (same seed => same stream) and keeps its
+    own rows, so an N-GPU run consumes the RNG exactly like the single-GPU global-batch run."""
+    rank, world = dp_rank_world()
+    if world == 1:
+        return torch.randn(rows, dim).to(device)
+    return torch.randn(rows * world, dim)[rank * rows:(rank + 1) * rows].to(device)
+
+
+# ----------------------------------------------------------------------------- layout
+def _dense_nhwc(x):
+    return x.dim() == 4 and x.is_contiguous(memory_format=CL)
+
+
+def _raw_to_nhwc(x):
+    """No-autograd conversion of a 4-D tensor to channels-last storage with our kernel."""
+    if _dense_nhwc(x):
+        return x
+    if not x.is_contiguous():
+        x = x.contiguous()
+    N, C, H, W = x.shape
+    y = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device, memory_format=CL)
+    if x.numel():
+        _call("srgan_nchw_to_nhwc", _p(x), _p(y), N, C, H, W, _stream())
+    return y
+
+
+def _raw_to_nchw(x):
+    if x.is_contiguous():
+        return x
+    if not _dense_nhwc(x):
+        return x.contiguous()
+    N, C, H, W = x.shape
+    y = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device)
+    if x.numel():
+        _call("srgan_nhwc_to_nchw", _p(x), _p(y), N, C, H, W, _stream())
+    return y
+
+
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _raw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _raw_to_nchw(g)
+
+
+def to_nhwc(x):
+    """Logical NCHW tensor -> same values stored channels-last (differentiable, no-op if already)."""
+    _req(x)
+    if x.dim() != 4:
+        raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
+    if _dense_nhwc(x):
+        return x
+    return _ToNHWC.apply(x)
+
+
+def _empty_nhwc(N, C, H, W, like):
+    return torch.empty((N, C, H, W), dtype=torch.float32, device=like.device, memory_format=CL)
+
+
+# ----------------------------------------------------------------------------- convolution
+def _desc(N, H, W, C, K, R, S, stride, pad):
+    d = ConvDesc()
+    d.N, d.H, d.W, d.C, d.K, d.R, d.S = N, H, W, C, K, R, S
+    d.stride, d.pad = stride, pad
+    d.P = (H + 2 * pad - R) // stride + 1
+    d.Q = (W + 2 * pad - S) // stride + 1
+    d.xs_n = d.xs_h = d.xs_w = d.xs_c = 0
+    return d
+
+
+def _krsc(w):
+    """Filter parameter [K,C,R,S] -> tensor whose storage is KRSC (no copy when already so)."""
+    if w.is_contiguous(memory_format=CL):
+        return w
+    return _raw_to_nhwc(w.detach())
+
+
+def _fprop(d, x, w, bias, act, slope):
+    y = _empty_nhwc(d.N, d.K, d.P, d.Q, x)
+    if y.numel() == 0:
+        return y
+    lib = _lib()
+    nb = lib.srgan_conv2d_workspace(d, 0, _engine)
+    ws = _workspace(x.device, nb) if nb else None
+    _call("srgan_conv2d_fprop", d, _p(x), _p(w), _p(bias), _p(y), act, slope, _engine, _p(ws), nb, _stream())
+    return y
+
+
+def _dgrad(d, dy, w, like):
+    dx = _empty_nhwc(d.N, d.C, d.H, d.W, like)
+    if dx.numel() == 0:
+        return dx
+    lib = _lib()
+    nb = lib.srgan_conv2d_workspace(d, 1, _engine)
+    ws = _workspace(dy.device, nb) if nb else None
+    _call("srgan_conv2d_dgrad", d, _p(dy), _p(w), _p(dx), _engine, _p(ws), nb, _stream())
+    return dx
+
+
+def _wgrad(d, x, dy, want_w, want_b):
+    dw = torch.empty((d.K, d.C, d.R, d.S), dtype=torch.float32, device=x.device, memory_format=CL) \
+        if want_w else None
+    db = torch.empty((d.K,), dtype=torch.float32, device=x.device) if want_b else None
+    if d.N == 0:
+        if dw is not None:
+            dw.zero_()
+        if db is not None:
+            db.zero_()
+        return dw, db
+    lib = _lib()
+    nb = lib.srgan_conv2d_workspace(d, 2, _engine)
+    ws = _workspace(x.device, nb) if nb else None
+    _call("srgan_conv2d_wgrad", d, _p(x), _p(dy), _p(dw), _p(db), _engine, _p(ws), nb, _stream())
+    return dw, db
+
+
+def _act_bwd(dy, y, act, slope):
+    if act == ACT_NONE:
+        return dy
+    dz = torch.empty_like(y)
+    _call("srgan_act_bwd", _p(dy), _p(y), _p(dz), y.numel(), act, slope, _stream())
+    return dz
+
+
+class _Conv2dFn(torch.autograd.Function):
+    """y = act(conv2d(x, w) + b); ref: nn.Conv2d (+LeakyReLU / Tanh that follow it), pyfiles/model.py."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act, slope):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        K, C2, R, S = weight.shape
+        if C2 != C:
+            raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
+        d = _desc(N, H, W, C, K, R, S, stride, pad)
+        y = _fprop(d, x, _krsc(weight), bias, act, slope)
+        ctx.d, ctx.act, ctx.slope = d, act, slope
+        ctx.weight, ctx.has_bias = weight, bias is not None
+        ctx.save_for_backward(x, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dz = _act_bwd(_raw_to_nhwc(dy), y, ctx.act, ctx.slope)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _dgrad(ctx.d, dz, _krsc(ctx.weight), x)       # live weight (see module docstring)
+        want_w = ctx.needs_input_grad[1]
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            dw, db = _wgrad(ctx.d, x, dz, want_w, want_b)
+        return dx, dw, db, None, None, None, None
+
+
+class _ConvTranspose2dFn(torch.autograd.Function):
+    """ref: nn.ConvTranspose2d pyfiles/model.py:227,230.  weight [Cin,Cout,R,S] stored channels-last is
+    exactly the KRSC filter of the mirrored convolution (K=Cin, C=Cout): forward = its dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        x = _raw_to_nhwc(x)
+        N, Cin, H, W = x.shape
+        Cin2, Cout, R, S = weight.shape
+        if Cin2 != Cin:
+            raise ValueError("conv_transpose2d: channel mismatch")
+        Ho = (H - 1) * stride - 2 * pad + R
+        Wo = (W - 1) * stride - 2 * pad + S
+        d = _desc(N, Ho, Wo, Cout, Cin, R, S, stride, pad)     # mirrored conv: (Ho,Wo,Cout) -> (H,W,Cin)
+        assert d.P == H and d.Q == W
+        y = _dgrad(d, x, _krsc(weight), x)
+        ctx.d, ctx.weight = d, weight
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _raw_to_nhwc(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _fprop(ctx.d, dy, _krsc(ctx.weight), None, ACT_NONE, 0.0)
+        if ctx.needs_input_grad[1]:
+            dw, _ = _wgrad(ctx.d, dy, x, True, False)
+        return dx, dw, None, None
+
+
+class _ReflectPadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        y = _empty_nhwc(N, C, H + 2 * pad, W + 2 * pad, x)
+        _call("srgan_reflect_pad_fwd", _p(x), _p(y), N, H, W, C, pad, _stream())
+        ctx.shape, ctx.pad = (N, C, H, W), pad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.shape
+        dy = _raw_to_nhwc(dy)
+        dx = _empty_nhwc(N, C, H, W, dy)
+        _call("srgan_reflect_pad_bwd", _p(dy), _p(dx), N, H, W, C, ctx.pad, _stream())
+        return dx, None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, padding_mode="zeros", act=ACT_NONE, slope=0.0):
+    _req(x, weight, bias)
+    if x.dim() != 4:
+        raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
+    if padding_mode == "reflect" and padding > 0:
+        x = _ReflectPadFn.apply(x, int(padding))
+        padding = 0
+    elif padding_mode not in ("zeros", "reflect"):
+        raise NotImplementedError("padding_mode %r" % (padding_mode,))
+    return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(act), float(slope))
+
+
+def conv_transpose2d(x, weight, stride=1, padding=0):
+    _req(x, weight)
+    return _ConvTranspose2dFn.apply(x, weight, int(stride), int(padding))
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x @ w.T + b as a 1x1 convolution over a [N,1,1,F] activation (ref: nn.Linear fcmean/fcvar/fcclass
+    pyfiles/model.py:395-396,455-457)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        N, F = x.shape
+        J = weight.shape[0]
+        d = _desc(N, 1, 1, F, J, 1, 1, 1, 0)
+        y = _fprop(d, x, weight.contiguous(), bias, ACT_NONE, 0.0).view(N, J)
+        ctx.d, ctx.weight, ctx.has_bias = d, weight, bias is not None
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        d = ctx.d
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _dgrad(d, dy, ctx.weight.contiguous(), x).view(d.N, d.C)
+        want_w = ctx.needs_input_grad[1]
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            dw, db = _wgrad(d, x, dy, want_w, want_b)
+            if dw is not None:
+                dw = dw.view(d.K, d.C)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    _req(x, weight, bias)
+    return _LinearFn.apply(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------- normalisation
+class _CondBiasFn(torch.autograd.Function):
+    """t = tanh(con @ W.T + b); ref: ConBias pyfiles/model.py:16-19,57."""
+
+    @staticmethod
+    def forward(ctx, con, weight, bias):
+        con = con.contiguous()
+        N, J = con.shape
+        C = weight.shape[0]
+        t = torch.empty((N, C), dtype=torch.float32, device=con.device)
+        if N:
+            _call("srgan_condbias_fwd", _p(con), _p(weight), _p(bias), _p(t), N, J, C, _stream())
+        ctx.weight = weight
+        ctx.save_for_backward(con, t)
+        return t
+
+    @staticmethod
+    def backward(ctx, dt):
+        con, t = ctx.saved_tensors
+        w = ctx.weight
+        N, J = con.shape
+        C = w.shape[0]
+        dt = dt.contiguous()
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.empty((C,), dtype=torch.float32, device=w.device) if ctx.needs_input_grad[2] else None
+        dcon = torch.empty_like(con) if ctx.needs_input_grad[0] else None
+        _call("srgan_condbias_bwd", _p(dt), _p(t), _p(con), _p(w), _p(dw), _p(db), _p(dcon), N, J, C, _stream())
+        return dcon, dw, db
+
+
+def cond_bias(con, weight, bias):
+    _req(con, weight, bias)
+    if not weight.is_contiguous():
+        raise SrganKernelError("cond_bias: weight must be contiguous")
+    return _CondBiasFn.apply(con, weight, bias)
+
+
+class _InstanceNormFn(torch.autograd.Function):
+    """y = act(((x-mean)*rstd + cbias) * gamma + beta) (+ residual).
+    ref: CBINorm2d.forward pyfiles/model.py:54-67, nn.InstanceNorm2d(affine=False) :178, ReLU/LeakyReLU/add."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, cbias, residual, eps, act, slope):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        if residual is not None:
+            residual = _raw_to_nhwc(residual)
+        if cbias is not None:
+            cbias = cbias.contiguous()
+        y = torch.empty_like(x)
+        mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        if x.numel():
+            _call("srgan_inorm_fwd", _p(x), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias),
+                  _p(residual), N, H * W, C, eps, act, slope, _stream())
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.act, ctx.slope = act, slope
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, mean, rstd, cbias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, cbias = ctx.saved_tensors
+        gamma, beta = ctx.gamma, ctx.beta
+        N, C, H, W = x.shape
+        dy = _raw_to_nhwc(dy)
+        dx = torch.empty_like(x)
+        s1 = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        s2 = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        if x.numel():
+            _call("srgan_inorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(dx),
+                  _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _stream())
+        dgamma = dbeta = dcb = None
+        need_g = gamma is not None and ctx.needs_input_grad[1]
+        need_b = beta is not None and ctx.needs_input_grad[2]
+        need_c = cbias is not None and ctx.needs_input_grad[3]
+        if need_g or need_b or need_c:
+            dgamma = torch.empty_like(gamma) if need_g else None
+            dbeta = torch.empty_like(beta) if need_b else None
+            dcb = torch.empty_like(cbias) if need_c else None
+            _call("srgan_inorm_param_grads", _p(s1), _p(s2), _p(gamma), _p(cbias), _p(dgamma), _p(dbeta), _p(dcb),
+                  N, C, _stream())
+        dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
+        return (dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, dcb, dres, None, None, None
+
+
+def instance_norm_act(x, gamma=None, beta=None, cbias=None, residual=None, eps=1e-5, act=ACT_NONE, slope=0.0):
+    _req(x, gamma, beta, cbias, residual)
+    if x.dim() != 4:
+        raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
+    if x.shape[1] % 8:
+        raise SrganKernelError("instance_norm_act: channel count must be a multiple of 8 (got %d)" % x.shape[1])
+    if residual is not None and act != ACT_NONE:
+        raise ValueError("residual add is only fused with act=none")
+    return _InstanceNormFn.apply(x, gamma, beta, cbias, residual, float(eps), int(act), float(slope))
+
+
+# ----------------------------------------------------------------------------- pooling
+def _pool_fn(fwd_name, bwd_name, out_hw):
+    class _Pool(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            x = _raw_to_nhwc(x)
+            N, C, H, W = x.shape
+            P, Q = out_hw(H, W)
+            y = _empty_nhwc(N, C, P, Q, x)
+            if y.numel():
+                _call(fwd_name, _p(x), _p(y), N, H, W, C, _stream())
+            ctx.shape = (N, C, H, W)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            N, C, H, W = ctx.shape
+            dy = _raw_to_nhwc(dy)
+            dx = _empty_nhwc(N, C, H, W, dy)
+            if dx.numel():
+                _call(bwd_name, _p(dy), _p(dx), N, H, W, C, _stream())
+            return dx
+    return _Pool
+
+
+_AvgPool2 = _pool_fn("srgan_avgpool2_fwd", "srgan_avgpool2_bwd", lambda H, W: (H // 2, W // 2))
+_AvgPool3s2 = _pool_fn("srgan_avgpool3s2_fwd", "srgan_avgpool3s2_bwd",
+                       lambda H, W: ((H - 1) // 2 + 1, (W - 1) // 2 + 1))
+
+
+def avg_pool2(x):
+    """nn.AvgPool2d(2, 2); ref pyfiles/model.py:365,368,426,429."""
+    _req(x)
+    return _AvgPool2.apply(x)
+
+
+def avg_pool3s2(x):
+    """nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False); ref pyfiles/model.py:286,324."""
+    _req(x)
+    return _AvgPool3s2.apply(x)
+
+
+class _AvgPool2AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _raw_to_nhwc(a), _raw_to_nhwc(b)
+        N, C, H, W = a.shape
+        y = torch.empty_like(b)
+        if tuple(b.shape) != (N, C, H // 2, W // 2):
+            raise ValueError("avg_pool2_add: shape mismatch")
+        if y.numel():
+            _call("srgan_avgpool2_add_fwd", _p(a), _p(b), _p(y), N, H, W, C, _stream())
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.shape
+        dy = _raw_to_nhwc(dy)
+        da = None
+        if ctx.needs_input_grad[0]:
+            da = _empty_nhwc(N, C, H, W, dy)
+            if da.numel():
+                _call("srgan_avgpool2_bwd", _p(dy), _p(da), N, H, W, C, _stream())
+        return da, (dy if ctx.needs_input_grad[1] else None)
+
+
+def avg_pool2_add(a, b):
+    """avgpool2(a) + b -- tail of the encoder block (ref pyfiles/model.py:374-375,435-436)."""
+    _req(a, b)
+    return _AvgPool2AddFn.apply(a, b)
+
+
+class _LReluGapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        f = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        if f.numel():
+            _call("srgan_lrelu_gap_fwd", _p(x), _p(f), N, H * W, C, slope, _stream())
+        ctx.slope = slope
+        ctx.save_for_backward(x)
+        return f
+
+    @staticmethod
+    def backward(ctx, df):
+        (x,) = ctx.saved_tensors
+        N, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        if dx.numel():
+            _call("srgan_lrelu_gap_bwd", _p(df.contiguous()), _p(x), _p(dx), N, H * W, C, ctx.slope, _stream())
+        return dx, None
+
+
+def lrelu_gap(x, slope=0.2):
+    """LeakyReLU(slope) then AdaptiveAvgPool2d(1), flattened to [N,C]; ref pyfiles/model.py:394,454."""
+    _req(x)
+    return _LReluGapFn.apply(x, float(slope))
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        if a.dim() == 4:
+            a, b = _raw_to_nhwc(a), _raw_to_nhwc(b)
+        else:
+            a, b = a.contiguous(), b.contiguous()
+        y = torch.empty_like(a)
+        if y.numel():
+            _call("srgan_add", _p(a), _p(b), _p(y), y.numel(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    _req(a, b)
+    if a.shape != b.shape:
+        raise ValueError("add: shape mismatch")
+    return _AddFn.apply(a, b)
+
+
+# ----------------------------------------------------------------------------- heads
+class _SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, J = x.shape
+        y = torch.empty_like(x)
+        if N:
+            _call("srgan_softmax_fwd", _p(x), _p(y), N, J, _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        N, J = y.shape
+        dx = torch.empty_like(y)
+        if N:
+            _call("srgan_softmax_bwd", _p(dy.contiguous()), _p(y), _p(dx), N, J, _stream())
+        return dx
+
+
+def softmax_rows(x):
+    """softmax over dim 1 of a [N,J] tensor; ref: nn.Softmax() (implicit dim=1) pyfiles/model.py:333-334."""
+    _req(x)
+    return _SoftmaxFn.apply(x)
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        mu, logvar, eps = mu.contiguous(), logvar.contiguous(), eps.contiguous()
+        z = torch.empty_like(mu)
+        if z.numel():
+            _call("srgan_reparam_fwd", _p(mu), _p(logvar), _p(eps), _p(z), z.numel(), _stream())
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        logvar, eps = ctx.saved_tensors
+        dz = dz.contiguous()
+        dmu = torch.empty_like(dz) if ctx.needs_input_grad[0] else None
+        dlv = torch.empty_like(dz) if ctx.needs_input_grad[1] else None
+        if dz.numel():
+            _call("srgan_reparam_bwd", _p(dz), _p(logvar), _p(eps), _p(dmu), _p(dlv), dz.numel(), _stream())
+        return dmu, dlv, None
+
+
+def reparametrize(mu, logvar, eps):
+    """z = eps * exp(0.5*logvar) + mu; ref pyfiles/model.py:398-402,459-463."""
+    _req(mu, logvar, eps)
+    return _ReparamFn.apply(mu, logvar, eps)
+
+
+# ----------------------------------------------------------------------------- losses
+def _same_layout(a, b):
+    """Bring two same-shape tensors to one dense storage order (channels-last for 4-D)."""
+    if a.dim() == 4:
+        return _raw_to_nhwc(a), _raw_to_nhwc(b)
+    return a.contiguous(), b.contiguous()
+
+
+class _L1MeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _same_layout(a, b)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        _call("srgan_l1_mean_fwd", _p(a), _p(b), a.numel(), _p(out), _p(_red_scratch(a.device)), _stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        _call("srgan_l1_mean_bwd", _p(a), _p(b), _p(g.contiguous()), _p(da), _p(db), a.numel(), _stream())
+        return da, db
+
+
+def l1_mean(a, b):
+    """torch.mean(torch.abs(a - b)); ref pyfiles/util_notebook.py:295,309,348,359,625,639,676,686."""
+    _req(a, b)
+    if a.shape != b.shape:
+        raise ValueError("l1_mean: shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+    return _L1MeanFn.apply(a, b)
+
+
+class _MseConstFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        x = _raw_to_nhwc(x) if x.dim() == 4 else x.contiguous()
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        _call("srgan_mse_const_fwd", _p(x), target, x.numel(), _p(out), _p(_red_scratch(x.device)), _stream())
+        ctx.target = target
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        _call("srgan_mse_const_bwd", _p(x), ctx.target, _p(g.contiguous()), _p(dx), x.numel(), _stream())
+        return dx, None
+
+
+def mse_const(x, target):
+    """nn.MSELoss()(x, full_like(x, target)); ref get_loss_D pyfiles/util.py:457-462."""
+    _req(x)
+    return _MseConstFn.apply(x, float(target))
+
+
+class _MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _same_layout(a, b)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        _call("srgan_mse_fwd", _p(a), _p(b), a.numel(), _p(out), _p(_red_scratch(a.device)), _stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        _call("srgan_mse_bwd", _p(a), _p(b), _p(g.contiguous()), _p(da), _p(db), a.numel(), _stream())
+        return da, db
+
+
+def mse(a, b):
+    """nn.MSELoss()(a, b); ref get_domainloss_D pyfiles/util.py:464-468."""
+    _req(a, b)
+    if a.shape != b.shape:
+        raise ValueError("mse: shape mismatch")
+    return _MseFn.apply(a, b)
+
+
+# ----------------------------------------------------------------------------- latent batch losses
+LAT_BKL, LAT_CORR, LAT_HIST, LAT_KL = 1, 2, 4, 8
+
+
+def latent_out_floats(D, bins):
+    return 4 + 4 * D + D * D + D * bins
+
+
+def latent_stats_views(out, D, bins):
+    """Named views into the statistics blob written by the latent-loss kernel."""
+    o = 4
+    v = {}
+    for name, n in (("mean", D), ("var", D), ("cdiag", D), ("corr", D * D), ("hist", D * bins), ("hsum", D)):
+        v[name] = out[o:o + n]
+        o += n
+    v["corr"] = v["corr"].view(D, D)
+    v["hist"] = v["hist"].view(D, bins)
+    return v
+
+
+class _LatentLossFn(torch.autograd.Function):
+    """[batch-KL, corr, hist, KL] of a latent batch; see srgan_latent_losses_fwd in the header.
+    `mu_all` (optional, no grad) is the all-gathered global batch whose rows [row0,row0+n_local) are `mu`."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, mu_all, logvar_all, row0, n_cfg, target, bins, hmin, hmax, sigma, flags):
+        mu = mu.contiguous()
+        full = mu if mu_all is None else mu_all.contiguous()
+        lv_full = None
+        if flags & LAT_KL:
+            lv_full = (logvar if logvar_all is None else logvar_all).contiguous()
+        n, D = full.shape
+        out = torch.empty((latent_out_floats(D, bins),), dtype=torch.float32, device=mu.device)
+        _call("srgan_latent_losses_fwd", _p(full), _p(lv_full), n, D, n_cfg, _p(target), bins, hmin, hmax, sigma,
+              flags, _p(out), _stream())
+        ctx.cfg = (n, D, n_cfg, bins, hmin, hmax, sigma, flags, row0, mu.shape[0])
+        ctx.save_for_backward(full, lv_full, target, out)
+        ctx.mark_non_differentiable(out)
+        return out[:4].clone(), out
+
+    @staticmethod
+    def backward(ctx, g4, _gout):
+        full, lv_full, target, out = ctx.saved_tensors
+        n, D, n_cfg, bins, hmin, hmax, sigma, flags, row0, rows = ctx.cfg
+        dmu = torch.empty((rows, D), dtype=torch.float32, device=full.device)
+        dlv = torch.empty((rows, D), dtype=torch.float32, device=full.device) \
+            if (flags & LAT_KL) and ctx.needs_input_grad[1] else None
+        _call("srgan_latent_losses_bwd", _p(full), _p(lv_full), n, D, n_cfg, _p(target), bins, hmin, hmax, sigma,
+              flags, _p(out), _p(g4.contiguous()), _p(dmu), _p(dlv), row0, rows, _stream())
+        return (dmu,) + (dlv,) + (None,) * 10
+
+
+def latent_losses(mu, logvar=None, n_cfg=2.0, target=None, bins=50, hmin=-10.0, hmax=10.0, sigma=0.2,
+                  flags=LAT_BKL | LAT_CORR | LAT_HIST, mu_all=None, logvar_all=None, row0=0):
+    """Returns (losses[4] = [batch-KL, corr, hist, KL], stats blob)."""
+    _req(mu, logvar, target, mu_all, logvar_all)
+    if (flags & LAT_HIST) and target is None:
+        raise ValueError("latent_losses: the histogram term needs a target")
+    if not (flags & LAT_HIST):
+        bins = 1
+    return _LatentLossFn.apply(mu, logvar, mu_all, logvar_all, int(row0), float(n_cfg), target, int(bins),
+                               float(hmin), float(hmax), float(sigma), int(flags))
+
+
+class _CorrcoefFn(torch.autograd.Function):
+    """corrcoef of the ROWS of x [D, n] (np.corrcoef convention); ref pyfiles/util.py:470-511."""
+
+    @staticmethod
+    def forward(ctx, x):
+        mu = x.t().contiguous()            # kernel layout: [n samples][D]
+        n, D = mu.shape
+        out = torch.empty((latent_out_floats(D, 1),), dtype=torch.float32, device=x.device)
+        _call("srgan_latent_losses_fwd", _p(mu), None, n, D, 2.0, None, 1, 0.0, 1.0, 1.0, LAT_CORR, _p(out),
+              _stream())
+        ctx.save_for_backward(mu, out)
+        return latent_stats_views(out, D, 1)["corr"].clone()
+
+    @staticmethod
+    def backward(ctx, dc):
+        mu, out = ctx.saved_tensors
+        n, D = mu.shape
+        dmu = torch.empty_like(mu)
+        _call("srgan_corrcoef_bwd", _p(mu), n, D, _p(out), _p(dc.contiguous()), _p(dmu), _stream())
+        return dmu.t()
+
+
+def corrcoef(x):
+    _req(x)
+    if x.dim() != 2:
+        raise ValueError("corrcoef expects a 2D tensor")
+    return _CorrcoefFn.apply(x)
+
+
+class _SoftHistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bins, hmin, hmax, sigma):
+        x = x.contiguous()
+        h = torch.empty((bins,), dtype=torch.float32, device=x.device)
+        _call("srgan_softhist_fwd", _p(x), x.numel(), bins, hmin, hmax, sigma, _p(h), _stream())
+        ctx.cfg = (bins, hmin, hmax, sigma)
+        ctx.save_for_backward(x)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        (x,) = ctx.saved_tensors
+        bins, hmin, hmax, sigma = ctx.cfg
+        dx = torch.empty_like(x)
+        _call("srgan_softhist_bwd", _p(x), _p(dh.contiguous()), x.numel(), bins, hmin, hmax, sigma, _p(dx),
+              _stream())
+        return dx, None, None, None, None
+
+
+def soft_histogram(x, bins, hmin, hmax, sigma):
+    """Gaussian-kernel soft histogram of a vector; ref GaussianHistogram.forward pyfiles/util.py:532-537."""
+    _req(x)
+    if x.dim() != 1:
+        raise ValueError("soft_histogram expects a 1D tensor")
+    return _SoftHistFn.apply(x, int(bins), float(hmin), float(hmax), float(sigma))
+
+
+# ----------------------------------------------------------------------------- optimizer
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (ref: optim.Adam(..., betas=(0.5, 0.999)) pyfiles/util_notebook.py:117-131,
+    500-507) with one kernel launch per parameter group: parameters, gradients and both moments of a
+    group live in flat buffers; `p.data` / `p.grad` are re-pointed at views of them."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._flat = {}
+
+    def _flatten(self, gi, group):
+        ps = [p for p in group["params"] if p.requires_grad]
+        if not ps:
+            return None
+        _req(*ps)
+        n = sum(p.numel() for p in ps)
+        dev = ps[0].device
+        fp = torch.empty(n, dtype=torch.float32, device=dev)
+        fg = torch.zeros(n, dtype=torch.float32, device=dev)
+        views = []
+        o = 0
+        for p in ps:
+            k = p.numel()
+            cl = p.dim() == 4 and p.is_contiguous(memory_format=CL) and not p.is_contiguous()
+            shape = tuple(p.shape)
+
+            def view(flat, o=o, k=k, cl=cl, shape=shape):
+                if cl:
+                    K, C, R, S = shape
+                    return flat[o:o + k].view(K, R, S, C).permute(0, 3, 1, 2)
+                return flat[o:o + k].view(shape)
+            if not (cl or p.is_contiguous()):
+                raise SrganKernelError("FusedAdam: parameters must be dense")
+            with torch.no_grad():
+                view(fp).copy_(p.data)
+                if p.grad is not None:
+                    view(fg).copy_(p.grad)
+            p.data = view(fp)
+            p.grad = view(fg)
+            views.append((p, view))
+            o += k
+        st = dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), step=0, views=views, params=ps)
+        self._flat[gi] = st
+        return st
+
+    def flat_grads(self):
+        """Flat gradient buffers (one per group) -- what a data-parallel caller all-reduces."""
+        out = []
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            if st is not None:
+                out.append(st["g"])
+        return out
+
+    def zero_grad(self, set_to_none=False):
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            if st is None:
+                continue
+            st["g"].zero_()
+            for p, view in st["views"]:
+                p.grad = view(st["g"])
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            if st is None:
+                continue
+            # gradients written by autograd into fresh tensors (p.grad re-assigned) are folded back
+            for p, view in st["views"]:
+                gv = view(st["g"])
+                if p.grad is None:
+                    gv.zero_()
+                elif p.grad.data_ptr() != gv.data_ptr():
+                    gv.copy_(p.grad)
+                    p.grad = gv
+            st["step"] += 1
+            b1, b2 = group["betas"]
+            _call("srgan_adam_step", _p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
+                  group["lr"], b1, b2, group["eps"], st["step"], _stream())

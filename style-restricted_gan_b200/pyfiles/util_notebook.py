@@ -1,0 +1,494 @@
+"""Training-step drivers of SingleGAN (notebooks 01/02) and Style-Restricted GAN (notebooks 03/05).
+
+Drop-in for the reference's `pyfiles/util_notebook.py`: `SingleGAN_training` / `SRGAN_training` keep their
+constructor signatures, attributes (`G, D, E, optG/D/E, scheG/D/E, lbd, k, n_batch, hi, target_image,
+c_rand, ...`) and methods (`opt_sche_initialization, G_transformation, update_D, update_GandE,
+UnrolledUpdate, train`), and `train()` returns `[errG, errD, errE]` as 0-dim tensors.
+
+The step is the reference's algorithm (ref pyfiles/util_notebook.py:28-734), including the behaviours that
+are easy to "fix" by accident:
+  * the discriminator really takes `k` Adam steps per `train()` -- the reference's Unrolled-GAN roll-back
+    loads a state_dict that aliases the live parameters, i.e. it is a no-op (ref :721,727);
+  * `corr_enc` and `hist` are only evaluated when `batch_KL > 0` (ref :644-662);
+  * batch-KL scales the unbiased variance by n_batch/(n_batch-1) once more, with n_batch the configured
+    batch size (ref :646);
+  * phase 2 (`errG_ex`) back-propagates through the generator graph built in `update_D` AFTER
+    `optG.step()` changed the weights in place: gradients use the new weights with the old activations
+    (torch-1.4 semantics, see srgan_ops docstring);
+  * all noise (z, eps) is drawn from the CPU default generator (ref :179,554; model.py:400,461).
+
+New here: one-process-per-GPU data parallelism.  When `torch.distributed` is initialised every rank holds a
+replica, works on its slice of the global batch, gradients are all-reduced (mean) after each backward, and
+the latent batch statistics are computed on the ALL-GATHERED mu so batch-KL / correlation / histogram
+losses equal their single-GPU global-batch values bit for bit.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import srgan_ops as ops
+from util import *  # noqa: F401,F403
+
+
+def get_adjustable_parameters(notebook_no=1):
+    """The hyper-parameter table notebook 01 iterates over (the other notebooks have none)."""
+    if notebook_no != 1:
+        return None
+    import pandas as pd
+    rows = [["conventionalKL", 1, 0], ["preposedKL", 1, 0], ["preposedKL", 5, 0.5]]
+    return pd.DataFrame(np.array(rows), columns=["restriction_type", "unrolled_k", "idt_reg"])
+
+
+# ------------------------------------------------------------------------------------------- data parallel
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _allreduce_mean_(t):
+    """In-place mean over ranks of a dense tensor."""
+    _, world = _world()
+    if world == 1:
+        return t
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(world)
+    return t
+
+
+def _sync_grads(module, optimizer=None):
+    """All-reduce (mean) the gradients of `module`: one collective over a flat buffer."""
+    _, world = _world()
+    if world == 1:
+        return
+    flat_bufs = None
+    if isinstance(optimizer, ops.FusedAdam):
+        grads = [p.grad for p in module.parameters() if p.grad is not None]
+        bufs = optimizer.flat_grads()
+        # only usable when the gradients already live in the optimizer's flat buffers
+        if grads and all(any(g.untyped_storage().data_ptr() == b.untyped_storage().data_ptr() for b in bufs)
+                         for g in grads):
+            flat_bufs = bufs
+    if flat_bufs is not None:
+        for b in flat_bufs:
+            _allreduce_mean_(b)
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) if g.is_contiguous() else g.contiguous(memory_format=torch.channels_last)
+                      .permute(0, 2, 3, 1).reshape(-1) for g in grads])
+    _allreduce_mean_(flat)
+    o = 0
+    for g in grads:
+        n = g.numel()
+        if g.is_contiguous():
+            g.copy_(flat[o:o + n].view_as(g))
+        else:
+            K, C, R, S = g.shape
+            g.copy_(flat[o:o + n].view(K, R, S, C).permute(0, 3, 1, 2))
+        o += n
+
+
+def _unwrap(net):
+    """The notebooks hand over nn.DataParallel wrappers; compute runs on the wrapped module."""
+    return net.module if isinstance(net, torch.nn.DataParallel) else net
+
+
+class _EncodedStyle(list):
+    """`[latent, mu, logvar, ...]` exactly as the reference returns it (a plain list subclass)."""
+
+
+# ------------------------------------------------------------------------------------------- shared engine
+class _UnrolledTrainer(object):
+    """Machinery shared by both trainers.  Subclasses define how the encoder and discriminator are called."""
+
+    # ---- construction -------------------------------------------------------------------------------
+    def _common_init(self, net, opt, criterion, lbd, unrolled_k, device, ref_label, batch_size,
+                     encoded_feature, ndim):
+        # nn.DataParallel wrappers (the notebooks pass them) stay visible as sg.G / sg.D / sg.E -- the notebooks
+        # save `sg.G.module.state_dict()` -- but compute runs on the wrapped modules: parallelism here is one
+        # process per GPU over torch.distributed, not single-process scatter/gather.
+        self._nG, self._nE = _unwrap(self.G), _unwrap(self.E)
+        self._nD = [_unwrap(d) for d in self.D] if isinstance(self.D, (list, tuple)) else _unwrap(self.D)
+        self.optG, self.optD, self.optE = opt[0], opt[1], opt[2]
+        self.scheG, self.scheD, self.scheE = None, None, None
+        self.criterion, self.criterion_class = criterion
+        self.lbd = lbd
+        self.k = unrolled_k
+        self.device = device
+        self.ref_label = ref_label
+        self.n_batch = batch_size
+        self.encoded_feature = encoded_feature
+        self.ndim = ndim
+        self.source_image = None
+        self.target_image = None
+        self.recon_image = None
+        self.label = None
+        self.c_rand = None
+        self.enc_info = None
+        self.target_cenc = None
+        if lbd["hist"] > 0:
+            self.hi = histogram_imitation(device)
+
+    @staticmethod
+    def _adam(module, lr):
+        return ops.FusedAdam(module.parameters(), lr=lr, betas=(0.5, 0.999))
+
+    @staticmethod
+    def _sched(optimizer):
+        return torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=0.95)
+
+    # ---- small helpers --------------------------------------------------------------------------------
+    def _onehot(self, label):
+        return class_encode(label, self.device, self.ref_label)
+
+    def _style_of(self, info):
+        if self.encoded_feature == "latent":
+            return info[0]
+        if self.encoded_feature == "mu":
+            return info[1]
+        raise ValueError("encoded_feature must be 'latent' or 'mu'")
+
+    def _generate(self, label, image, style):
+        cond = torch.cat([self._onehot(label), style], 1)
+        return self._nG(image, cond)
+
+    def G_transformation(self, target_label, source_image, encoder=False, ref_image=None):
+        """Translate `source_image` to `target_label`.  Style = encoder output of `ref_image` when `encoder`,
+        else fresh N(0,1) noise.  Returns (image, info): info is [latent, mu, logvar(, ...)] or the noise."""
+        if encoder:
+            info = self._encode(ref_image, target_label)
+            style = self._style_of(info)
+        else:
+            style = ops.host_normal(source_image.shape[0], self.ndim, self.device)
+            info = style
+        return self._generate(target_label, source_image, style), info
+
+    def _latent_restriction(self, info):
+        """KL / batch-KL / correlation / histogram terms (already weighted by their lambdas) on the encoder
+        output of the source batch, all from ONE fused kernel.  ref :299-332 / :629-662."""
+        lbd = self.lbd
+        flags = 0
+        if lbd["KL"] > 0:
+            flags |= ops.LAT_KL
+        if lbd["batch_KL"] > 0:
+            flags |= ops.LAT_BKL
+            if lbd["corr_enc"] > 0:
+                flags |= ops.LAT_CORR
+            if lbd["hist"] > 0:
+                flags |= ops.LAT_HIST
+        if not flags:
+            return {}
+        mu, logvar = info[1], info[2]
+        rank, world = _world()
+        mu_all = lv_all = None
+        if world > 1:
+            # the statistics are those of the global batch: gather mu (B_global x ndim floats)
+            mu_all = torch.empty((mu.shape[0] * world, mu.shape[1]), dtype=mu.dtype, device=mu.device)
+            dist.all_gather_into_tensor(mu_all, mu.detach().contiguous())
+            if flags & ops.LAT_KL:
+                lv_all = torch.empty_like(mu_all)
+                dist.all_gather_into_tensor(lv_all, logvar.detach().contiguous())
+        hi = getattr(self, "hi", None)
+        kw = {}
+        if flags & ops.LAT_HIST:
+            g = hi.gausshist
+            kw = dict(target=hi.target, bins=g.bins, hmin=g.min, hmax=g.max, sigma=g.sigma)
+        losses, _ = ops.latent_losses(mu, logvar if flags & ops.LAT_KL else None, n_cfg=self.n_batch, flags=flags,
+                                      mu_all=mu_all, logvar_all=lv_all, row0=rank * mu.shape[0], **kw)
+        terms = {}
+        if flags & ops.LAT_KL:
+            terms["KL"] = losses[3] * lbd["KL"]
+        if flags & ops.LAT_BKL:
+            terms["batch_KL"] = losses[0] * lbd["batch_KL"]
+        if flags & ops.LAT_CORR:
+            terms["corr_enc"] = losses[1] * lbd["corr_enc"]
+        if flags & ops.LAT_HIST:
+            terms["hist"] = losses[2] * lbd["hist"]
+        return terms
+
+    # ---- the step --------------------------------------------------------------------------------------
+    def update_GandE(self):
+        """Phase 1: one step of G and E on the SingleGAN losses; phase 2: one more step of G alone on the
+        latent-regression losses.  Returns [errG, errE_output]."""
+        lbd = self.lbd
+        src, lab = self.source_image, self.label
+        self._nG.zero_grad()
+        self._nE.zero_grad()
+
+        recon_image, enc_info = self.G_transformation(lab["source"], self.target_image, True, src)
+        errG = self._fool_D(self.target_image, lab["target"])
+        cyc = ops.l1_mean(src, recon_image)
+        errG = errG + cyc * lbd["cycle"]
+        errE_output = cyc * lbd["cycle"]
+
+        # The restriction terms do not touch the RNG, so evaluating them in one fused launch here (after the
+        # identity pass) is equivalent to the reference's interleaving; they are ADDED in the reference's order.
+        if lbd["idt"] > 0:
+            identity_image, _ = self.G_transformation(lab["source"], src, True, src)
+            idt = ops.l1_mean(src, identity_image)
+            errG = errG + idt * lbd["idt"]
+        terms = self._latent_restriction(enc_info)
+        errE = 0
+        if "KL" in terms:
+            errE = errE + terms["KL"]
+            errE_output = errE_output + terms["KL"]
+        if lbd["idt"] > 0:
+            errE_output = errE_output + idt * lbd["idt"]
+        for key in ("batch_KL", "corr_enc", "hist"):
+            if key in terms:
+                errE = errE + terms[key]
+                errE_output = errE_output + terms[key]
+        _, world = _world()
+        # Every rank evaluates the GLOBAL restriction loss but differentiates only its own rows: those
+        # gradients must be summed over ranks while _sync_grads averages -> pre-scale by the world size.
+        restrict_bp = errE * world if (world > 1 and torch.is_tensor(errE)) else errE
+
+        errG.backward(retain_graph=True)
+        if torch.is_tensor(restrict_bp):
+            restrict_bp.backward(retain_graph=True)
+        _sync_grads(self._nG, self.optG)
+        _sync_grads(self._nE, self.optE)
+        self.optG.step()
+        self.optE.step()
+        hook = getattr(self, "_after_phase1", None)     # test hook (teacher forcing of the post-step weights)
+        if hook is not None:
+            hook(self)
+
+        # ---- phase 2: G only (E receives gradients but is not stepped) ----
+        self._nG.zero_grad()
+        self._nE.zero_grad()
+        target_mu = self._encode(self.target_image, lab["target"])[1]
+        errG_ex = ops.l1_mean(self.c_rand, target_mu) * lbd["reg"]
+        if lbd["idt_reg"] * lbd["idt"] > 0:
+            errG_ex = errG_ex + self._identity_regression() * lbd["idt_reg"] * (lbd["idt"] / lbd["cycle"])
+        errG_ex.backward()
+        _sync_grads(self._nG, self.optG)
+        self.optG.step()
+        return [errG + errG_ex, errE_output]
+
+    def train(self, source_image, label):
+        self.source_image = ops.to_nhwc(source_image)
+        self.label = label
+        return self.UnrolledUpdate()
+
+    def _report(self, errs):
+        """Average the reported scalars over ranks so they equal the global-batch values."""
+        _, world = _world()
+        if world == 1:
+            return errs
+        out = []
+        for e in errs:
+            if torch.is_tensor(e):
+                e = _allreduce_mean_(e.detach().clone())
+            out.append(e)
+        return out
+
+
+# ------------------------------------------------------------------------------------------- SingleGAN (nb 01/02)
+class SingleGAN_training(_UnrolledTrainer):
+    """SingleGAN with a class-conditioned encoder `E(image, onehot)`; `singleD=False` uses one patch
+    discriminator per class, fed the samples of that class only.  ref pyfiles/util_notebook.py:28-417."""
+
+    def __init__(self, net, opt, criterion, lbd, unrolled_k, device, ref_label, ndim,
+                 classes, batch_size=64, encoded_feature="latent", singleD=False):
+        self.G, self.D, self.E = net[0], net[1], net[2]
+        self._common_init(net, opt, criterion, lbd, unrolled_k, device, ref_label, batch_size, encoded_feature,
+                          ndim)
+        self.classes = classes
+        self.singleD = singleD
+
+    def opt_sche_initialization(self, lr=[0.0001, 0.0001, 0.0001]):
+        lr_G, lr_D, lr_E = lr
+        if self.optG is None:
+            self.optG = self._adam(self._nG, lr_G)
+        self.scheG = self._sched(self.optG)
+        if self.singleD:
+            if self.optD is None:
+                self.optD = self._adam(self._nD, lr_D)
+            self.scheD = self._sched(self.optD)
+        else:
+            self.optD = [self._adam(self._nD[i], lr_D) for i in self.classes]
+            self.scheD = [self._sched(o) for o in self.optD]
+        if self.optE is None:
+            self.optE = self._adam(self._nE, lr_E)
+        self.scheE = self._sched(self.optE)
+
+    def _encode(self, image, label):
+        return _EncodedStyle(self._nE(image, self._onehot(label)))
+
+    def _class_mask(self, which, i):
+        return torch.as_tensor(self.label[which]).to(self.device) == i
+
+    def _fool_D(self, fake, fake_label):
+        if self.singleD:
+            output, output_class = self._nD(fake)
+            return get_loss_D(output, 1., self.criterion, self.device) + \
+                get_domainloss_D(output_class, self._onehot(fake_label), self.criterion_class) * self.lbd["class"]
+        err = 0
+        for i in self.classes:
+            sub = fake[self._class_mask("target", i)]
+            if sub.shape[0] != 0:
+                err = err + get_loss_D(self._nD[i](sub), 1., self.criterion, self.device) / len(self.classes)
+        return err
+
+    def update_D(self, keep_graph=True):
+        with torch.set_grad_enabled(keep_graph):
+            self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
+        fake = self.target_image.detach()
+        if self.singleD:
+            self._nD.zero_grad()
+            output, output_class = self._nD(self.source_image)
+            errD = get_loss_D(output, 1., self.criterion, self.device) + \
+                get_domainloss_D(output_class, self._onehot(self.label["source"]), self.criterion_class) \
+                * self.lbd["class"]
+            output, _ = self._nD(fake)
+            errD = errD + get_loss_D(output, 0., self.criterion, self.device)
+            errD.backward()
+            _sync_grads(self._nD, self.optD)
+            self.optD.step()
+            return errD
+        # one discriminator per class; like the reference, the LAST class's loss is what gets returned
+        for i in self.classes:
+            errD = 0
+            self._nD[i].zero_grad()
+            real = self.source_image[self._class_mask("source", i)]
+            if real.shape[0] != 0:
+                errD = errD + get_loss_D(self._nD[i](real), 1., self.criterion, self.device)
+            sub = fake[self._class_mask("target", i)]
+            if sub.shape[0] != 0:
+                errD = errD + get_loss_D(self._nD[i](sub), 0., self.criterion, self.device)
+            if torch.is_tensor(errD):
+                errD.backward()
+            self.optD[i].step()
+        return errD
+
+    def _identity_regression(self):
+        image, z = self.G_transformation(self.label["source"], self.source_image, False)
+        mu = self._encode(image, self.label["source"])[1]
+        return ops.l1_mean(z, mu)
+
+    def UnrolledUpdate(self):
+        for i in range(self.k):
+            errD = self.update_D(keep_graph=(i == self.k - 1))
+            if i == 0:
+                errorD = errD
+                # (the reference snapshots D.state_dict() here and reloads it below; the snapshot aliases the
+                #  live parameters, so nothing is rolled back -- reproduced by doing nothing)
+        errorG, errorE = self.update_GandE()
+        return self._report([errorG, errorD, errorE])
+
+
+# ------------------------------------------------------------------------------------------- SRGAN (nb 03/05)
+class SRGAN_training(_UnrolledTrainer):
+    """Style-Restricted GAN: unconditional encoder `E(image) -> (z, mu, logvar, class_logits, None)`, one
+    discriminator with patch + class heads.  ref pyfiles/util_notebook.py:419-734."""
+
+    def __init__(self, net, opt, criterion, lbd, unrolled_k, device, ref_label,
+                 batch_size=64, encoded_feature="latent", ndim=8):
+        self.G, self.D, self.E = net[0].to(device), net[1].to(device), net[2].to(device)
+        self._common_init(net, opt, criterion, lbd, unrolled_k, device, ref_label, batch_size, encoded_feature,
+                          ndim)
+
+    def opt_sche_initialization(self, lr=[0.0001, 0.0001, 0.0001]):
+        lr_G, lr_D, lr_E = lr
+        if self.optG is None:
+            self.optG = self._adam(self._nG, lr_G)
+        self.scheG = self._sched(self.optG)
+        if self.optD is None:
+            self.optD = self._adam(self._nD, lr_D)
+        self.scheD = self._sched(self.optD)
+        if self.optE is None:
+            self.optE = self._adam(self._nE, lr_E)
+        self.scheE = self._sched(self.optE)
+
+    def _encode(self, image, label=None):
+        return _EncodedStyle(self._nE(image))
+
+    def _fool_D(self, fake, fake_label):
+        output, output_class = self._nD(fake)
+        return get_loss_D(output, 1., self.criterion, self.device) + \
+            get_domainloss_D(output_class, self._onehot(fake_label), self.criterion_class) * self.lbd["class"]
+
+    def update_D(self, keep_graph=True):
+        self._nD.zero_grad()
+        with torch.set_grad_enabled(keep_graph):
+            self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
+        output, output_class = self._nD(self.source_image)
+        errD = get_loss_D(output, 1., self.criterion, self.device) + \
+            get_domainloss_D(output_class, self._onehot(self.label["source"]), self.criterion_class) \
+            * self.lbd["class"]
+        output, _ = self._nD(self.target_image.detach())
+        errD = errD + get_loss_D(output, 0., self.criterion, self.device)
+        errD.backward()
+        _sync_grads(self._nD, self.optD)
+        self.optD.step()
+        return errD
+
+    def _identity_regression(self):
+        image, info = self.G_transformation(self.label["source"], self.source_image, True, self.source_image)
+        mu = self._encode(image)[1]
+        return ops.l1_mean(info[1], mu)
+
+    def UnrolledUpdate(self):
+        for i in range(self.k):
+            errD = self.update_D(keep_graph=(i == self.k - 1))
+            if i == 0:
+                errorD = errD       # (state_dict snapshot / reload of the reference is an aliasing no-op)
+        errorG, errorE = self.update_GandE()
+        return self._report([errorG, errorD, errorE])
+
+
+# ------------------------------------------------------------------------------------------- visual check
+def get_output_and_plot(sg, dataset, index, class_info, random_sample_num=5, *legacy, device="cuda"):
+    """Grid of translations of one sample (source / target / reconstruction / identity, by encoder style and
+    by random styles).  Notebooks 01/02 pass one extra positional argument that the current signature of
+    the reference no longer has; it is accepted and, when it names a device, used as such."""
+    for extra in legacy:
+        if isinstance(extra, (str, torch.device)):
+            device = extra
+    if isinstance(random_sample_num, (str, torch.device)):
+        device, random_sample_num = random_sample_num, 5
+    import matplotlib.pyplot as plt
+    classes, label_discription = class_info
+    image0, label0 = dataset[index][0], dataset[index][1]
+    n = random_sample_num
+    with torch.no_grad():
+        src = image0.view(1, 3, 128, 128).to(device)
+        src_label = torch.tensor(label0).view(1,)
+        others = torch.tensor(get_target(src_label, classes, whole=False, shuffle=False))
+        tgt_label = others[:, 0:1]
+        show = lambda t: image_from_output(cuda2cpu(t))
+
+        by_enc, _ = sg.G_transformation(tgt_label, src, True, src)
+        by_rand, _ = sg.G_transformation(tgt_label.repeat(1, n), src.repeat(n, 1, 1, 1), False)
+        first = by_rand[0:1]
+        recon_enc, _ = sg.G_transformation(src_label, first, True, src)
+        idt_enc, _ = sg.G_transformation(src_label, src, True, src)
+        per_class, _ = sg.G_transformation(others, src.repeat(len(classes) - 1, 1, 1, 1), False)
+        recon_rand, _ = sg.G_transformation(src_label.repeat(n), first.repeat(n, 1, 1, 1), False)
+        idt_rand, _ = sg.G_transformation(src_label.repeat(n), src.repeat(n, 1, 1, 1), False)
+
+    rows, cols = n + 1, 4
+    fig = plt.figure(figsize=(5 * cols, 5 * rows))
+
+    def cell(pos, img, title):
+        ax = fig.add_subplot(rows, cols, pos)
+        ax.imshow(img)
+        ax.set_title(title)
+
+    cell(1, show(src)[0], "source")
+    cell(2, show(by_enc)[0], "target by source condition")
+    cell(3, show(recon_enc)[0], "recon by source condition")
+    cell(4, show(idt_enc)[0], "identity image by source condition")
+    for i, img in enumerate(show(per_class)):
+        cell(4 * (i + 1) + 1, img, label_discription[others[0][i]])
+    for col, batch, title in ((2, by_rand, "target by random latent"), (3, recon_rand, "recon by random latent"),
+                              (4, idt_rand, "idt by random latent")):
+        for i, img in enumerate(show(batch)):
+            cell(4 * (i + 1) + col, img, title)
+    return fig

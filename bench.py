@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- SRGAN train images/sec (full G+E+D step) on N B200s, with roofline and CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                      (the reference algorithm on the host CPU cores)
+
+A "step" is one `sg.train(x, label)` of the notebook-03 recipe (SRGAN, proposed losses, unrolled k=5:
+5 discriminator updates + generator/encoder phase 1 + generator phase 2, optimizer steps included) on a
+synthetic CelebA-shaped batch (U(-1,1) 3x128x128 images, 4 domains), random-init weights.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "style-restricted_gan_b200")
+for p in (os.path.join(PKG, "pyfiles"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GF_PER_IMG = {"srgan_nb03": 433.09, "nb02_solo": 423.22}      # conv+linear GFLOP / image / step
+WORKLOADS = {
+    "srgan_nb03": dict(kind="srgan", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu",
+                       desc="SRGAN nb03 recipe: G(3,64,2,2,6)+Encoder+solo-multi D, proposed losses "
+                            "(class1 cycle5 idt5 reg.5 idt_reg.5 bKL10 corr100 hist100), unrolled k=5"),
+    "nb02_solo": dict(kind="single_solo", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu",
+                      desc="SingleGAN nb02 recipe: Encoder_original + solo-multi D, proposed losses, k=5"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_case(name, batch):
+    import cases
+    w = WORKLOADS[name]
+    lbd = dict(cases.PROPOSED, **{"class": 1})
+    return dict(kind=w["kind"], nch=w["nch"], dis_nch=w["dis_nch"], enc_nch=w["enc_nch"], res_num=w["res_num"],
+                batch=batch, k=w["k"], lbd=lbd, feature=w["feature"], seed=0)
+
+
+def synthetic(batch, seed, get_target):
+    import cases
+    return cases.synthetic_batch(batch, get_target, seed=seed)
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def time_oracle(case, steps, warmup, threads):
+    """Reference algorithm (CPU oracle port) on the host cores: images/s over `steps` train() calls."""
+    import cases
+    import srgan_oracle as so
+    torch.set_num_threads(threads)
+    model, util, _ = cases.use_product_modules()       # module classes are only used to draw the default init
+    torch.manual_seed(0)
+    np.random.seed(0)
+    nets = cases.build_nets(model, case)
+    tr = cases.build_oracle(case, cases.state_dicts(nets), so)
+    x, label = synthetic(case["batch"], 123, util.get_target)
+    for _ in range(warmup):
+        tr.train(x, label)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train(x, label)
+    dt = time.perf_counter() - t0
+    return case["batch"] * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = args.cpu_batch
+    case = build_case(args.workload, batch)
+    steps = max(1, min(args.steps, 3))
+    ips, spt = time_oracle(case, steps, min(args.warmup, 1), threads)
+    sample = "%d step(s) of %s at batch %d on %d host threads (oracle port of the reference)" % (
+        steps, args.workload, batch, threads)
+    line = {"impl": "reference", "metric": "srgan_train_images_per_sec", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": spt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "batch": batch},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def time_dominant_kernel(batch, dev):
+    """CUDA-event time of the dominant kernel alone: the residual-block convolution forward
+    (3x3, 256->256 channels, 32x32, batch `batch`) through the C ABI, L2 flushed between launches."""
+    import srgan_ops as ops
+    x = torch.randn(batch, 256, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(256, 256, 3, 3, device=dev) * 0.02).contiguous(memory_format=torch.channels_last)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        ops.conv2d(x, w, None, 1, 1)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv2d(x, w, None, 1, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    flops = 2.0 * batch * 1024 * 256 * 2304
+    d = ops._desc(batch, 32, 32, 256, 256, 3, 3, 1, 1)
+    engine = ops._lib().srgan_conv2d_engine(d, 0)
+    return ms, flops, ("tcgen05_tf32" if engine == 2 else "ffma_fp32")
+
+
+def measure_tf32_peak(dev):
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import cases
+    import srgan_ops as ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    if args.engine:
+        ops.set_conv_engine(args.engine)
+
+    batch = args.batch                                   # per-GPU batch: weak scaling
+    case = build_case(args.workload, batch * world)      # n_batch (batch-KL) = configured GLOBAL batch
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    nets = cases.build_nets(model, case, dev)
+    G, D, E = nets
+    sg = cases.build_trainer(nb, case, (G.to(dev), D.to(dev), E.to(dev)), dev)
+    # every rank gets its own slice of the synthetic global batch
+    xg, lab = synthetic(batch * world, 123, util.get_target)
+    sl = slice(rank * batch, (rank + 1) * batch)
+    x_host = xg[sl].contiguous().pin_memory()
+    src_host = lab["source"][sl].contiguous().pin_memory()
+    tgt = lab["target"][sl].contiguous()
+    x_dev = x_host.to(dev)
+    label_dev = {"source": src_host.to(dev), "target": tgt}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        calls0 = ops.abi_calls
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, ops.abi_calls - calls0, clocks
+
+    def step_resident():
+        sg.train(x_dev, label_dev)
+
+    sink = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        ld = {"source": src_host.to(dev, non_blocking=True), "target": tgt}
+        errs = sg.train(xd, ld)
+        sink.copy_(torch.stack([e.detach().float() for e in errs]), non_blocking=False)   # device -> host read
+
+    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, True)
+    value = batch * world * args.steps / (ms * 1e-3)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1, False)
+    e2e = batch * world * args.steps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        kms, kflops, kname = time_dominant_kernel(batch, dev)
+        tf32_peak = measure_tf32_peak(dev)
+        achieved = kflops / (kms * 1e-3) / 1e12
+        peak = tf32_peak if kname == "tcgen05_tf32" else tf32_peak
+        roof = {"bound": "tensor", "kernel": "conv2d fprop 3x3 256->256 @32x32 (residual block), " + kname,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "cuBLAS TF32 8192^3 matmul measured in this run (MEASURED_PEAKS.json has no TF32 "
+                               "entry; bf16 there: %.1f TF/s, %s)" % (pk["bf16"], pk["src"]),
+                "kernel_ms": kms, "step_gflop_per_image": GF_PER_IMG[args.workload],
+                "step_tflops": value * GF_PER_IMG[args.workload] / 1e3}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            cb = args.cpu_batch
+            ips, spt = time_oracle(build_case(args.workload, cb), 1, 0, threads)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": "1 step of the same recipe at batch %d (%.1f s) on %d host threads" % (cb, spt, threads)}
+        h2d = x_host.numel() * 4 + src_host.numel() * 8 + 3 * (batch * 8 * 4)
+        line = {"metric": "srgan_train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if kname == "tcgen05_tf32" else "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS[args.workload]["desc"], "per_gpu_batch": batch,
+                           "global_batch": batch * world, "image": "3x128x128", "domains": 4,
+                           "parallelism": "dp%d" % world, "conv_engine": ops.get_conv_engine(),
+                           "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="srgan_nb03", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
+    ap.add_argument("--engine", default=None, choices=[None, "auto", "fp32", "tf32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,7 @@ def test_oracle_matches_reference_golden(name):
     # gradients at every optimizer step and weights after it (digests: norm, probe dot, 32 samples).
     # G gradients are ill-conditioned (L1 sign flips): looser bound for phase 2.
     checked = 0
+    agg = {}
     for key, ref in g.items():
         if "." not in key or key.split(".")[0] in ("init", "enc", "stats", "ref", "label", "x") \
                 or key in ("errs", "hist_target"):
@@ -91,11 +92,17 @@ def test_oracle_matches_reference_golden(name):
             if kind == "grad":
                 assert abs(d[0] - ref[0]) <= 0.15 * scale, (key, d[0], ref[0])
             continue
-        # G (and E, which is fed through G's L1 losses) gradients carry the L1-sign noise floor of SURVEY F12
-        tol = 5e-3 if step in ("G0", "E0") else 1e-3
+        # G (and E, which is fed through G's L1 losses) gradients carry the L1-sign noise floor of SURVEY F12:
+        # loose per parameter, tight on the whole step (vector of per-parameter norms + all samples)
+        tol = 2e-2 if step in ("G0", "E0") else 1e-3
         assert abs(d[0] - ref[0]) <= tol * scale, (key, d[0], ref[0])
         assert np.max(np.abs(d[2:] - ref[2:])) <= 2 * tol * max(np.max(np.abs(ref[2:])), scale * 1e-2), key
+        a = agg.setdefault(step + "." + kind, [[], []])
+        a[0].append(d)
+        a[1].append(ref)
         checked += 1
+    for stepkind, (got, ref) in agg.items():
+        assert _rel(np.concatenate(got), np.concatenate(ref)) < 3e-3, stepkind
     assert checked > 50
 
 

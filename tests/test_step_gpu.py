@@ -1,0 +1,179 @@
+"""GPU: one full training step of the product (SRGAN_training / SingleGAN_training on the B200 kernels, through
+the C ABI) against the CPU oracle on the same seeded weights, batch and host-drawn noise.
+
+Tolerances (fp32 FFMA engine vs the fp32 CPU oracle; stated per quantity):
+  losses 1e-4 relative; mu/logvar 1e-4; D gradients 1e-3; E phase-1 5e-3; G phase-1 1e-2 (L1-sign noise
+  floor); phase 2 is compared with TEACHER FORCING (the oracle's post-step weights are injected
+  into the product after phase 1) at 2e-2.
+With the tcgen05 TF32 engine: losses 5e-3, gradients 1e-1 (norm-level)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import srgan_ops as ops
+import srgan_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel_all(a, b):
+    num = den = 0.0
+    for k in b:
+        if b[k] is None:
+            continue
+        assert a.get(k) is not None, k
+        num += float((a[k].double().cpu() - b[k].double()).pow(2).sum())
+        den += float(b[k].double().pow(2).sum())
+    return (num / max(den, 1e-300)) ** 0.5
+
+
+def _capture(opt, net, key, record):
+    orig = opt.step
+    count = {"n": 0}
+
+    def step(*a, **k):
+        record["%s%d.grad" % (key, count["n"])] = {n: (None if p.grad is None else p.grad.detach().clone())
+                                                   for n, p in net.named_parameters()}
+        count["n"] += 1
+        return orig(*a, **k)
+    opt.step = step
+
+
+def _run_case(name, engine):
+    c = cases.CASES[name]
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(c["seed"])
+    np.random.seed(c["seed"])
+    nets = cases.build_nets(model, name, DEV)
+    sds = cases.state_dicts(nets)
+    torch.manual_seed(c["seed"] + 500)
+    oracle = cases.build_oracle(name, sds, so)
+    G, D, E = nets
+    G.to(DEV), E.to(DEV)
+    D = [d.to(DEV) for d in D] if isinstance(D, list) else D.to(DEV)
+    torch.manual_seed(c["seed"] + 500)
+    sg = cases.build_trainer(nb, name, (G, D, E), DEV)
+    x, label = cases.synthetic_batch(c["batch"], util.get_target)
+
+    oracle.record = {}
+    torch.manual_seed(c["seed"] + 1000)
+    errs_o = [float(e) for e in oracle.train(x, label)]
+    rec_o = oracle.record
+
+    ops.set_conv_engine(engine)
+    rec = {}
+    _capture(sg.optG, G, "G", rec)
+    _capture(sg.optE, E, "E", rec)
+    if isinstance(sg.optD, list):
+        for i, o in enumerate(sg.optD):
+            _capture(o, D[i], "Dc%d_" % i, rec)
+    else:
+        _capture(sg.optD, D, "D", rec)
+
+    def force(t):
+        with torch.no_grad():
+            for net, key in ((G, "G0.weight"), (E, "E0.weight")):
+                for n, p in net.named_parameters():
+                    p.copy_(rec_o[key][n].to(DEV))
+    sg._after_phase1 = force
+    torch.manual_seed(c["seed"] + 1000)
+    try:
+        errs = sg.train(x.to(DEV), {"source": label["source"].to(DEV), "target": label["target"]})
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_engine("auto")
+    rec["E_final.grad"] = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in E.named_parameters()}
+    return errs_o, rec_o, [float(e) for e in errs], rec, oracle, sg
+
+
+def _compare(name, engine, t):
+    errs_o, rec_o, errs, rec, oracle, sg = _run_case(name, engine)
+    for got, ref in zip(errs, errs_o):
+        assert abs(got - ref) <= t["loss"] * max(1.0, abs(ref)), (errs, errs_o)
+    k = cases.CASES[name]["k"]
+    if cases.CASES[name]["kind"] == "single_multi":
+        for i in range(cases.N_CLASS):
+            assert _rel_all(rec["Dc%d_%d.grad" % (i, k - 1)], rec_o["Dc%d_%d.grad" % (i, k - 1)]) < t["D"]
+    else:
+        for it in range(k):
+            assert _rel_all(rec["D%d.grad" % it], rec_o["D%d.grad" % it]) < t["D"], it
+    e0, g0 = _rel_all(rec["E0.grad"], rec_o["E0.grad"]), _rel_all(rec["G0.grad"], rec_o["G0.grad"])
+    g1, e1 = _rel_all(rec["G1.grad"], rec_o["G1.grad"]), _rel_all(rec["E_final.grad"], rec_o["E_final.grad"])
+    print("%s[%s] losses %s vs %s | E0 %.2e G0 %.2e | G1 %.2e E_final %.2e" % (name, engine, errs, errs_o, e0, g0, g1, e1))
+    assert e0 < t["E0"] and g0 < t["G0"], (e0, g0)
+    assert g1 < t["P2"] and e1 < t["P2"], (g1, e1)
+
+
+FP32_TOL = dict(loss=1e-4, D=1e-3, E0=5e-3, G0=1e-2, P2=2e-2)
+TF32_TOL = dict(loss=5e-3, D=5e-2, E0=2e-1, G0=3e-1, P2=5e-1)
+
+
+@pytest.mark.parametrize("name", ["srgan_small", "single_solo_small", "single_multi_small"])
+def test_step_matches_oracle_fp32_engine(name):
+    _compare(name, "fp32", FP32_TOL)
+
+
+def test_full_width_step_matches_oracle_fp32_engine():
+    _compare("srgan_full", "fp32", FP32_TOL)
+
+
+def test_full_width_step_auto_engine():
+    """Production engine selection (tcgen05 TF32 where the shape qualifies)."""
+    _compare("srgan_full", "auto", TF32_TOL)
+
+
+def test_step_matches_reference_golden_losses():
+    """Product losses against the golden vector recorded from the unmodified reference (same seeds)."""
+    import os
+    name = "srgan_small"
+    c = cases.CASES[name]
+    g = dict(np.load(os.path.join(cases.GOLDEN, name + ".npz")))
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(c["seed"])
+    np.random.seed(c["seed"])
+    G, D, E = cases.build_nets(model, name, DEV)
+    sg = cases.build_trainer(nb, name, (G.to(DEV), D.to(DEV), E.to(DEV)), DEV)   # make_golden.py's RNG order
+    x, label = cases.synthetic_batch(c["batch"], util.get_target)
+    ops.set_conv_engine("fp32")
+    torch.manual_seed(c["seed"] + 1000)
+    try:
+        errs = [float(e) for e in sg.train(x.to(DEV), {"source": label["source"].to(DEV), "target": label["target"]})]
+    finally:
+        ops.set_conv_engine("auto")
+    for got, ref in zip(errs, g["errs"]):
+        assert abs(got - ref) <= 1e-4 * max(1.0, abs(ref)), (errs, g["errs"])
+
+
+def test_module_api_surface():
+    """state_dict keys/shapes, return structures and error behaviour the notebooks rely on."""
+    model, util, nb = cases.use_product_modules()
+    G = model.SingleGenerator(3, 8, 2, 2, 1, "instance", num_con=12).to(DEV)
+    D = model.SingleDiscriminator_solo_multi(3, 8, 2, 4, "instance", 4).to(DEV)
+    E = model.Encoder(3, 8, 8, 4, "instance", 4, DEV).to(DEV)
+    x = torch.rand(2, 3, 128, 128, device=DEV) * 2 - 1
+    c = torch.randn(2, 12, device=DEV)
+    y = G(x, c)
+    assert y.shape == (2, 3, 128, 128) and float(y.abs().max()) <= 1.0
+    (o1, o2), (c1, c2) = D(x)
+    assert o1.shape == (2, 1, 7, 7) and o2.shape == (2, 1, 3, 3) and c1.shape == (2, 4) and c2.shape == (2, 4)
+    assert torch.allclose(c1.sum(1), torch.ones(2, device=DEV), atol=1e-5)
+    z, mu, logvar, cls, none = E(x)
+    assert z.shape == mu.shape == logvar.shape == (2, 8) and cls.shape == (2, 4) and none is None
+    with pytest.raises(ValueError):
+        model.CBINorm2d(8, 12)(torch.zeros(2, 8, 4, device=DEV), c)
+    with pytest.raises(NotImplementedError):
+        model.get_norm_layer("group")
+    assert "resBlocks.0.cn1.ConBias.0.weight" in G.state_dict() and "up_convs.2.weight" in G.state_dict()
+    assert G.state_dict()["up_convs.0.weight"].shape == (32, 16, 4, 4)
+    assert sorted(k for k in D.state_dict() if "classification" in k) == [
+        "classification_layer1.0.bias", "classification_layer1.0.weight",
+        "classification_layer2.0.bias", "classification_layer2.0.weight"]
+    cls_keys = list(model.Encoder_classifier(3, 8, 8, 4, "instance", 4).state_dict().keys())
+    missing = [k for k in E.state_dict() if k not in cls_keys]
+    assert missing == ["fcmean.weight", "fcmean.bias", "fcvar.weight", "fcvar.bias"]     # nb05 cell 22 output
+    E.freeze_melt(cls_keys, "freeze")
+    assert [n for n, p in E.named_parameters() if p.requires_grad] == missing
+    E.freeze_melt(cls_keys, "melt")
+    assert all(p.requires_grad for p in E.parameters())

@@ -1,15 +1,511 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (TF32 operands, fp32 accumulate).
-// Placeholder until the kernels land: reports "unsupported" so AUTO resolves to the FFMA engine.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution engine (TF32 operands straight from fp32 NHWC storage,
+// fp32 accumulation in tensor memory).  sm_100a only.
+//
+// One CTA computes a [128 output pixels] x [BN output channels] tile:
+//   D[m][n] = sum over taps t, channel chunks c :  A_t[m][c..c+32) . B_t[n][c..c+32)
+//   A_t : a TMA box {32 ch, bw, 1, bh, bn} of the activation (viewed 5-D, see below) shifted by the tap
+//         offset; out-of-bounds coordinates are zero-filled by TMA  == zero padding for free;
+//   B_t : a TMA box {32 ch, 1 tap, BN filters} of the KRSC filter (or its transposed copy);
+//   both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 = epilogue
+// (tcgen05.ld -> bias / activation -> global).  smem ring of kStages (full/empty mbarriers),
+// tcgen05.commit releases a stage when the MMAs that read it have retired.
+//
+// The same kernel serves, through a per-launch "tap table" and output-pixel mapping:
+//   fprop stride 1        taps (r,s) at offsets (r-pad, s-pad)
+//   fprop stride 2        activation viewed as (2C, W/2, 2, H/2, N): a tap selects a row/column parity
+//   dgrad stride 1        A = dy, filter transposed to [C][taps][K], taps at offsets (pad-r, pad-s)
+//   dgrad stride 2 /      4 output-parity classes (blockIdx.z), each a 2x2-tap stride-1 problem on dy,
+//   conv-transpose fwd    written to every second output pixel
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
 
 namespace srgan {
-bool conv_umma_supported(const srgan_conv_desc*, int) { return false; }
-size_t conv_umma_workspace(const srgan_conv_desc*, int) { return 0; }
-int conv_fprop_umma_launch(const srgan_conv_desc*, const float*, const float*, const float*, float*, int, float,
-                           void*, size_t, cudaStream_t) { return SRGAN_E_UNSUPPORTED; }
-int conv_dgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, void*, size_t,
-                           cudaStream_t) { return SRGAN_E_UNSUPPORTED; }
+
+constexpr int kUmmaThreads = 192;
+constexpr int kMaxTaps = 64;
+constexpr int kABytes = 128 * 128;          // 128 pixel rows x 128 B (32 fp32 channels)
+
+struct UmmaConvP {
+  int c_chunks;                  // reduction channels / 32
+  int tiles_w, tiles_h, tiles_n; // M-tile grid over the (N, P, Q) pixel grid of this launch
+  int lw, lh;                    // log2 of box width / height (bw * bh * bn == 128)
+  int Nn, P, Q;                  // extents of the pixel grid (validity masks)
+  int out_H, out_W, out_C;       // output tensor [N][out_H][out_W][out_C]
+  int os;                        // output pixel scale (2 for the parity-class launches)
+  int K;                         // valid output channels (columns)
+  int act;
+  float slope;
+  int cls_oph[4], cls_opw[4];    // output pixel parity of each class
+  int tap_begin[5];
+  int4 taps[kMaxTaps];           // {channel offset, dw, hp | (filter tap << 8), dh}
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 28)) __trap();      // a lost arrive must fail loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // instruction descriptor: D=f32, A=B=tf32, K-major both, N=BN, M=128
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y) {
+  using Cfg = UmmaCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = blockIdx.z;
+  const int tap0 = p.tap_begin[cls], ntaps = p.tap_begin[cls + 1] - tap0;
+  const int iters = ntaps * p.c_chunks;
+
+  // tile origin in the pixel grid
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int bw = 1 << p.lw, bh = 1 << p.lh;
+  const int bn = 128 >> (p.lw + p.lh);
+  const int q0 = tw * bw, p0 = th * bh, n0 = tn * bn;
+  const int col0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int tap = tap0 + it / p.c_chunks;
+        const int cc = (it % p.c_chunks) * 32;
+        const int4 tp = p.taps[tap];
+        mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
+        mbar_expect_tx(full + stage, Cfg::kStageBytes);
+        tma_load_5d(&map_a, full + stage, sa, cc + tp.x, q0 + tp.y, tp.z & 0xff, p0 + tp.w, n0);
+        tma_load_3d(&map_b, full + stage, sa + kABytes, cc, tp.z >> 8, col0);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+        const uint64_t adesc = smem_desc_sw128(sa);
+        const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)       // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
+          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc, (it | k) != 0);
+        umma_commit(empty + stage);       // stage reusable once these MMAs have read it
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);             // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+    const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
+    const int wl = m & (bw - 1), hl = (m >> p.lw) & (bh - 1), nl = m >> (p.lw + p.lh);
+    const int n = n0 + nl, pp = p0 + hl, qq = q0 + wl;
+    const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
+    float* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
+                       (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int kChunk = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += kChunk) {
+      float v[32];
+      if (kChunk == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < kChunk; j += 4) {
+          const int col = col0 + c + j;
+          if (col + 3 < p.K && (p.out_C & 3) == 0) {
+            float4 o;
+            o.x = apply_act(v[j + 0] + (bias ? __ldg(bias + col + 0) : 0.f), p.act, p.slope);
+            o.y = apply_act(v[j + 1] + (bias ? __ldg(bias + col + 1) : 0.f), p.act, p.slope);
+            o.z = apply_act(v[j + 2] + (bias ? __ldg(bias + col + 2) : 0.f), p.act, p.slope);
+            o.w = apply_act(v[j + 3] + (bias ? __ldg(bias + col + 3) : 0.f), p.act, p.slope);
+            *reinterpret_cast<float4*>(yrow + col) = o;
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.K)
+                yrow[col + e] = apply_act(v[j + e] + (bias ? __ldg(bias + col + e) : 0.f), p.act, p.slope);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// w[K][T][C] -> wt[C][T][K]  (filter transpose for the dgrad-shaped problems)
+__global__ void filter_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int T, int C) {
+  __shared__ float tile[32][33];
+  const int tp = blockIdx.z;
+  const int k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int k = k0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (k < K && c < C) ? w[((size_t)k * T + tp) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, k = k0 + threadIdx.x;
+    if (k < K && c < C) wt[((size_t)c * T + tp) * K + k] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SRGAN_E_UNSUPPORTED; }
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SRGAN_E_BADARG; }
+  return SRGAN_OK;
+}
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// choose the pixel box (bw x bh x bn = 128, powers of two) covering a P x Q grid
+static void pick_box(int P, int Q, int* lw, int* lh) {
+  int w = 1 << ilog2(Q);
+  if (w > 128) w = 128;
+  int h = 1 << ilog2(P);
+  if (h > 128 / w) h = 128 / w;
+  *lw = ilog2(w);
+  *lh = ilog2(h);
+}
+
+static int pick_bn(int K) {
+  if (K > 128) return 256;
+  if (K > 64) return 128;
+  if (K > 32) return 64;
+  if (K > 16) return 32;
+  return 16;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, float* y,
+                     dim3 grid, cudaStream_t st) {
+  using Cfg = UmmaCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmem);
+    if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  conv_umma_kernel<BN><<<grid, kUmmaThreads, Cfg::kSmem, st>>>(ma, mb, p, bias, y);
+  SRGAN_RETURN_LAUNCH();
+}
+
+// Generic launcher.  act_*: the tensor providing the A operand, [aN][aH][aW][aC] NHWC; `a_stride` 1 or 2
+// (2 => parity view).  filt: [fK][T][fC] with fC == aC the reduction channels, fK = output channels.
+struct Problem {
+  const float* act; int aN, aH, aW, aC; int a_stride;
+  const float* filt; int fK, T;
+  int Nn, P, Q;              // pixel grid per class
+  int out_H, out_W, os;
+  int ncls;
+  UmmaConvP p;               // taps / classes prefilled
+};
+
+static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  const int C = pr.aC;
+  if (pr.a_stride == 1) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)pr.aW, 1, (uint64_t)pr.aH, (uint64_t)pr.aN};
+    uint64_t str[4] = {(uint64_t)C * 4, (uint64_t)pr.aW * C * 4, (uint64_t)pr.aW * C * 4,
+                       (uint64_t)pr.aH * pr.aW * C * 4};
+    pick_box(pr.P, pr.Q, &pr.p.lw, &pr.p.lh);
+    uint32_t box[5] = {32, 1u << pr.p.lw, 1, 1u << pr.p.lh, 128u >> (pr.p.lw + pr.p.lh)};
+    if (int e = encode_map(&ma, pr.act, 5, dims, str, box)) return e;
+  } else {
+    uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)pr.aW / 2, 2, (uint64_t)pr.aH / 2, (uint64_t)pr.aN};
+    uint64_t str[4] = {(uint64_t)2 * C * 4, (uint64_t)pr.aW * C * 4, (uint64_t)2 * pr.aW * C * 4,
+                       (uint64_t)pr.aH * pr.aW * C * 4};
+    pick_box(pr.P, pr.Q, &pr.p.lw, &pr.p.lh);
+    uint32_t box[5] = {32, 1u << pr.p.lw, 1, 1u << pr.p.lh, 128u >> (pr.p.lw + pr.p.lh)};
+    if (int e = encode_map(&ma, pr.act, 5, dims, str, box)) return e;
+  }
+  const int BN = pick_bn(pr.fK);
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)pr.T, (uint64_t)pr.fK};
+    uint64_t str[2] = {(uint64_t)C * 4, (uint64_t)pr.T * C * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)BN};
+    if (int e = encode_map(&mb, pr.filt, 3, dims, str, box)) return e;
+  }
+  UmmaConvP& p = pr.p;
+  p.c_chunks = C / 32;
+  const int bw = 1 << p.lw, bh = 1 << p.lh, bn = 128 >> (p.lw + p.lh);
+  p.tiles_w = ceil_div(pr.Q, bw); p.tiles_h = ceil_div(pr.P, bh); p.tiles_n = ceil_div(pr.Nn, bn);
+  p.Nn = pr.Nn; p.P = pr.P; p.Q = pr.Q;
+  p.out_H = pr.out_H; p.out_W = pr.out_W; p.out_C = pr.fK; p.os = pr.os; p.K = pr.fK;
+  p.act = act; p.slope = slope;
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
+  switch (BN) {
+    case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st);
+    case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st);
+    case 64:  return launch_bn<64>(ma, mb, p, bias, y, grid, st);
+    case 32:  return launch_bn<32>(ma, mb, p, bias, y, grid, st);
+    default:  return launch_bn<16>(ma, mb, p, bias, y, grid, st);
+  }
+}
+
+static inline int floordiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+bool conv_umma_supported(const srgan_conv_desc* d, int pass) {
+  if (d->N < 1) return false;
+  if (pass == 0) {
+    if (d->C % 32) return false;
+    if (d->R * d->S > kMaxTaps) return false;
+    if (d->stride == 1) return true;
+    if (d->stride == 2) return d->H % 2 == 0 && d->W % 2 == 0;
+    return false;
+  }
+  if (pass == 1) {
+    if (d->K % 32) return false;             // reduction runs over the output channels of the conv
+    if (d->stride == 1) return d->R * d->S <= kMaxTaps && d->pad < d->R && d->pad < d->S;
+    if (d->stride == 2)
+      return d->R % 2 == 0 && d->S % 2 == 0 && d->H == 2 * d->P && d->W == 2 * d->Q && d->R * d->S <= kMaxTaps;
+    return false;
+  }
+  return false;   // wgrad: FFMA engine for now
+}
+
+size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
+  if (pass == 1) return (size_t)d->K * d->R * d->S * d->C * sizeof(float);   // transposed filter
+  return 0;
+}
+
+int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                           int act, float slope, void*, size_t, cudaStream_t st) {
+  Problem pr = {};
+  pr.act = x; pr.aN = d->N; pr.aH = d->H; pr.aW = d->W; pr.aC = d->C; pr.a_stride = d->stride;
+  pr.filt = w; pr.fK = d->K; pr.T = d->R * d->S;
+  pr.Nn = d->N; pr.P = d->P; pr.Q = d->Q; pr.out_H = d->P; pr.out_W = d->Q; pr.os = 1; pr.ncls = 1;
+  UmmaConvP& p = pr.p;
+  p.tap_begin[0] = 0;
+  int nt = 0;
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s) {
+      int a = r - d->pad, b = s - d->pad;
+      int4 tp;
+      if (d->stride == 1) {
+        tp = make_int4(0, b, 0 | ((r * d->S + s) << 8), a);
+      } else {
+        int hp = ((a % 2) + 2) % 2, wp = ((b % 2) + 2) % 2;
+        tp = make_int4(wp * d->C, floordiv2(b), hp | ((r * d->S + s) << 8), floordiv2(a));
+      }
+      p.taps[nt++] = tp;
+    }
+  p.tap_begin[1] = nt;
+  p.cls_oph[0] = 0; p.cls_opw[0] = 0;
+  return run_problem(pr, bias, y, act, slope, st);
+}
+
+int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
+                           size_t ws_bytes, cudaStream_t st) {
+  const int T = d->R * d->S;
+  size_t need = (size_t)d->K * T * d->C * sizeof(float);
+  if (ws_bytes < need || !ws) { set_error("conv dgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  float* wt = (float*)ws;       // [C][T][K]
+  {
+    dim3 g(ceil_div(d->C, 32), ceil_div(d->K, 32), T);
+    filter_transpose_kernel<<<g, dim3(32, 8), 0, st>>>(w, wt, d->K, T, d->C);
+  }
+  Problem pr = {};
+  pr.act = dy; pr.aN = d->N; pr.aH = d->P; pr.aW = d->Q; pr.aC = d->K; pr.a_stride = 1;
+  pr.filt = wt; pr.fK = d->C; pr.T = T;
+  UmmaConvP& p = pr.p;
+  if (d->stride == 1) {
+    pr.Nn = d->N; pr.P = d->H; pr.Q = d->W; pr.out_H = d->H; pr.out_W = d->W; pr.os = 1; pr.ncls = 1;
+    int nt = 0;
+    p.tap_begin[0] = 0;
+    for (int r = 0; r < d->R; ++r)
+      for (int s = 0; s < d->S; ++s) p.taps[nt++] = make_int4(0, d->pad - s, 0 | ((r * d->S + s) << 8), d->pad - r);
+    p.tap_begin[1] = nt;
+    p.cls_oph[0] = 0; p.cls_opw[0] = 0;
+  } else {
+    // output pixel (2*i + ph, 2*j + pw): taps r with (ph + pad - r) even, source row i + (ph + pad - r)/2
+    pr.Nn = d->N; pr.P = d->H / 2; pr.Q = d->W / 2; pr.out_H = d->H; pr.out_W = d->W; pr.os = 2; pr.ncls = 4;
+    int nt = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int ph = cls >> 1, pw = cls & 1;
+      p.tap_begin[cls] = nt;
+      p.cls_oph[cls] = ph; p.cls_opw[cls] = pw;
+      for (int r = 0; r < d->R; ++r) {
+        if ((ph + d->pad - r) % 2) continue;
+        for (int s = 0; s < d->S; ++s) {
+          if ((pw + d->pad - s) % 2) continue;
+          p.taps[nt++] = make_int4(0, floordiv2(pw + d->pad - s), 0 | ((r * d->S + s) << 8), floordiv2(ph + d->pad - r));
+        }
+      }
+    }
+    p.tap_begin[4] = nt;
+  }
+  return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st);
+}
+
 int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
-                           cudaStream_t) { return SRGAN_E_UNSUPPORTED; }
+                           cudaStream_t) {
+  set_error("conv wgrad: tcgen05 engine not available for this pass");
+  return SRGAN_E_UNSUPPORTED;
+}
+
 }  // namespace srgan
-extern "C" int srgan_has_tcgen05(void) { return 0; }
+
+extern "C" int srgan_has_tcgen05(void) { return 1; }

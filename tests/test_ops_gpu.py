@@ -78,7 +78,7 @@ def test_conv2d_fp32_engine(geom):
     b = _rand(K, seed=3).requires_grad_(True) if bias else None
     ins = [x, w] + ([b] if bias else [])
     _check(lambda x, w, b=None: ops.conv2d(x, w, b, stride, pad),
-           lambda x, w, b=None: F.conv2d(x, w, b, stride, pad), ins, 2e-6, 2e-5, ["x", "w", "b"])
+           lambda x, w, b=None: F.conv2d(x, w, b, stride, pad), ins, 1e-5, 3e-5, ["x", "w", "b"])  # fp32 sums of up to 32768 terms
 
 
 def test_conv2d_nchw_input_and_fused_activation():

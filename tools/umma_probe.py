@@ -36,7 +36,7 @@ def run_case(i):
     name, kind, N, C, H, W, K, R, stride, pad = CASES[i]
     g = torch.Generator().manual_seed(i)
     CL = torch.channels_last
-    ops.set_conv_engine("tf32")
+    ops.set_conv_engine("auto")
     if kind == "convT":
         x = torch.randn(N, C, H, W, generator=g).cuda().contiguous(memory_format=CL)
         w = (torch.randn(C, K, R, R, generator=g) * (C * 4) ** -0.5).cuda().contiguous(memory_format=CL)
@@ -61,8 +61,10 @@ def run_case(i):
     torch.cuda.synchronize()
     err = (y.double() - ref).abs()
     rel = float((y.double() - ref).norm() / ref.norm())
-    print("%-26s rel-L2 %.3e  max-abs %.3e  ref-rms %.3e  nan %d" % (
-        name, rel, float(err.max()), float(ref.pow(2).mean().sqrt()), int(torch.isnan(y).sum())), flush=True)
+    dd = ops._desc(N, H, W, C, K, R, R, stride, pad) if kind != "convT" else None
+    eng = ops._lib().srgan_conv2d_engine(dd, 1 if kind == "dgrad" else 0) if dd is not None else -9
+    print("%-26s eng %d rel-L2 %.3e  max-abs %.3e  ref-rms %.3e  nan %d" % (
+        name, eng, rel, float(err.max()), float(ref.pow(2).mean().sqrt()), int(torch.isnan(y).sum())), flush=True)
     if rel > 5e-3:
         yf, rf = y.detach().permute(0, 2, 3, 1).reshape(-1, y.shape[1]), ref.permute(0, 2, 3, 1).reshape(-1, y.shape[1])
         print("   got[0,:8]", [round(float(v), 4) for v in yf[0, :8]])

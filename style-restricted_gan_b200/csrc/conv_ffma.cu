@@ -429,6 +429,10 @@ int conv_dgrad_ffma_launch(const srgan_conv_desc* d, const float* dy, const floa
   SRGAN_RETURN_LAUNCH();
 }
 
+void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st) {
+  splitk_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(part, out, n, splits);
+}
+
 int colsum_launch(const float* x, float* out, long long rows, int C, cudaStream_t st) {
   if (C == 0) return SRGAN_OK;
   colsum_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(x, out, rows, C);

@@ -276,6 +276,140 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ wgrad
+// dW[k][t][c] = sum over pixels m :  dY[m][k] * X_t[m][c]          (X_t = x shifted by tap t, zero outside)
+// Both operands are "MN-major": the reduction index (pixel) is the slow dimension in memory.  A stage holds
+// a chunk of 32 pixels: dY box {32 k, pixel box} x 4 (128 filters) and X box {32 c, pixel box} x BN/32, each a
+// 4 KB swizzled region whose rows are pixels.  UMMA descriptors: MN-block stride (LBO) 4096 B, 8-pixel group
+// stride (SBO) 1024 B.  grid = (k tiles * c tiles, taps, pixel splits); splits write partial sums that a
+// fixed-order reduction kernel adds (deterministic).
+struct UmmaWgradP {
+  int tiles_c;                   // c tiles per k tile (blockIdx.x = kt * tiles_c + ct)
+  int tiles_w, tiles_h, tiles_n; // pixel-chunk grid
+  int lw, lh;                    // log2 chunk box width / height (bw*bh*bn == 32)
+  int chunks, chunks_per_split;
+  int K, C, T;                   // dW[K][T][C]
+  long long split_stride;        // elements between partial results
+  int4 taps[kMaxTaps];           // {channel offset, dw, hp, dh} of x for each filter tap
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;                // leading byte offset: next block of 32 MN elements
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next group of 8 pixels
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ UmmaWgradP p, float* __restrict__ out) {
+  using Cfg = UmmaCfg<BN>;
+  // same stage size as the forward kernel: 16 KB of dY + BN*128 B of X per 32-pixel chunk
+  constexpr uint32_t kIdescMN = Cfg::kIdesc | (1u << 15) | (1u << 16);     // A and B MN-major
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x / p.tiles_c, ct = blockIdx.x % p.tiles_c;
+  const int tap = blockIdx.y;
+  const int k0 = kt * 128, c0 = ct * BN;
+  const int ch_beg = blockIdx.z * p.chunks_per_split;
+  const int ch_end = min(p.chunks, ch_beg + p.chunks_per_split);
+  const int iters = ch_end - ch_beg;
+  const int bw = 1 << p.lw, bh = 1 << p.lh;
+  const int bn = 32 >> (p.lw + p.lh);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_x) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int4 tp = p.taps[tap];
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        int ch = ch_beg + it;
+        const int tw = ch % p.tiles_w; ch /= p.tiles_w;
+        const int th = ch % p.tiles_h;
+        const int tn = ch / p.tiles_h;
+        const int q0 = tw * bw, p0 = th * bh, n0 = tn * bn;
+        mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
+        mbar_expect_tx(full + stage, Cfg::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_5d(&map_dy, full + stage, sa + j * 4096, k0 + 32 * j, q0, 0, p0, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_5d(&map_x, full + stage, sa + kABytes + j * 4096, c0 + 32 * j + tp.x, q0 + tp.y, tp.z, p0 + tp.w, n0);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+        const uint64_t adesc = smem_desc_mn_sw128(sa);
+        const uint64_t bdesc = smem_desc_mn_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)       // 4 x 8 pixels; next 8-pixel group is 1024 B further (+64 in the field)
+          umma_tf32(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), kIdescMN, (it | k) != 0);
+        umma_commit(empty + stage);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int k = k0 + quad * 32 + lane;                 // accumulator row == filter index
+    const bool valid = k < p.K && iters > 0;
+    float* orow = out + (size_t)blockIdx.z * p.split_stride + ((size_t)k * p.T + tap) * p.C;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld32(taddr + c, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = c0 + c + j;
+          if (col < p.C) *reinterpret_cast<float4*>(orow + col) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // w[K][T][C] -> wt[C][T][K]  (filter transpose for the dgrad-shaped problems)
 __global__ void filter_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int T, int C) {
   __shared__ float tile[32][33];
@@ -364,6 +498,10 @@ struct Problem {
 };
 
 static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st) {
+  if (((uintptr_t)pr.act | (uintptr_t)pr.filt | (uintptr_t)y) % 16) {
+    set_error("tcgen05 conv: tensors must be 16-byte aligned");
+    return SRGAN_E_BADARG;
+  }
   CUtensorMap ma, mb;
   const int C = pr.aC;
   if (pr.a_stride == 1) {
@@ -423,11 +561,43 @@ bool conv_umma_supported(const srgan_conv_desc* d, int pass) {
       return d->R % 2 == 0 && d->S % 2 == 0 && d->H == 2 * d->P && d->W == 2 * d->Q && d->R * d->S <= kMaxTaps;
     return false;
   }
-  return false;   // wgrad: FFMA engine for now
+  // wgrad
+  if (d->C % 32 || d->R * d->S > kMaxTaps) return false;
+  if (d->stride == 1) return true;
+  if (d->stride == 2) return d->H % 2 == 0 && d->W % 2 == 0;
+  return false;
+}
+
+struct WgradPlan { int BN, lw, lh, tiles_w, tiles_h, tiles_n, chunks, cps, splits, tiles_k, tiles_c; };
+
+static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
+  WgradPlan w;
+  w.BN = d->C >= 256 ? 256 : (d->C >= 128 ? 128 : (d->C >= 64 ? 64 : 32));
+  int bw = 1 << ilog2(d->Q);
+  if (bw > 32) bw = 32;
+  int bh = 1 << ilog2(d->P);
+  if (bh > 32 / bw) bh = 32 / bw;
+  w.lw = ilog2(bw); w.lh = ilog2(bh);
+  int bn = 32 / (bw * bh);
+  w.tiles_w = ceil_div(d->Q, bw); w.tiles_h = ceil_div(d->P, bh); w.tiles_n = ceil_div(d->N, bn);
+  w.chunks = w.tiles_w * w.tiles_h * w.tiles_n;
+  w.tiles_k = ceil_div(d->K, 128); w.tiles_c = ceil_div(d->C, w.BN);
+  int tiles = w.tiles_k * w.tiles_c * d->R * d->S;
+  int splits = ceil_div(2 * kNumSMs, tiles);
+  if (splits > w.chunks) splits = w.chunks;
+  if (splits > 128) splits = 128;
+  if (splits < 1) splits = 1;
+  w.cps = ceil_div(w.chunks, splits);
+  w.splits = ceil_div(w.chunks, w.cps);
+  return w;
 }
 
 size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
   if (pass == 1) return (size_t)d->K * d->R * d->S * d->C * sizeof(float);   // transposed filter
+  if (pass == 2) {
+    WgradPlan w = plan_wgrad(d);
+    return w.splits > 1 ? (size_t)w.splits * d->K * d->R * d->S * d->C * sizeof(float) : 0;
+  }
   return 0;
 }
 
@@ -500,10 +670,83 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
   return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st);
 }
 
-int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
-                           cudaStream_t) {
-  set_error("conv wgrad: tcgen05 engine not available for this pass");
-  return SRGAN_E_UNSUPPORTED;
+void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st);
+int colsum_launch(const float* x, float* out, long long rows, int C, cudaStream_t st);
+
+template <int BN>
+static int launch_wgrad_bn(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
+                           cudaStream_t st) {
+  using Cfg = UmmaCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmem);
+    if (e != cudaSuccess) { set_error("wgrad_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  wgrad_umma_kernel<BN><<<grid, kUmmaThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
+  SRGAN_RETURN_LAUNCH();
+}
+
+int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                           void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (dbias) {
+    if (int e = colsum_launch(dy, dbias, (long long)d->N * d->P * d->Q, d->K, st)) return e;
+  }
+  if (!dw) return SRGAN_OK;
+  if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw | (uintptr_t)ws) % 16) {
+    set_error("tcgen05 wgrad: tensors must be 16-byte aligned");
+    return SRGAN_E_BADARG;
+  }
+  const WgradPlan w = plan_wgrad(d);
+  const int T = d->R * d->S;
+  const size_t need = conv_umma_workspace(d, 2);
+  if (need > ws_bytes || (need && !ws)) { set_error("conv wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  CUtensorMap mdy, mx;
+  const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = 32u / (bw * bh);
+  {
+    uint64_t dims[5] = {(uint64_t)d->K, (uint64_t)d->Q, 1, (uint64_t)d->P, (uint64_t)d->N};
+    uint64_t str[4] = {(uint64_t)d->K * 4, (uint64_t)d->Q * d->K * 4, (uint64_t)d->Q * d->K * 4,
+                       (uint64_t)d->P * d->Q * d->K * 4};
+    uint32_t box[5] = {32, bw, 1, bh, bn};
+    if (int e = encode_map(&mdy, dy, 5, dims, str, box)) return e;
+  }
+  const int C = d->C;
+  if (d->stride == 1) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)d->W, 1, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[4] = {(uint64_t)C * 4, (uint64_t)d->W * C * 4, (uint64_t)d->W * C * 4, (uint64_t)d->H * d->W * C * 4};
+    uint32_t box[5] = {32, bw, 1, bh, bn};
+    if (int e = encode_map(&mx, x, 5, dims, str, box)) return e;
+  } else {
+    uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)d->W / 2, 2, (uint64_t)d->H / 2, (uint64_t)d->N};
+    uint64_t str[4] = {(uint64_t)2 * C * 4, (uint64_t)d->W * C * 4, (uint64_t)2 * d->W * C * 4,
+                       (uint64_t)d->H * d->W * C * 4};
+    uint32_t box[5] = {32, bw, 1, bh, bn};
+    if (int e = encode_map(&mx, x, 5, dims, str, box)) return e;
+  }
+  UmmaWgradP p = {};
+  p.tiles_c = w.tiles_c; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
+  p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
+  p.K = d->K; p.C = C; p.T = T;
+  p.split_stride = (long long)d->K * T * C;
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s) {
+      int a = r - d->pad, b = s - d->pad;
+      if (d->stride == 1) p.taps[r * d->S + s] = make_int4(0, b, 0, a);
+      else p.taps[r * d->S + s] = make_int4((((b % 2) + 2) % 2) * C, floordiv2(b), ((a % 2) + 2) % 2, floordiv2(a));
+    }
+  float* out = w.splits > 1 ? (float*)ws : dw;
+  dim3 grid(w.tiles_k * w.tiles_c, T, w.splits);
+  int e;
+  switch (w.BN) {
+    case 256: e = launch_wgrad_bn<256>(mdy, mx, p, out, grid, st); break;
+    case 128: e = launch_wgrad_bn<128>(mdy, mx, p, out, grid, st); break;
+    case 64:  e = launch_wgrad_bn<64>(mdy, mx, p, out, grid, st); break;
+    default:  e = launch_wgrad_bn<32>(mdy, mx, p, out, grid, st); break;
+  }
+  if (e) return e;
+  if (w.splits > 1) splitk_reduce_launch((const float*)ws, dw, (long long)d->K * T * C, w.splits, st);
+  SRGAN_RETURN_LAUNCH();
 }
 
 }  // namespace srgan

@@ -317,6 +317,8 @@ extern "C" int srgan_inorm_fwd(const float* x, float* y, float* mean, float* rst
                                int C, float eps, int act, float slope, void* stream) {
   SRGAN_CHECK_ARG(x && y && mean && rstd, "null pointer");
   SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
+  SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)residual) % 16 == 0, "pointers must be 16-byte aligned");
   SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
   if (N == 0) return SRGAN_OK;
   NormPlan pl = plan_norm(N, HW, C, 1);
@@ -334,6 +336,9 @@ extern "C" int srgan_inorm_bwd(const float* dy, const float* x, const float* mea
                                float* s2, int N, int HW, int C, int act, float slope, void* stream) {
   SRGAN_CHECK_ARG(dy && x && mean && rstd && dx && s1 && s2, "null pointer");
   SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
+  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)dx | (uintptr_t)s1 | (uintptr_t)s2) % 16 == 0,
+                  "pointers must be 16-byte aligned");
   SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
   if (N == 0) return SRGAN_OK;
   NormPlan pl = plan_norm(N, HW, C, 2);

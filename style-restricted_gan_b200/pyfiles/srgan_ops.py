@@ -860,9 +860,11 @@ class FusedAdam(torch.optim.Optimizer):
         if not ps:
             return None
         _req(*ps)
-        n = sum(p.numel() for p in ps)
+        # every parameter starts on a 256-byte boundary: TMA tensor maps need 16-byte aligned bases and the
+        # glue kernels use float4 loads; the padding is zero and stays zero under Adam
+        n = sum(-(-p.numel() // 64) * 64 for p in ps)
         dev = ps[0].device
-        fp = torch.empty(n, dtype=torch.float32, device=dev)
+        fp = torch.zeros(n, dtype=torch.float32, device=dev)
         fg = torch.zeros(n, dtype=torch.float32, device=dev)
         views = []
         o = 0
@@ -885,7 +887,7 @@ class FusedAdam(torch.optim.Optimizer):
             p.data = view(fp)
             p.grad = view(fg)
             views.append((p, view))
-            o += k
+            o += -(-k // 64) * 64
         st = dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), step=0, views=views, params=ps)
         self._flat[gi] = st
         return st

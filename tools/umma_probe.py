@@ -26,6 +26,15 @@ CASES = [
     ("d_c3_s2_dgrad", "dgrad", 2, 256, 16, 16, 512, 4, 2, 1),
     ("shortcut1x1_31", "fprop", 2, 64, 31, 31, 128, 1, 1, 0),
     ("convT", "convT", 2, 256, 32, 32, 128, 4, 2, 1),
+    ("wgrad_1x1_c32_k128", "wgrad", 1, 32, 4, 8, 128, 1, 1, 0),
+    ("wgrad_1x1_c64_k256", "wgrad", 2, 64, 16, 16, 256, 1, 1, 0),
+    ("wgrad_res3x3", "wgrad", 4, 256, 32, 32, 256, 3, 1, 1),
+    ("wgrad_down4x4s2", "wgrad", 2, 64, 128, 128, 128, 4, 2, 1),
+    ("wgrad_out7x7_k3", "wgrad", 2, 64, 128, 128, 3, 7, 1, 3),
+    ("wgrad_enc_valid_62", "wgrad", 2, 64, 64, 64, 128, 3, 1, 0),
+    ("wgrad_enc_tail7", "wgrad", 3, 512, 9, 9, 1024, 3, 1, 0),
+    ("wgrad_d_c3", "wgrad", 2, 256, 16, 16, 512, 4, 2, 1),
+    ("wgrad_dclass", "wgrad", 2, 512, 8, 8, 4, 8, 1, 0),
 ]
 
 
@@ -48,6 +57,15 @@ def run_case(i):
         b = torch.randn(K, generator=g).cuda()
         y = ops.conv2d(x, w, b, stride, pad)
         ref = F.conv2d(x.double(), w.double(), b.double(), stride, pad)
+    elif kind == "wgrad":
+        x = torch.randn(N, C, H, W, generator=g).cuda().contiguous(memory_format=CL)
+        wr = (torch.randn(K, C, R, R, generator=g) * (C * R * R) ** -0.5).cuda().double().requires_grad_(True)
+        yr = F.conv2d(x.double(), wr, None, stride, pad)
+        gy = torch.randn(yr.shape, generator=g).cuda().contiguous(memory_format=CL)
+        d = ops._desc(N, H, W, C, K, R, R, stride, pad)
+        y, _ = ops._wgrad(d, x, gy, True, False)
+        yr.backward(gy.double())
+        ref = wr.grad
     else:
         x = torch.randn(N, C, H, W, generator=g).cuda().contiguous(memory_format=CL).requires_grad_(True)
         w = (torch.randn(K, C, R, R, generator=g) * (C * R * R) ** -0.5).cuda().contiguous(memory_format=CL)
@@ -62,7 +80,7 @@ def run_case(i):
     err = (y.double() - ref).abs()
     rel = float((y.double() - ref).norm() / ref.norm())
     dd = ops._desc(N, H, W, C, K, R, R, stride, pad) if kind != "convT" else None
-    eng = ops._lib().srgan_conv2d_engine(dd, 1 if kind == "dgrad" else 0) if dd is not None else -9
+    eng = ops._lib().srgan_conv2d_engine(dd, {"dgrad": 1, "wgrad": 2}.get(kind, 0)) if dd is not None else -9
     print("%-26s eng %d rel-L2 %.3e  max-abs %.3e  ref-rms %.3e  nan %d" % (
         name, eng, rel, float(err.max()), float(ref.pow(2).mean().sqrt()), int(torch.isnan(y).sum())), flush=True)
     if rel > 5e-3:
@@ -81,7 +99,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
-        for i in range(len(CASES)):
+        first = int(os.environ.get("PROBE_FROM", "0"))
+        for i in range(first, len(CASES)):
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True,
                                    text=True, timeout=180)

@@ -17,6 +17,7 @@
 //   dgrad stride 1        A = dy, filter transposed to [C][taps][K], taps at offsets (pad-r, pad-s)
 //   dgrad stride 2 /      4 output-parity classes (blockIdx.z), each a 2x2-tap stride-1 problem on dy,
 //   conv-transpose fwd    written to every second output pixel
+#include <stdlib.h>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include "common.cuh"
@@ -291,16 +292,19 @@ struct UmmaWgradP {
   int chunks, chunks_per_split;
   int K, C, T;                   // dW[K][T][C]
   long long split_stride;        // elements between partial results
+  unsigned long long desc_hi;    // descriptor bits above the start address (LBO, SBO, version, layout type)
   int4 taps[kMaxTaps];           // {channel offset, dw, hp, dh} of x for each filter tap
 };
 
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+// MN-major TF32 operands only exist in the "128B swizzle, 32-byte atom" layout (UMMA layout type
+// SWIZZLE_128B_BASE32B <-> TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 MN elements), 32-byte
+// chunks XOR-ed with (row & 3); canonical K blocks are 4 rows.
+__host__ __device__ inline uint64_t mn_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)(4096 >> 4) << 16;                // leading byte offset: next block of 32 MN elements
-  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next group of 8 pixels
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;           // leading byte offset: next block of 32 MN elements
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;           // stride byte offset: next group of 4 pixel rows
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;                     // 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -371,10 +375,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         mbar_wait(full + stage, phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-        const uint64_t adesc = smem_desc_mn_sw128(sa);
-        const uint64_t bdesc = smem_desc_mn_sw128(sa + kABytes);
+        const uint64_t adesc = p.desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+        const uint64_t bdesc = p.desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)       // 4 x 8 pixels; next 8-pixel group is 1024 B further (+64 in the field)
+        for (int k = 0; k < 4; ++k)       // 4 x 8 pixels; 8 pixel rows = 1024 B further (+64 in the address field)
           umma_tf32(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), kIdescMN, (it | k) != 0);
         umma_commit(empty + stage);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -440,12 +444,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                      const uint32_t* box) {
+                      const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SRGAN_E_UNSUPPORTED; }
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SRGAN_E_BADARG; }
   return SRGAN_OK;
@@ -561,8 +565,8 @@ bool conv_umma_supported(const srgan_conv_desc* d, int pass) {
       return d->R % 2 == 0 && d->S % 2 == 0 && d->H == 2 * d->P && d->W == 2 * d->Q && d->R * d->S <= kMaxTaps;
     return false;
   }
-  // wgrad
-  if (d->C % 32 || d->R * d->S > kMaxTaps) return false;
+  // wgrad (the dy tensor map needs 16-byte aligned pixel rows: K % 4 == 0)
+  if (d->C % 32 || d->K % 4 || d->R * d->S > kMaxTaps) return false;
   if (d->stride == 1) return true;
   if (d->stride == 2) return d->H % 2 == 0 && d->W % 2 == 0;
   return false;
@@ -704,31 +708,38 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
   if (need > ws_bytes || (need && !ws)) { set_error("conv wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
   CUtensorMap mdy, mx;
   const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = 32u / (bw * bh);
+  // bring-up overrides (undocumented, debugging only)
+  static const char* e_swz = getenv("SRGAN_DBG_WGRAD_TMASWZ");
+  static const char* e_lbo = getenv("SRGAN_DBG_WGRAD_LBO");
+  static const char* e_sbo = getenv("SRGAN_DBG_WGRAD_SBO");
+  static const char* e_lay = getenv("SRGAN_DBG_WGRAD_LAYOUT");
+  const CUtensorMapSwizzle swz = e_swz ? (CUtensorMapSwizzle)atoi(e_swz) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   {
     uint64_t dims[5] = {(uint64_t)d->K, (uint64_t)d->Q, 1, (uint64_t)d->P, (uint64_t)d->N};
     uint64_t str[4] = {(uint64_t)d->K * 4, (uint64_t)d->Q * d->K * 4, (uint64_t)d->Q * d->K * 4,
                        (uint64_t)d->P * d->Q * d->K * 4};
     uint32_t box[5] = {32, bw, 1, bh, bn};
-    if (int e = encode_map(&mdy, dy, 5, dims, str, box)) return e;
+    if (int e = encode_map(&mdy, dy, 5, dims, str, box, swz)) return e;
   }
   const int C = d->C;
   if (d->stride == 1) {
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)d->W, 1, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t str[4] = {(uint64_t)C * 4, (uint64_t)d->W * C * 4, (uint64_t)d->W * C * 4, (uint64_t)d->H * d->W * C * 4};
     uint32_t box[5] = {32, bw, 1, bh, bn};
-    if (int e = encode_map(&mx, x, 5, dims, str, box)) return e;
+    if (int e = encode_map(&mx, x, 5, dims, str, box, swz)) return e;
   } else {
     uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)d->W / 2, 2, (uint64_t)d->H / 2, (uint64_t)d->N};
     uint64_t str[4] = {(uint64_t)2 * C * 4, (uint64_t)d->W * C * 4, (uint64_t)2 * d->W * C * 4,
                        (uint64_t)d->H * d->W * C * 4};
     uint32_t box[5] = {32, bw, 1, bh, bn};
-    if (int e = encode_map(&mx, x, 5, dims, str, box)) return e;
+    if (int e = encode_map(&mx, x, 5, dims, str, box, swz)) return e;
   }
   UmmaWgradP p = {};
   p.tiles_c = w.tiles_c; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
   p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
   p.K = d->K; p.C = C; p.T = T;
   p.split_stride = (long long)d->K * T * C;
+  p.desc_hi = mn_desc_hi(e_lbo ? atoi(e_lbo) : 4096, e_sbo ? atoi(e_sbo) : 512, e_lay ? atoi(e_lay) : 1);
   for (int r = 0; r < d->R; ++r)
     for (int s = 0; s < d->S; ++s) {
       int a = r - d->pad, b = s - d->pad;

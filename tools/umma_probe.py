@@ -95,8 +95,30 @@ def run_case(i):
     return rel
 
 
+def sweep_wgrad():
+    """Descriptor / TMA-swizzle variants for the MN-major wgrad operands on two small cases."""
+    variants = [dict(), dict(SBO="1024"), dict(LAYOUT="2", TMASWZ="3", SBO="1024"), dict(LAYOUT="2", TMASWZ="3"),
+                dict(LAYOUT="1", TMASWZ="3"), dict(LBO="512", SBO="4096"), dict(LBO="1024", SBO="4096"),
+                dict(TMASWZ="5"), dict(TMASWZ="6", LAYOUT="1")]
+    idx = [i for i, c in enumerate(CASES) if c[0] in ("wgrad_1x1_c32_k128", "wgrad_1x1_c64_k256", "wgrad_res3x3")]
+    for v in variants:
+        env = dict(os.environ)
+        for k, val in v.items():
+            env["SRGAN_DBG_WGRAD_" + k] = val
+        for i in idx:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True,
+                                   text=True, timeout=120, env=env)
+                line = (r.stdout.strip().splitlines() or ["(no output) rc=%d %s" % (r.returncode, r.stderr.strip()[-200:])])[0]
+            except subprocess.TimeoutExpired:
+                line = "TIMEOUT"
+            print(str(v), "|", line, flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        sweep_wgrad()
+    elif len(sys.argv) > 1:
         run_case(int(sys.argv[1]))
     else:
         first = int(os.environ.get("PROBE_FROM", "0"))

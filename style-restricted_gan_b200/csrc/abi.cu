@@ -21,7 +21,7 @@ int conv_fprop_ffma_launch(const srgan_conv_desc*, const float*, const float*, c
 int conv_dgrad_ffma_launch(const srgan_conv_desc*, const float*, const float*, float*, cudaStream_t);
 int conv_wgrad_ffma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
                            cudaStream_t);
-int colsum_launch(const float*, float*, long long, int, cudaStream_t);
+int colsum_launch(const float*, float*, long long, int, float*, int, cudaStream_t);
 
 // conv_umma.cu (tcgen05 engine)
 bool conv_umma_supported(const srgan_conv_desc* d, int pass);
@@ -115,5 +115,5 @@ extern "C" int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, cons
 
 extern "C" int srgan_colsum(const float* x, float* out, size_t rows, int C, void* stream) {
   SRGAN_CHECK_ARG(x && out && C >= 0, "bad argument");
-  return colsum_launch(x, out, (long long)rows, C, (cudaStream_t)stream);
+  return colsum_launch(x, out, (long long)rows, C, nullptr, 0, (cudaStream_t)stream);
 }

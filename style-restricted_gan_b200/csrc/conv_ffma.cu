@@ -365,8 +365,29 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
   }
 }
 
+// stage 1 of the two-stage column sum: block (x = column tile, y = row block) sums its row range
+__global__ void colsum_partial_kernel(const float* __restrict__ x, float* __restrict__ part, long long rows, int C,
+                                      long long rows_per_block) {
+  __shared__ float red[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * C + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    part[(long long)blockIdx.y * C + c] = t;
+  }
+}
+
 using CfgWide = Cfg<128, 64, 16, 8, 4>;    // general shapes
 using CfgThin = Cfg<256, 16, 16, 8, 2>;    // few output columns (K = 1,3,4 heads; C=3 dgrad)
+using CfgHalf = Cfg<64, 64, 16, 4, 4>;     // wgrad of layers with <= 64 filters (stems)
 
 static ConvP to_p(const srgan_conv_desc* d) {
   ConvP p;
@@ -383,7 +404,7 @@ static ConvP to_p(const srgan_conv_desc* d) {
 int wgrad_ffma_splits(const srgan_conv_desc* d) {
   long long Mpix = (long long)d->N * d->P * d->Q;
   int Ng = d->R * d->S * d->C;
-  int tiles = ceil_div(d->K, 128) * ceil_div(Ng, 64);
+  int tiles = ceil_div(d->K, d->K <= 64 ? 64 : 128) * ceil_div(Ng, 64);
   int splits = ceil_div(2 * kNumSMs, tiles);
   long long maxs = ceil_div64(Mpix, 64);   // keep >= 64 pixels per split
   if (splits > maxs) splits = (int)maxs;
@@ -392,11 +413,13 @@ int wgrad_ffma_splits(const srgan_conv_desc* d) {
   return splits;
 }
 
+constexpr int kColsumBlocksF = 64;
+
 size_t conv_ffma_workspace(const srgan_conv_desc* d, int pass) {
   if (pass != 2) return 0;
   int splits = wgrad_ffma_splits(d);
-  if (splits == 1) return 0;
-  return (size_t)splits * d->K * d->R * d->S * d->C * sizeof(float);
+  size_t b = splits == 1 ? 0 : (size_t)splits * d->K * d->R * d->S * d->C * sizeof(float);
+  return b + (size_t)kColsumBlocksF * d->K * sizeof(float);
 }
 
 int conv_fprop_ffma_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias,
@@ -433,9 +456,18 @@ void splitk_reduce_launch(const float* part, float* out, long long n, int splits
   splitk_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(part, out, n, splits);
 }
 
-int colsum_launch(const float* x, float* out, long long rows, int C, cudaStream_t st) {
+// out[c] = sum_r x[r][c].  With scratch (>= blocks*C floats) large inputs use two fixed-order stages.
+int colsum_launch(const float* x, float* out, long long rows, int C, float* scratch, int scratch_blocks,
+                  cudaStream_t st) {
   if (C == 0) return SRGAN_OK;
-  colsum_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(x, out, rows, C);
+  if (scratch && scratch_blocks > 1 && rows >= 4096) {
+    long long rpb = ceil_div64(rows, scratch_blocks);
+    int nb = (int)ceil_div64(rows, rpb);
+    colsum_partial_kernel<<<dim3(ceil_div(C, 32), nb), dim3(32, 8), 0, st>>>(x, scratch, rows, C, rpb);
+    colsum_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(scratch, out, nb, C);
+  } else {
+    colsum_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, st>>>(x, out, rows, C);
+  }
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -444,20 +476,26 @@ int conv_wgrad_ffma_launch(const srgan_conv_desc* d, const float* x, const float
   ConvP p = to_p(d);
   long long Mpix = (long long)d->N * d->P * d->Q;
   int Ng = d->R * d->S * d->C;
+  int splits = wgrad_ffma_splits(d);
+  size_t need = conv_ffma_workspace(d, 2);
+  if (need > ws_bytes || !ws) { set_error("conv_wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  float* csum = (float*)ws + (splits == 1 ? 0 : (size_t)splits * d->K * Ng);
   if (dw) {
-    int splits = wgrad_ffma_splits(d);
-    size_t need = conv_ffma_workspace(d, 2);
-    if (need > ws_bytes) { set_error("conv_wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
     long long chunk = ceil_div64(ceil_div64(Mpix, splits), CfgWide::kBK) * CfgWide::kBK;
     float* out = splits == 1 ? dw : (float*)ws;
-    dim3 g(ceil_div(d->K, CfgWide::kBM), ceil_div(Ng, CfgWide::kBN), splits);
-    conv_wgrad_ffma<CfgWide><<<g, 256, 0, st>>>(p, x, dy, out, chunk);
+    if (d->K <= 64) {
+      dim3 g(ceil_div(d->K, CfgHalf::kBM), ceil_div(Ng, CfgHalf::kBN), splits);
+      conv_wgrad_ffma<CfgHalf><<<g, 256, 0, st>>>(p, x, dy, out, chunk);
+    } else {
+      dim3 g(ceil_div(d->K, CfgWide::kBM), ceil_div(Ng, CfgWide::kBN), splits);
+      conv_wgrad_ffma<CfgWide><<<g, 256, 0, st>>>(p, x, dy, out, chunk);
+    }
     if (splits > 1) {
       long long n = (long long)d->K * Ng;
       splitk_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>((const float*)ws, dw, n, splits);
     }
   }
-  if (dbias) colsum_kernel<<<ceil_div(d->K, 32), dim3(32, 8), 0, st>>>(dy, dbias, Mpix, d->K);
+  if (dbias) return colsum_launch(dy, dbias, Mpix, d->K, csum, kColsumBlocksF, st);
   SRGAN_RETURN_LAUNCH();
 }
 

@@ -561,15 +561,28 @@ bool conv_umma_supported(const srgan_conv_desc* d, int pass) {
   if (pass == 1) {
     if (d->K % 32) return false;             // reduction runs over the output channels of the conv
     if (d->stride == 1) return d->R * d->S <= kMaxTaps && d->pad < d->R && d->pad < d->S;
-    if (d->stride == 2)
-      return d->R % 2 == 0 && d->S % 2 == 0 && d->H == 2 * d->P && d->W == 2 * d->Q && d->R * d->S <= kMaxTaps;
+    if (d->stride == 2)   // four output-parity classes over an (H/2, W/2) grid; dy rows outside [0,P) are TMA zero-fill
+      return d->H % 2 == 0 && d->W % 2 == 0 && d->R * d->S <= kMaxTaps && d->R >= 2 && d->S >= 2;
     return false;
   }
-  // wgrad (the dy tensor map needs 16-byte aligned pixel rows: K % 4 == 0)
-  if (d->C % 32 || d->K % 4 || d->R * d->S > kMaxTaps) return false;
+  // wgrad (dy is re-packed to a multiple of 4 channels when K % 4 != 0: TMA needs 16-byte pixel rows)
+  if (d->C % 32 || d->R * d->S > kMaxTaps) return false;
   if (d->stride == 1) return true;
   if (d->stride == 2) return d->H % 2 == 0 && d->W % 2 == 0;
   return false;
+}
+
+constexpr int kColsumBlocks = 64;
+
+// dst[pix][0..Kp) = src[pix][0..K) followed by zeros
+__global__ void pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t pixels, int K,
+                                    int Kp) {
+  const size_t total = pixels * Kp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t pix = i / Kp;
+    int k = (int)(i - pix * Kp);
+    dst[i] = k < K ? __ldg(src + pix * K + k) : 0.f;
+  }
 }
 
 struct WgradPlan { int BN, lw, lh, tiles_w, tiles_h, tiles_n, chunks, cps, splits, tiles_k, tiles_c; };
@@ -600,7 +613,10 @@ size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
   if (pass == 1) return (size_t)d->K * d->R * d->S * d->C * sizeof(float);   // transposed filter
   if (pass == 2) {
     WgradPlan w = plan_wgrad(d);
-    return w.splits > 1 ? (size_t)w.splits * d->K * d->R * d->S * d->C * sizeof(float) : 0;
+    size_t b = w.splits > 1 ? (size_t)w.splits * d->K * d->R * d->S * d->C * sizeof(float) : 0;
+    if (d->K % 4) b += (size_t)d->N * d->P * d->Q * ((d->K + 3) / 4 * 4) * sizeof(float);   // re-packed dy
+    b += (size_t)kColsumBlocks * d->K * sizeof(float);                                      // bias-gradient partials
+    return b;
   }
   return 0;
 }
@@ -675,7 +691,8 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
 }
 
 void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st);
-int colsum_launch(const float* x, float* out, long long rows, int C, cudaStream_t st);
+int colsum_launch(const float* x, float* out, long long rows, int C, float* scratch, int scratch_blocks,
+                  cudaStream_t st);
 
 template <int BN>
 static int launch_wgrad_bn(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
@@ -694,18 +711,30 @@ static int launch_wgrad_bn(const CUtensorMap& mdy, const CUtensorMap& mx, const 
 
 int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                            void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (dbias) {
-    if (int e = colsum_launch(dy, dbias, (long long)d->N * d->P * d->Q, d->K, st)) return e;
-  }
-  if (!dw) return SRGAN_OK;
+  const WgradPlan w = plan_wgrad(d);
+  const int T = d->R * d->S;
+  const size_t need = conv_umma_workspace(d, 2);
+  if (need > ws_bytes || !ws) { set_error("conv wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
   if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw | (uintptr_t)ws) % 16) {
     set_error("tcgen05 wgrad: tensors must be 16-byte aligned");
     return SRGAN_E_BADARG;
   }
-  const WgradPlan w = plan_wgrad(d);
-  const int T = d->R * d->S;
-  const size_t need = conv_umma_workspace(d, 2);
-  if (need > ws_bytes || (need && !ws)) { set_error("conv wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  // workspace layout: [split partials][re-packed dy][colsum partials]
+  float* part = (float*)ws;
+  float* dyp = part + (w.splits > 1 ? (size_t)w.splits * d->K * T * d->C : 0);
+  const int Kp = (d->K + 3) / 4 * 4;
+  const size_t pixels = (size_t)d->N * d->P * d->Q;
+  float* csum = dyp + (d->K % 4 ? pixels * Kp : 0);
+  if (dbias) {
+    if (int e = colsum_launch(dy, dbias, (long long)pixels, d->K, csum, kColsumBlocks, st)) return e;
+  }
+  if (!dw) return SRGAN_OK;
+  if (d->K % 4) {
+    size_t total = pixels * Kp;
+    unsigned blocks = (unsigned)((total + 255) / 256 < (size_t)kNumSMs * 8 ? (total + 255) / 256 : (size_t)kNumSMs * 8);
+    pad_channels_kernel<<<blocks, 256, 0, st>>>(dy, dyp, pixels, d->K, Kp);
+    dy = dyp;
+  }
   CUtensorMap mdy, mx;
   const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = 32u / (bw * bh);
   // bring-up overrides (undocumented, debugging only)
@@ -715,9 +744,9 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
   static const char* e_lay = getenv("SRGAN_DBG_WGRAD_LAYOUT");
   const CUtensorMapSwizzle swz = e_swz ? (CUtensorMapSwizzle)atoi(e_swz) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   {
-    uint64_t dims[5] = {(uint64_t)d->K, (uint64_t)d->Q, 1, (uint64_t)d->P, (uint64_t)d->N};
-    uint64_t str[4] = {(uint64_t)d->K * 4, (uint64_t)d->Q * d->K * 4, (uint64_t)d->Q * d->K * 4,
-                       (uint64_t)d->P * d->Q * d->K * 4};
+    uint64_t dims[5] = {(uint64_t)Kp, (uint64_t)d->Q, 1, (uint64_t)d->P, (uint64_t)d->N};
+    uint64_t str[4] = {(uint64_t)Kp * 4, (uint64_t)d->Q * Kp * 4, (uint64_t)d->Q * Kp * 4,
+                       (uint64_t)d->P * d->Q * Kp * 4};
     uint32_t box[5] = {32, bw, 1, bh, bn};
     if (int e = encode_map(&mdy, dy, 5, dims, str, box, swz)) return e;
   }
@@ -746,7 +775,7 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
       if (d->stride == 1) p.taps[r * d->S + s] = make_int4(0, b, 0, a);
       else p.taps[r * d->S + s] = make_int4((((b % 2) + 2) % 2) * C, floordiv2(b), ((a % 2) + 2) % 2, floordiv2(a));
     }
-  float* out = w.splits > 1 ? (float*)ws : dw;
+  float* out = w.splits > 1 ? part : dw;
   dim3 grid(w.tiles_k * w.tiles_c, T, w.splits);
   int e;
   switch (w.BN) {
@@ -756,7 +785,7 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
     default:  e = launch_wgrad_bn<32>(mdy, mx, p, out, grid, st); break;
   }
   if (e) return e;
-  if (w.splits > 1) splitk_reduce_launch((const float*)ws, dw, (long long)d->K * T * C, w.splits, st);
+  if (w.splits > 1) splitk_reduce_launch(part, dw, (long long)d->K * T * C, w.splits, st);
   SRGAN_RETURN_LAUNCH();
 }
 

@@ -293,6 +293,9 @@ struct UmmaWgradP {
   int K, C, T;                   // dW[K][T][C]
   long long split_stride;        // elements between partial results
   unsigned long long desc_hi;    // descriptor bits above the start address (LBO, SBO, version, layout type)
+  int ntapn;                     // > 0: "taps as N" mode -- the N dimension is ntapn blocks of 32 packed columns,
+                                 //      block j loaded with taps[j] (thin-tensor wgrad, see conv_wgrad_thin_launch)
+  unsigned int idesc;            // instruction descriptor override for that mode (N = 32 * ntapn)
   int4 taps[kMaxTaps];           // {channel offset, dw, hp, dh} of x for each filter tap
 };
 
@@ -348,6 +351,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       const int4 tp = p.taps[tap];
+      const int nbx = p.ntapn > 0 ? p.ntapn : BN / 32;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -358,17 +362,25 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int q0 = tw * bw, p0 = th * bh, n0 = tn * bn;
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
-        mbar_expect_tx(full + stage, Cfg::kStageBytes);
+        mbar_expect_tx(full + stage, kABytes + nbx * 4096);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_5d(&map_dy, full + stage, sa + j * 4096, k0 + 32 * j, q0, 0, p0, n0);
+        if (p.ntapn > 0) {
+          for (int j = 0; j < nbx; ++j) {
+            const int4 tj = p.taps[j];
+            tma_load_5d(&map_x, full + stage, sa + kABytes + j * 4096, tj.x, q0 + tj.y, tj.z, p0 + tj.w, n0);
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          tma_load_5d(&map_x, full + stage, sa + kABytes + j * 4096, c0 + 32 * j + tp.x, q0 + tp.y, tp.z, p0 + tp.w, n0);
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_5d(&map_x, full + stage, sa + kABytes + j * 4096, c0 + 32 * j + tp.x, q0 + tp.y, tp.z, p0 + tp.w, n0);
+        }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      const uint32_t idesc = p.ntapn > 0 ? p.idesc : kIdescMN;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -379,7 +391,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const uint64_t bdesc = p.desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
 #pragma unroll
         for (int k = 0; k < 4; ++k)       // 4 x 8 pixels; 8 pixel rows = 1024 B further (+64 in the address field)
-          umma_tf32(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), kIdescMN, (it | k) != 0);
+          umma_tf32(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it | k) != 0);
         umma_commit(empty + stage);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -501,14 +513,17 @@ struct Problem {
   UmmaConvP p;               // taps / classes prefilled
 };
 
-static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st) {
+static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st,
+                       const CUtensorMap* ma_prebuilt = nullptr) {
   if (((uintptr_t)pr.act | (uintptr_t)pr.filt | (uintptr_t)y) % 16) {
     set_error("tcgen05 conv: tensors must be 16-byte aligned");
     return SRGAN_E_BADARG;
   }
   CUtensorMap ma, mb;
   const int C = pr.aC;
-  if (pr.a_stride == 1) {
+  if (ma_prebuilt) {
+    ma = *ma_prebuilt;            // caller picked the box with pick_box(pr.P, pr.Q) and filled pr.p.lw / lh
+  } else if (pr.a_stride == 1) {
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)pr.aW, 1, (uint64_t)pr.aH, (uint64_t)pr.aN};
     uint64_t str[4] = {(uint64_t)C * 4, (uint64_t)pr.aW * C * 4, (uint64_t)pr.aW * C * 4,
                        (uint64_t)pr.aH * pr.aW * C * 4};
@@ -547,10 +562,167 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ thin tensors
+// Convolutions with <= 4 channels on one side (RGB stems and heads) would waste the tensor core on a
+// 3-wide GEMM dimension.  They are run "row-packed" instead: the thin tensor is copied once into a zero-
+// padded NHWC4 buffer TP[N][Hp][Wp][4]; for a filter row r the S taps x 4 channels of one output pixel are
+// then 4*S CONTIGUOUS floats, so a TMA map whose pixel stride (16 B * conv stride) is smaller than its
+// 32-float inner box delivers im2col rows  A_r[pixel][j = s*4 + c]  straight into the swizzled smem layout.
+// The GEMM reduction per filter row is one 32-wide chunk (S <= 8), i.e. R "taps" of 32 "channels".
+//   fprop, thin input  (C <= 4)             y  = sum_r A_r(xpad)  . Bp[k][r][s*4+c]
+//   dgrad, thin dy     (K <= 4, stride 1)   dx = sum_r' A_r'(dypad) . Bp[c][r'][s'*4+k]   (flipped filter)
+//   wgrad, thin x      (C <= 4)             out[k][r][s*4+c]   = sum_pix dy[pix][k] A_r(xpad)[pix][.]
+//   wgrad, thin dy     (K <= 4, stride 1)   out[c][r'][s'*4+k] = sum_pix x[pix][c]  A_r'(dypad)[pix][.]
+// The wgrad forms run wgrad_umma_kernel in "taps as N" mode: all R filter rows are N-blocks of ONE MMA, so
+// the fat tensor is read exactly once.
+struct ThinPlan {
+  int mode;                 // 0: the thin tensor is the conv input x ; 1: it is dy (flipped taps)
+  int st;                   // pixel stride of the packed view (conv stride, 1 for mode 1)
+  int tc, tH, tW;           // thin tensor [N][tH][tW][tc]
+  int padH, padW;           // physical zero padding of TP (top/left)
+  int Hp, Wp;
+  int fH, fW, fC;           // fat tensor [N][fH][fW][fC] == the pixel grid of the GEMM
+  int R, S, N;
+};
+
+static bool thin_fits(const srgan_conv_desc* d) { return d->S * 4 <= 32 && d->R <= 8 && (d->stride == 1 || d->stride == 2); }
+
+static bool thin_plan(const srgan_conv_desc* d, int pass, ThinPlan* t) {
+  if (!thin_fits(d)) return false;
+  const bool thin_in = d->C <= 4, thin_out = d->K <= 4;
+  ThinPlan q = {};
+  q.R = d->R; q.S = d->S; q.N = d->N;
+  if (pass == 0 || (pass == 2 && thin_in)) {
+    if (!thin_in) return false;
+    q.mode = 0; q.st = d->stride; q.tc = d->C; q.tH = d->H; q.tW = d->W; q.padH = q.padW = d->pad;
+    q.fH = d->P; q.fW = d->Q; q.fC = d->K;
+    if (pass == 2 && d->K % 4) return false;
+  } else {
+    if (!thin_out || d->stride != 1 || d->pad > d->R - 1 || d->pad > d->S - 1) return false;
+    q.mode = 1; q.st = 1; q.tc = d->K; q.tH = d->P; q.tW = d->Q; q.padH = d->R - 1 - d->pad; q.padW = d->S - 1 - d->pad;
+    q.fH = d->H; q.fW = d->W; q.fC = d->C;
+    if (d->C % 4) return false;
+  }
+  if (pass == 2 && q.fC > 128) return false;            // one 128-row accumulator tile
+  int hp = q.tH + 2 * q.padH, need_h = (q.fH - 1) * q.st + q.R;
+  if (need_h > hp) hp = need_h;
+  q.Hp = (hp + q.st - 1) / q.st * q.st;
+  int wp = q.tW + 2 * q.padW, need_w = (q.fW - 1) * q.st + 8;
+  q.Wp = need_w > wp ? need_w : wp;
+  *t = q;
+  return true;
+}
+
+// TP[n][hp][wp][0..3] = thin[n][hp - padH][wp - padW][0..tc) or 0
+__global__ void thin_pad_kernel(const float* __restrict__ src, float4* __restrict__ dst, int N, int tH, int tW, int tc,
+                                int Hp, int Wp, int padH, int padW) {
+  const size_t total = (size_t)N * Hp * Wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp);
+    const size_t t = i / Wp;
+    const int hp = (int)(t % Hp);
+    const int n = (int)(t / Hp);
+    const int h = hp - padH, w = wp - padW;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < tH && w >= 0 && w < tW) {
+      const float* s = src + (((size_t)n * tH + h) * tW + w) * tc;
+      for (int c = 0; c < tc; ++c) v[c] = __ldg(s + c);
+    }
+    dst[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// mode 0: bp[k][r][s*4+c]  = w[k][r][s][c]                 (rows = K)
+// mode 1: bp[c][r'][s'*4+k] = w[k][R-1-r'][S-1-s'][c]       (rows = C)
+__global__ void thin_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ bp, int K, int C, int R, int S,
+                                        int mode) {
+  const int rows = mode == 0 ? K : C;
+  const int total = rows * R * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i & 31, r = (i >> 5) % R, row = i / (32 * R);
+    const int s = j >> 2, t = j & 3;
+    float v = 0.f;
+    if (s < S) {
+      if (mode == 0) { if (t < C) v = w[(((size_t)row * R + r) * S + s) * C + t]; }
+      else           { if (t < K) v = w[(((size_t)t * R + (R - 1 - r)) * S + (S - 1 - s)) * C + row]; }
+    }
+    bp[i] = v;
+  }
+}
+
+// dw[k][r][s][c] = sum over splits of  part[.][k][r][s*4+c]  (mode 0)  or  part[.][c][R-1-r][(S-1-s)*4+k]  (mode 1)
+__global__ void thin_unpack_wgrad_kernel(const float* __restrict__ part, float* __restrict__ dw, int K, int C, int R, int S,
+                                         int mode, int splits, long long split_stride) {
+  const int total = K * R * S * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, s = (i / C) % S, r = (i / (C * S)) % R, k = i / (C * S * R);
+    const size_t src = mode == 0 ? (((size_t)k * R + r) * 32 + s * 4 + c)
+                                 : (((size_t)c * R + (R - 1 - r)) * 32 + (S - 1 - s) * 4 + k);
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += part[(size_t)z * split_stride + src];
+    dw[i] = acc;
+  }
+}
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static void thin_box(int fH, int fW, int pixels, int* lw, int* lh) {   // pow2 box bw x bh x bn = pixels
+  int w = 1 << ilog2(fW);
+  if (w > pixels) w = pixels;
+  int h = 1 << ilog2(fH);
+  if (h > pixels / w) h = pixels / w;
+  *lw = ilog2(w); *lh = ilog2(h);
+}
+
+static int thin_map(CUtensorMap* m, const float* tp, const ThinPlan& t, int lw, int lh, int pixels, CUtensorMapSwizzle swz) {
+  // {32 packed floats, fat column (stride st pixels), row parity, fat row, image}; strides overlap on purpose
+  uint64_t dims[5] = {32, (uint64_t)t.fW, (uint64_t)t.st, (uint64_t)(t.Hp / t.st), (uint64_t)t.N};
+  uint64_t str[4] = {(uint64_t)t.st * 16, (uint64_t)t.Wp * 16, (uint64_t)t.st * t.Wp * 16, (uint64_t)t.Hp * t.Wp * 16};
+  uint32_t box[5] = {32, 1u << lw, 1, 1u << lh, (uint32_t)pixels >> (lw + lh)};
+  return encode_map(m, tp, 5, dims, str, box, swz);
+}
+
+static size_t thin_tp_bytes(const ThinPlan& t) { return align256((size_t)t.N * t.Hp * t.Wp * 16); }
+
+static int thin_pad_launch(const ThinPlan& t, const float* thin, float* tp, cudaStream_t st) {
+  const size_t total = (size_t)t.N * t.Hp * t.Wp;
+  unsigned blocks = (unsigned)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+  thin_pad_kernel<<<blocks, 256, 0, st>>>(thin, (float4*)tp, t.N, t.tH, t.tW, t.tc, t.Hp, t.Wp, t.padH, t.padW);
+  SRGAN_RETURN_LAUNCH();
+}
+
+// y = act(conv(x) + bias) with thin x (pass 0)  /  dx = conv_transpose(dy) with thin dy (pass 1)
+static int conv_thin_fwdlike_launch(const srgan_conv_desc* d, int pass, const float* thin, const float* w,
+                                    const float* bias, float* out, int act, float slope, void* ws, size_t ws_bytes,
+                                    cudaStream_t st) {
+  ThinPlan t;
+  if (!thin_plan(d, pass, &t)) { set_error("thin conv: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  const size_t tpb = thin_tp_bytes(t), bpb = align256((size_t)t.fC * t.R * 32 * sizeof(float));
+  if (!ws || ws_bytes < tpb + bpb) { set_error("thin conv: workspace %zu < %zu", ws_bytes, tpb + bpb); return SRGAN_E_WORKSPACE; }
+  float* tp = (float*)ws;
+  float* bp = (float*)((uint8_t*)ws + tpb);
+  if (int e = thin_pad_launch(t, thin, tp, st)) return e;
+  thin_pack_filter_kernel<<<ceil_div(t.fC * t.R * 32, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
+  Problem pr = {};
+  pr.act = tp; pr.aN = t.N; pr.aH = t.Hp; pr.aW = t.Wp; pr.aC = 32; pr.a_stride = 1;
+  pr.filt = bp; pr.fK = t.fC; pr.T = t.R;
+  pr.Nn = t.N; pr.P = t.fH; pr.Q = t.fW; pr.out_H = t.fH; pr.out_W = t.fW; pr.os = 1; pr.ncls = 1;
+  UmmaConvP& p = pr.p;
+  p.tap_begin[0] = 0; p.tap_begin[1] = t.R;
+  for (int r = 0; r < t.R; ++r) p.taps[r] = make_int4(0, 0, (r % t.st) | (r << 8), r / t.st);
+  p.cls_oph[0] = 0; p.cls_opw[0] = 0;
+  pick_box(pr.P, pr.Q, &p.lw, &p.lh);
+  CUtensorMap ma;
+  if (int e = thin_map(&ma, tp, t, p.lw, p.lh, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  return run_problem(pr, bias, out, act, slope, st, &ma);
+}
+
 static inline int floordiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
 bool conv_umma_supported(const srgan_conv_desc* d, int pass) {
   if (d->N < 1) return false;
+  { ThinPlan t; if (thin_plan(d, pass, &t)) return true; }
   if (pass == 0) {
     if (d->C % 32) return false;
     if (d->R * d->S > kMaxTaps) return false;
@@ -609,7 +781,10 @@ static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
   return w;
 }
 
+static size_t thin_workspace(const srgan_conv_desc* d, int pass, const ThinPlan& t);
+
 size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
+  { ThinPlan t; if (thin_plan(d, pass, &t)) return thin_workspace(d, pass, t); }
   if (pass == 1) return (size_t)d->K * d->R * d->S * d->C * sizeof(float);   // transposed filter
   if (pass == 2) {
     WgradPlan w = plan_wgrad(d);
@@ -622,7 +797,8 @@ size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
 }
 
 int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                           int act, float slope, void*, size_t, cudaStream_t st) {
+                           int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  { ThinPlan t; if (thin_plan(d, 0, &t)) return conv_thin_fwdlike_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st); }
   Problem pr = {};
   pr.act = x; pr.aN = d->N; pr.aH = d->H; pr.aW = d->W; pr.aC = d->C; pr.a_stride = d->stride;
   pr.filt = w; pr.fK = d->K; pr.T = d->R * d->S;
@@ -649,6 +825,7 @@ int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float
 
 int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
                            size_t ws_bytes, cudaStream_t st) {
+  { ThinPlan t; if (thin_plan(d, 1, &t)) return conv_thin_fwdlike_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st); }
   const int T = d->R * d->S;
   size_t need = (size_t)d->K * T * d->C * sizeof(float);
   if (ws_bytes < need || !ws) { set_error("conv dgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
@@ -709,8 +886,90 @@ static int launch_wgrad_bn(const CUtensorMap& mdy, const CUtensorMap& mx, const 
   SRGAN_RETURN_LAUNCH();
 }
 
+
+// ---- thin wgrad: out[row][r][32] = sum_pix fat[pix][row] * A_r(TP)[pix][.]  (rows = fat channels <= 128)
+struct ThinWgradPlan { int BN, lw, lh, tiles_w, tiles_h, tiles_n, chunks, cps, splits; };
+
+static ThinWgradPlan plan_thin_wgrad(const ThinPlan& t) {
+  ThinWgradPlan w;
+  w.BN = t.R * 32 > 128 ? 256 : (t.R * 32 > 64 ? 128 : (t.R * 32 > 32 ? 64 : 32));
+  thin_box(t.fH, t.fW, 32, &w.lw, &w.lh);
+  const int bw = 1 << w.lw, bh = 1 << w.lh, bn = 32 / (bw * bh);
+  w.tiles_w = ceil_div(t.fW, bw); w.tiles_h = ceil_div(t.fH, bh); w.tiles_n = ceil_div(t.N, bn);
+  w.chunks = w.tiles_w * w.tiles_h * w.tiles_n;
+  int splits = w.chunks < kNumSMs ? w.chunks : kNumSMs;     // one resident CTA per SM, every CTA the full tile
+  w.cps = ceil_div(w.chunks, splits);
+  w.splits = ceil_div(w.chunks, w.cps);
+  return w;
+}
+
+static size_t thin_workspace(const srgan_conv_desc* d, int pass, const ThinPlan& t) {
+  size_t b = thin_tp_bytes(t);
+  if (pass != 2) return b + align256((size_t)t.fC * t.R * 32 * sizeof(float));
+  ThinWgradPlan w = plan_thin_wgrad(t);
+  b += align256((size_t)w.splits * t.fC * t.R * 32 * sizeof(float));
+  b += (size_t)kColsumBlocks * d->K * sizeof(float);
+  return b;
+}
+
+static int conv_wgrad_thin_launch(const srgan_conv_desc* d, const ThinPlan& t, const float* x, const float* dy,
+                                  float* dw, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const ThinWgradPlan w = plan_thin_wgrad(t);
+  const size_t need = thin_workspace(d, 2, t);
+  if (need > ws_bytes || !ws) { set_error("thin wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)ws) % 16) {
+    set_error("thin wgrad: tensors must be 16-byte aligned");
+    return SRGAN_E_BADARG;
+  }
+  const size_t row_elems = (size_t)t.R * 32, part_elems = (size_t)t.fC * row_elems;
+  float* tp = (float*)ws;
+  float* part = (float*)((uint8_t*)ws + thin_tp_bytes(t));
+  float* csum = (float*)((uint8_t*)part + align256((size_t)w.splits * part_elems * sizeof(float)));
+  if (dbias) {
+    if (int e = colsum_launch(dy, dbias, (long long)d->N * d->P * d->Q, d->K, csum, kColsumBlocks, st)) return e;
+  }
+  if (!dw) return SRGAN_OK;
+  const float* thin = t.mode == 0 ? x : dy;
+  const float* fat = t.mode == 0 ? dy : x;
+  if (int e = thin_pad_launch(t, thin, tp, st)) return e;
+  CUtensorMap mfat, mthin;
+  const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = 32u / (bw * bh);
+  {
+    uint64_t dims[5] = {(uint64_t)t.fC, (uint64_t)t.fW, 1, (uint64_t)t.fH, (uint64_t)t.N};
+    uint64_t str[4] = {(uint64_t)t.fC * 4, (uint64_t)t.fW * t.fC * 4, (uint64_t)t.fW * t.fC * 4,
+                       (uint64_t)t.fH * t.fW * t.fC * 4};
+    uint32_t box[5] = {32, bw, 1, bh, bn};
+    if (int e = encode_map(&mfat, fat, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  }
+  if (int e = thin_map(&mthin, tp, t, w.lw, w.lh, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  UmmaWgradP p = {};
+  p.tiles_c = 1; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
+  p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
+  p.K = t.fC; p.C = (int)row_elems; p.T = 1;
+  p.split_stride = (long long)part_elems;
+  p.desc_hi = mn_desc_hi(4096, 512, 1);
+  p.ntapn = t.R;
+  // D=f32, A=B=tf32, both MN-major, N = 32*R, M = 128
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((t.R * 32) >> 3) << 17) |
+            ((128u >> 4) << 24);
+  for (int r = 0; r < t.R; ++r) p.taps[r] = make_int4(0, 0, r % t.st, r / t.st);
+  dim3 grid(1, 1, w.splits);
+  int e;
+  switch (w.BN) {
+    case 256: e = launch_wgrad_bn<256>(mfat, mthin, p, part, grid, st); break;
+    case 128: e = launch_wgrad_bn<128>(mfat, mthin, p, part, grid, st); break;
+    case 64:  e = launch_wgrad_bn<64>(mfat, mthin, p, part, grid, st); break;
+    default:  e = launch_wgrad_bn<32>(mfat, mthin, p, part, grid, st); break;
+  }
+  if (e) return e;
+  thin_unpack_wgrad_kernel<<<ceil_div(d->K * d->R * d->S * d->C, 256), 256, 0, st>>>(
+      part, dw, d->K, d->C, d->R, d->S, t.mode, w.splits, (long long)part_elems);
+  SRGAN_RETURN_LAUNCH();
+}
+
 int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                            void* ws, size_t ws_bytes, cudaStream_t st) {
+  { ThinPlan t; if (thin_plan(d, 2, &t)) return conv_wgrad_thin_launch(d, t, x, dy, dw, dbias, ws, ws_bytes, st); }
   const WgradPlan w = plan_wgrad(d);
   const int T = d->R * d->S;
   const size_t need = conv_umma_workspace(d, 2);

@@ -45,6 +45,14 @@ GEOMS = [
     ("D2.c3", 2, 128, 8, 8, 256, 4, 2, 1, False),
     ("D.patch", 2, 512, 8, 8, 1, 4, 1, 1, True),
     ("D.class", 2, 512, 8, 8, 4, 8, 1, 0, True),
+    # thin (<= 4 channel) tensors: row-packed im2col through an overlapping-stride TMA map
+    ("G.stem", 2, 3, 128, 128, 64, 7, 1, 3, False),
+    ("E.stem", 2, 3, 128, 128, 64, 7, 2, 1, True),
+    ("D.stem", 3, 3, 128, 128, 64, 4, 2, 1, False),
+    ("D2.stem", 2, 3, 64, 64, 32, 4, 2, 1, False),
+    ("thin.odd", 3, 2, 37, 29, 32, 5, 1, 2, True),
+    ("thin.odd.s2", 2, 4, 30, 22, 40, 3, 2, 1, False),
+    ("thin.out.odd", 2, 32, 19, 27, 2, 5, 1, 2, True),
 ]
 
 

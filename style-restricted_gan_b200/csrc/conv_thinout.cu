@@ -1,0 +1,284 @@
+// Stride-1 convolutions whose OUTPUT has <= 4 channels (the generator's RGB head, and the input gradient of its
+// RGB stem): tcgen05 row-GEMM + in-CTA col2im.  sm_100a only.
+//
+//   out[h][q][t] = sum_{r,s,f} in[h + r - padH][q + s - padW][f] * Wt[(r,s,t)][f]
+//
+// A direct implicit GEMM has N = 3 and re-reads the fat input once per tap (49x for the 7x7 head).  Instead each
+// input image row h' is multiplied ONCE by the whole packed filter
+//   Z_h'[q'][(r, s*4+t)] = sum_f in[h'][q'][f] * Bp[r*32 + s*4 + t][f]          (M = 128 pixels, N = 32*R, K = C)
+// with the accumulator in tensor memory (double buffered), and the epilogue warps scatter-free "col2im" it:
+//   out[h][q][t] = sum_r sum_s Z_{h+r-padH}[q + s - padW][(r, s*4+t)]
+// The column shift crosses lanes, so every 32-column block of Z goes through a transposed shared-memory
+// staging buffer; the row shift is a ring of R partial output rows held in registers (a CTA walks down a band
+// of rows, so each input row is read from global memory once per band).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2..5 epilogue.
+#include "umma_ptx.cuh"
+
+namespace srgan {
+
+constexpr int kTOThreads = 192;
+constexpr int kTOStages = 3;
+constexpr int kTOZRow = 144;                 // floats per staging row: 128 pixels + margins (pad <= 8 each side)
+constexpr int kTOZBuf = 32 * kTOZRow;        // one staging buffer: 32 packed columns
+
+struct ThinOutP {
+  int Hi, Wi, Ho, Wo;
+  int tc, R, S, padH, padW;
+  int nchunks;                   // input channels / 32
+  int bands, BH;                 // row bands per image, rows per band
+  int act;
+  float slope;
+  unsigned int idesc;
+};
+
+__global__ void __launch_bounds__(kTOThreads, 1)
+conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ ThinOutP p, const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  // (offset arithmetic on the __shared__ symbol keeps the address space visible: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int b_bytes = p.nchunks * p.R * 4096;           // packed filter: per chunk R*32 rows of 128 B
+  const int a_bytes = p.nchunks * 16384;                // one input row: per chunk 128 pixels of 128 B
+  uint8_t* sb = smem;
+  uint8_t* sa = smem + b_bytes;
+  float* zs = reinterpret_cast<float*>(sa + kTOStages * a_bytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(zs + 2 * kTOZBuf);
+  uint64_t* a_empty = a_full + kTOStages;
+  uint64_t* t_full = a_empty + kTOStages;               // [2]
+  uint64_t* t_empty = t_full + 2;                       // [2]
+  uint64_t* b_full = t_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x / p.bands, band = blockIdx.x % p.bands;
+  const int h0 = band * p.BH, h1 = min(p.Ho, h0 + p.BH);
+  const int hp_beg = h0 - p.padH, hp_end = (h1 - 1) - p.padH + (p.R - 1);     // inclusive range of input rows
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTOStages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4); }
+    mbar_init(b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * kTOZBuf; i += kTOThreads) zs[i] = 0.f;     // margins stay zero
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, b_bytes);
+      for (int j = 0; j < p.nchunks; ++j) tma_load_2d(&map_b, b_full, sb + j * p.R * 4096, 32 * j, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int hp = hp_beg; hp <= hp_end; ++hp) {
+        if (hp < 0 || hp >= p.Hi) continue;
+        mbar_wait(a_empty + stage, phase ^ 1);
+        uint8_t* dst = sa + stage * a_bytes;
+        mbar_expect_tx(a_full + stage, a_bytes);
+        for (int j = 0; j < p.nchunks; ++j) tma_load_4d(&map_in, a_full + stage, dst + j * 16384, 32 * j, 0, hp, n);
+        if (++stage == kTOStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      int stage = 0, i = 0;
+      uint32_t phase = 0;
+      for (int hp = hp_beg; hp <= hp_end; ++hp) {
+        if (hp < 0 || hp >= p.Hi) continue;
+        const int buf = i & 1;
+        mbar_wait(a_full + stage, phase);
+        mbar_wait(t_empty + buf, ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sa + stage * a_bytes), b0 = smem_u32(sb);
+        for (int j = 0; j < p.nchunks; ++j) {
+          const uint64_t adesc = smem_desc_sw128(a0 + j * 16384);
+          const uint64_t bdesc = smem_desc_sw128(b0 + j * p.R * 4096);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + buf * 256, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (j | k) != 0);
+        }
+        umma_commit(a_empty + stage);
+        umma_commit(t_full + buf);
+        if (++stage == kTOStages) { stage = 0; phase ^= 1; }
+        ++i;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int qq = quad * 32 + lane;                    // TMEM lane == input pixel q' == output pixel q
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float acc[8][4];                                    // acc[7 - r] collects filter row r; acc[8 - R] completes first
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[a][t] = 0.f;
+    float bv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) bv[t] = (bias && t < p.tc) ? __ldg(bias + t) : 0.f;
+    int i = 0, zi = 0;
+    for (int hp = hp_beg; hp <= hp_end; ++hp) {
+      if (hp >= 0 && hp < p.Hi) {
+        const int buf = i & 1;
+        mbar_wait(t_full + buf, (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int h = hp - r + p.padH;
+          if (r < p.R && h >= h0 && h < h1) {           // uniform over the CTA
+            float v[32];
+            tmem_ld32(taddr + buf * 256 + r * 32, v);
+            float* zb = zs + (zi & 1) * kTOZBuf;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < p.S * 4) zb[j * kTOZRow + p.padW + qq] = v[j];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              if (s < p.S) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (t < p.tc) acc[7 - r][t] += zb[(s * 4 + t) * kTOZRow + qq + s];
+              }
+            ++zi;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + buf);
+        ++i;
+      }
+      // output row hp + padH - (R-1) has now received all of its filter rows
+      const int hd = hp + p.padH - (p.R - 1);
+      if (hd >= h0 && hd < h1 && qq < p.Wo) {
+        float* o = out + (((size_t)n * p.Ho + hd) * p.Wo + qq) * p.tc;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          if (a == 8 - p.R) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (t < p.tc) o[t] = apply_act(acc[a][t] + bv[t], p.act, p.slope);
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < 7; ++a)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[a][t] = acc[a + 1][t];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[7][t] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// mode 0 (fprop, K <= 4):  bp[r*32 + s*4 + k][c] = w[k][r][s][c]                    rows of C floats
+// mode 1 (dgrad, C <= 4):  bp[r'*32 + s'*4 + c][k] = w[k][R-1-r'][S-1-s'][c]        rows of K floats
+__global__ void thinout_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ bp, int K, int C, int R,
+                                           int S, int mode) {
+  const int F = mode == 0 ? C : K, tc = mode == 0 ? K : C;
+  const int total = R * 32 * F;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int f = i % F, j = (i / F) & 31, r = i / (F * 32);
+    const int s = j >> 2, t = j & 3;
+    float v = 0.f;
+    if (s < S && t < tc) {
+      if (mode == 0) v = w[(((size_t)t * R + r) * S + s) * C + f];
+      else           v = w[(((size_t)f * R + (R - 1 - r)) * S + (S - 1 - s)) * C + t];
+    }
+    bp[i] = v;
+  }
+}
+
+struct ThinOutPlan { int mode, Hi, Wi, Ho, Wo, F, tc, padH, padW, bands, BH; };
+
+static bool thinout_plan(const srgan_conv_desc* d, int pass, ThinOutPlan* t) {
+  if (d->stride != 1 || d->S * 4 > 32 || d->R > 8 || d->N < 1) return false;
+  ThinOutPlan q = {};
+  if (pass == 0) {
+    if (d->K > 4) return false;
+    q.mode = 0; q.Hi = d->H; q.Wi = d->W; q.Ho = d->P; q.Wo = d->Q; q.F = d->C; q.tc = d->K;
+    q.padH = q.padW = d->pad;
+  } else if (pass == 1) {
+    if (d->C > 4 || d->pad > d->R - 1 || d->pad > d->S - 1) return false;
+    q.mode = 1; q.Hi = d->P; q.Wi = d->Q; q.Ho = d->H; q.Wo = d->W; q.F = d->K; q.tc = d->C;
+    q.padH = d->R - 1 - d->pad; q.padW = d->S - 1 - d->pad;
+  } else {
+    return false;
+  }
+  if (q.F != 32 && q.F != 64) return false;
+  if (q.Wi > 128 || q.Wo > 128 || q.padW > 8) return false;
+  // rows per band: minimise  waves x (rows + halo) over one-CTA-per-SM waves
+  long best = -1;
+  for (int b = 1; b <= q.Ho; ++b) {
+    int bh = ceil_div(q.Ho, b);
+    if (ceil_div(q.Ho, bh) != b) continue;
+    long waves = ((long)d->N * b + kNumSMs - 1) / kNumSMs;
+    long cost = waves * (bh + d->R - 1 + 4);
+    if (best < 0 || cost < best) { best = cost; q.bands = b; q.BH = bh; }
+  }
+  *t = q;
+  return true;
+}
+
+bool conv_thinout_supported(const srgan_conv_desc* d, int pass) {
+  ThinOutPlan t;
+  return thinout_plan(d, pass, &t);
+}
+
+size_t conv_thinout_workspace(const srgan_conv_desc* d, int pass) {
+  ThinOutPlan t;
+  if (!thinout_plan(d, pass, &t)) return 0;
+  return (size_t)d->R * 32 * t.F * sizeof(float);
+}
+
+// pass 0: in = x, out = y (bias/activation fused);  pass 1: in = dy, out = dx
+int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, const float* w, const float* bias,
+                        float* out, int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  ThinOutPlan t;
+  if (!thinout_plan(d, pass, &t)) { set_error("thin-output conv: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  const size_t need = conv_thinout_workspace(d, pass);
+  if (!ws || ws_bytes < need) { set_error("thin-output conv: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  if (((uintptr_t)in | (uintptr_t)ws) % 16) { set_error("thin-output conv: tensors must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  float* bp = (float*)ws;
+  thinout_pack_filter_kernel<<<ceil_div(d->R * 32 * t.F, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
+  CUtensorMap min, mb;
+  {
+    uint64_t dims[4] = {(uint64_t)t.F, (uint64_t)t.Wi, (uint64_t)t.Hi, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)t.F * 4, (uint64_t)t.Wi * t.F * 4, (uint64_t)t.Hi * t.Wi * t.F * 4};
+    uint32_t box[4] = {32, 128, 1, 1};
+    if (int e = encode_map(&min, in, 4, dims, str, box)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)t.F, (uint64_t)d->R * 32};
+    uint64_t str[1] = {(uint64_t)t.F * 4};
+    uint32_t box[2] = {32, (uint32_t)d->R * 32};
+    if (int e = encode_map(&mb, bp, 2, dims, str, box)) return e;
+  }
+  ThinOutP p = {};
+  p.Hi = t.Hi; p.Wi = t.Wi; p.Ho = t.Ho; p.Wo = t.Wo; p.tc = t.tc; p.R = d->R; p.S = d->S;
+  p.padH = t.padH; p.padW = t.padW; p.nchunks = t.F / 32; p.bands = t.bands; p.BH = t.BH;
+  p.act = act; p.slope = slope;
+  // D = f32, A = B = tf32, both K-major, N = 32*R, M = 128
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((d->R * 32) >> 3) << 17) | ((128u >> 4) << 24);
+  const size_t smem = 1024 + (size_t)p.nchunks * d->R * 4096 + (size_t)kTOStages * p.nchunks * 16384 +
+                      2 * kTOZBuf * sizeof(float) + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_thinout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("conv_thinout smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  conv_thinout_kernel<<<d->N * t.bands, kTOThreads, smem, st>>>(min, mb, p, bias, out);
+  SRGAN_RETURN_LAUNCH();
+}
+
+}  // namespace srgan

@@ -18,9 +18,7 @@
 //   dgrad stride 2 /      4 output-parity classes (blockIdx.z), each a 2x2-tap stride-1 problem on dy,
 //   conv-transpose fwd    written to every second output pixel
 #include <stdlib.h>
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace srgan {
 
@@ -42,108 +40,6 @@ struct UmmaConvP {
   int tap_begin[5];
   int4 taps[kMaxTaps];           // {channel offset, dw, hp | (filter tap << 8), dh}
 };
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 28)) __trap();      // a lost arrive must fail loudly, never hang the GPU
-  }
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                            int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
-  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-  return d;
-}
 
 template <int BN>
 struct UmmaCfg {
@@ -443,30 +339,6 @@ __global__ void filter_transpose_kernel(const float* __restrict__ w, float* __re
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
-  }
-  return fn;
-}
-
-static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                      const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  auto enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SRGAN_E_UNSUPPORTED; }
-  uint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SRGAN_E_BADARG; }
-  return SRGAN_OK;
-}
-
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // choose the pixel box (bw x bh x bn = 128, powers of two) covering a P x Q grid
@@ -720,8 +592,15 @@ static int conv_thin_fwdlike_launch(const srgan_conv_desc* d, int pass, const fl
 
 static inline int floordiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
+// conv_thinout.cu
+bool conv_thinout_supported(const srgan_conv_desc* d, int pass);
+size_t conv_thinout_workspace(const srgan_conv_desc* d, int pass);
+int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, const float* w, const float* bias,
+                        float* out, int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+
 bool conv_umma_supported(const srgan_conv_desc* d, int pass) {
   if (d->N < 1) return false;
+  if (conv_thinout_supported(d, pass)) return true;
   { ThinPlan t; if (thin_plan(d, pass, &t)) return true; }
   if (pass == 0) {
     if (d->C % 32) return false;
@@ -784,6 +663,7 @@ static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
 static size_t thin_workspace(const srgan_conv_desc* d, int pass, const ThinPlan& t);
 
 size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
+  if (conv_thinout_supported(d, pass)) return conv_thinout_workspace(d, pass);
   { ThinPlan t; if (thin_plan(d, pass, &t)) return thin_workspace(d, pass, t); }
   if (pass == 1) return (size_t)d->K * d->R * d->S * d->C * sizeof(float);   // transposed filter
   if (pass == 2) {
@@ -798,6 +678,7 @@ size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
 
 int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                            int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (conv_thinout_supported(d, 0)) return conv_thinout_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st);
   { ThinPlan t; if (thin_plan(d, 0, &t)) return conv_thin_fwdlike_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st); }
   Problem pr = {};
   pr.act = x; pr.aN = d->N; pr.aH = d->H; pr.aW = d->W; pr.aC = d->C; pr.a_stride = d->stride;
@@ -825,6 +706,7 @@ int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float
 
 int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
                            size_t ws_bytes, cudaStream_t st) {
+  if (conv_thinout_supported(d, 1)) return conv_thinout_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st);
   { ThinPlan t; if (thin_plan(d, 1, &t)) return conv_thin_fwdlike_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st); }
   const int T = d->R * d->S;
   size_t need = (size_t)d->K * T * d->C * sizeof(float);

@@ -106,3 +106,15 @@ def test_fused_epilogue_tcgen05():
     y = ops.conv2d(x, w, b, 2, 1, "zeros", ops.ACT_LRELU, 0.01)
     ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), 2, 1), 0.01)
     assert _rel(y, ref) < TOL
+
+
+def test_thin_output_row_gemm_tanh_and_bands():
+    """RGB head (64 -> 3, 7x7) through the row-GEMM + col2im kernel: fused tanh, bias, several row bands,
+    width below the 128-pixel tile, batch large enough for more than one wave."""
+    for (N, C, H, W, K, R, pad) in ((5, 64, 40, 128, 3, 7, 3), (3, 32, 23, 50, 4, 3, 1), (160, 64, 8, 16, 1, 7, 3)):
+        x = _rand(N, C, H, W, seed=21).contiguous(memory_format=CL)
+        w = _rand(K, C, R, R, seed=22, scale=(C * R * R) ** -0.5).contiguous(memory_format=CL)
+        b = _rand(K, seed=23)
+        y = ops.conv2d(x, w, b, 1, pad, "zeros", ops.ACT_TANH, 0.0)
+        ref = torch.tanh(F.conv2d(x.double(), w.double(), b.double(), 1, pad))
+        assert _rel(y, ref) < TOL, (N, C, H, W, K, R, pad)

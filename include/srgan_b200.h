@@ -102,13 +102,16 @@ int srgan_reflect_pad_bwd(const float* dy, float* dx, int N, int H, int W, int C
  * srgan_inorm_param_grads turns (s1,s2) into dgamma, dbeta (accumulated over n in a fixed
  * order, overwritten) and dcbias[n][c].
  */
+size_t srgan_inorm_workspace(int N, int HW, int C);   /* bytes of slice-partial scratch for fwd and bwd */
 int srgan_inorm_fwd(const float* x, float* y, float* mean, float* rstd,
                     const float* gamma, const float* beta, const float* cbias, const float* residual,
-                    int N, int HW, int C, float eps, int act, float slope, void* stream);
+                    int N, int HW, int C, float eps, int act, float slope,
+                    void* workspace, size_t workspace_bytes, void* stream);
 int srgan_inorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const float* cbias,
                     float* dx, float* s1, float* s2,
-                    int N, int HW, int C, int act, float slope, void* stream);
+                    int N, int HW, int C, int act, float slope,
+                    void* workspace, size_t workspace_bytes, void* stream);
 int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma, const float* cbias,
                             float* dgamma, float* dbeta, float* dcbias, int N, int C, void* stream);
 

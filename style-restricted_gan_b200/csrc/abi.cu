@@ -22,6 +22,9 @@ int conv_dgrad_ffma_launch(const srgan_conv_desc*, const float*, const float*, f
 int conv_wgrad_ffma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
                            cudaStream_t);
 int colsum_launch(const float*, float*, long long, int, float*, int, cudaStream_t);
+bool conv_head_supported(const srgan_conv_desc* d);
+int conv_fprop_head_launch(const srgan_conv_desc*, const float*, const float*, const float*, float*, int, float,
+                           cudaStream_t);
 
 // conv_umma.cu (tcgen05 engine)
 bool conv_umma_supported(const srgan_conv_desc* d, int pass);
@@ -85,6 +88,8 @@ extern "C" int srgan_conv2d_fprop(const srgan_conv_desc* d, const float* x, cons
                                   void* stream) {
   if (int e = check_desc(d)) return e;
   SRGAN_CHECK_ARG(x && w && y, "null pointer");
+  if (engine != SRGAN_CONV_TF32 && dense_x(d) && conv_head_supported(d))      // long-reduction 1..4-logit heads
+    return conv_fprop_head_launch(d, x, w, bias, y, act, slope, (cudaStream_t)stream);
   int e = resolve_engine(d, 0, engine);
   if (e < 0) { set_error("conv fprop: shape not supported by the tcgen05 engine"); return e; }
   if (e == SRGAN_CONV_TF32)

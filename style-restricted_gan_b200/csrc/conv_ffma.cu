@@ -452,6 +452,57 @@ int conv_dgrad_ffma_launch(const srgan_conv_desc* d, const float* dy, const floa
   SRGAN_RETURN_LAUNCH();
 }
 
+// ------------------------------------------------------------------------------------ small-K heads
+// Discriminator heads (K = 1 patch logit, K = 4 class logits) have a long reduction (up to 64 taps x 512
+// channels) and very few output pixels: one block per output pixel, threads stride over the (tap, channel/4)
+// index space with float4 loads, fixed-order block reduction (deterministic).  Exact fp32.
+template <int KMAX>
+__global__ void __launch_bounds__(256) conv_fprop_head_kernel(ConvP d, const float* __restrict__ x,
+                                                              const float* __restrict__ w,
+                                                              const float* __restrict__ bias,
+                                                              float* __restrict__ y, int act, float slope) {
+  __shared__ float red[32];
+  const int pix = blockIdx.x;
+  const int q = pix % d.Q, pp = (pix / d.Q) % d.P, n = pix / (d.Q * d.P);
+  const int C4 = d.C >> 2, T = d.R * d.S;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int i = threadIdx.x; i < T * C4; i += blockDim.x) {
+    const int t = i / C4, c4 = i - t * C4;
+    const int r = t / d.S, s = t - r * d.S;
+    const int h = pp * d.stride - d.pad + r, ww = q * d.stride - d.pad + s;
+    if (h < 0 || h >= d.H || ww < 0 || ww >= d.W) continue;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * d.H + h) * d.W + ww) * d.C) + c4);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < d.K) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((size_t)k * T + t) * d.C) + c4);
+        acc[k] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[k]))));
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < d.K) {
+      const float v = block_sum(acc[k], red);
+      if (threadIdx.x == 0) y[(size_t)pix * d.K + k] = apply_act(v + (bias ? bias[k] : 0.f), act, slope);
+    }
+}
+
+bool conv_head_supported(const srgan_conv_desc* d) {
+  return d->K <= 4 && d->C % 4 == 0 && (long long)d->N * d->P * d->Q <= 65536 && d->R * d->S * d->C >= 1024;
+}
+
+int conv_fprop_head_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                           int act, float slope, cudaStream_t st) {
+  ConvP p = to_p(d);
+  const unsigned pixels = (unsigned)(d->N * d->P * d->Q);
+  if (pixels == 0) return SRGAN_OK;
+  if (((uintptr_t)x | (uintptr_t)w) % 16) { set_error("head conv: tensors must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  conv_fprop_head_kernel<4><<<pixels, 256, 0, st>>>(p, x, w, bias, y, act, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+
 void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st) {
   splitk_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(part, out, n, splits);
 }

@@ -9,7 +9,7 @@
 // with the accumulator in tensor memory (double buffered), and the epilogue warps scatter-free "col2im" it:
 //   out[h][q][t] = sum_r sum_s Z_{h+r-padH}[q + s - padW][(r, s*4+t)]
 // The column shift crosses lanes, so every 32-column block of Z goes through a transposed shared-memory
-// staging buffer; the row shift is a ring of R partial output rows held in registers (a CTA walks down a band
+// staging buffer; the row shift is a ring of partial output rows in shared memory (a CTA walks down a band
 // of rows, so each input row is read from global memory once per band).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2..5 epilogue.
 #include "umma_ptx.cuh"
@@ -42,7 +42,8 @@ conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
   uint8_t* sb = smem;
   uint8_t* sa = smem + b_bytes;
   float* zs = reinterpret_cast<float*>(sa + kTOStages * a_bytes);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(zs + 2 * kTOZBuf);
+  float* accs = zs + 2 * kTOZBuf;                       // [8 rows][4][128]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(accs + 8 * 4 * 128);
   uint64_t* a_empty = a_full + kTOStages;
   uint64_t* t_full = a_empty + kTOStages;               // [2]
   uint64_t* t_empty = t_full + 2;                       // [2]
@@ -62,7 +63,7 @@ conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_in) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
   }
-  for (int i = threadIdx.x; i < 2 * kTOZBuf; i += kTOThreads) zs[i] = 0.f;     // margins stay zero
+  for (int i = threadIdx.x; i < 2 * kTOZBuf + 8 * 4 * 128; i += kTOThreads) zs[i] = 0.f;   // margins stay zero
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -113,11 +114,7 @@ conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     const int quad = warp & 3;
     const int qq = quad * 32 + lane;                    // TMEM lane == input pixel q' == output pixel q
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float acc[8][4];                                    // acc[7 - r] collects filter row r; acc[8 - R] completes first
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) acc[a][t] = 0.f;
+    // ring of partial output rows: accs[h & 7][t][pixel]; a thread only ever touches its own pixel column
     float bv[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) bv[t] = (bias && t < p.tc) ? __ldg(bias + t) : 0.f;
@@ -127,26 +124,30 @@ conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         const int buf = i & 1;
         mbar_wait(t_full + buf, (i >> 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
+#pragma unroll 1
+        for (int r = 0; r < p.R; ++r) {                 // (kept rolled: the body is ~150 instructions)
           const int h = hp - r + p.padH;
-          if (r < p.R && h >= h0 && h < h1) {           // uniform over the CTA
-            float v[32];
-            tmem_ld32(taddr + buf * 256 + r * 32, v);
-            float* zb = zs + (zi & 1) * kTOZBuf;
+          if (h < h0 || h >= h1) continue;              // uniform over the CTA
+          float v[32];
+          tmem_ld32(taddr + buf * 256 + r * 32, v);
+          float* zb = zs + (zi & 1) * kTOZBuf;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < p.S * 4) zb[j * kTOZRow + p.padW + qq] = v[j];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int j = 0; j < 32; ++j)
+            if (j < p.S * 4) zb[j * kTOZRow + p.padW + qq] = v[j];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-              if (s < p.S) {
+          for (int s = 0; s < 8; ++s)
+            if (s < p.S) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (t < p.tc) acc[7 - r][t] += zb[(s * 4 + t) * kTOZRow + qq + s];
-              }
-            ++zi;
-          }
+              for (int t = 0; t < 4; ++t)
+                if (t < p.tc) sum[t] += zb[(s * 4 + t) * kTOZRow + qq + s];
+            }
+          float* ar = accs + (h & 7) * 4 * 128 + qq;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t < p.tc) ar[t * 128] += sum[t];
+          ++zi;
         }
         tc_fence_before();
         __syncwarp();
@@ -155,22 +156,16 @@ conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       }
       // output row hp + padH - (R-1) has now received all of its filter rows
       const int hd = hp + p.padH - (p.R - 1);
-      if (hd >= h0 && hd < h1 && qq < p.Wo) {
+      if (hd >= h0 && hd < h1) {
+        float* ar = accs + (hd & 7) * 4 * 128 + qq;
         float* o = out + (((size_t)n * p.Ho + hd) * p.Wo + qq) * p.tc;
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
-          if (a == 8 - p.R) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (t < p.tc) o[t] = apply_act(acc[a][t] + bv[t], p.act, p.slope);
+        for (int t = 0; t < 4; ++t)
+          if (t < p.tc) {
+            if (qq < p.Wo) o[t] = apply_act(ar[t * 128] + bv[t], p.act, p.slope);
+            ar[t * 128] = 0.f;
           }
       }
-#pragma unroll
-      for (int a = 0; a < 7; ++a)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) acc[a][t] = acc[a + 1][t];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) acc[7][t] = 0.f;
     }
   }
   __syncthreads();
@@ -270,7 +265,7 @@ int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, con
   // D = f32, A = B = tf32, both K-major, N = 32*R, M = 128
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((d->R * 32) >> 3) << 17) | ((128u >> 4) << 24);
   const size_t smem = 1024 + (size_t)p.nchunks * d->R * 4096 + (size_t)kTOStages * p.nchunks * 16384 +
-                      2 * kTOZBuf * sizeof(float) + 256;
+                      (2 * kTOZBuf + 8 * 4 * 128) * sizeof(float) + 256;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_thinout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

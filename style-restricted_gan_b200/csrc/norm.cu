@@ -2,216 +2,253 @@
 //
 //   xh = (x - mean_hw) * rstd_hw ; v = (xh + cbias[n][c]) * gamma[c] + beta[c] ; y = act(v) (+ residual)
 //
-// HBM-bound.  One CTA owns (image n, CH consecutive channels, one slice of the HW pixels).  The
-// pixel dimension is split over a thread-block CLUSTER of SP CTAs: each CTA keeps its slice of
-// the plane in shared memory, the per-channel partial sums are exchanged through distributed
-// shared memory (DSMEM) in rank order (deterministic), and the slice is normalised from shared
-// memory -> the plane is read from HBM exactly once and written once (2*4 bytes / element fwd,
-// 3*4 bytes / element bwd: the algorithmic minimum).  When a slice cannot fit in shared memory
-// the same kernel re-reads global memory (CACHED=false).
-#include <cooperative_groups.h>
+// HBM-bound streaming design: every pass is a grid of (pixel slice, image, channel chunk) CTAs whose threads
+// read whole pixel rows with float4 loads (consecutive threads -> consecutive 16 B: every 128-byte line is
+// used completely), 4 independent loads in flight per thread and several CTAs per SM, no shared-memory
+// staging, so the memory system sees tens of KB in flight per SM.
+//   forward : (1) statistics  - per-slice partial sums of (x - p), (x - p)^2 about a per-channel pivot p
+//                               (the first pixel; keeps the one-pass variance well conditioned);
+//             (2) apply       - every CTA folds the <= 64 slice partials of its channels in a fixed order
+//                               (deterministic), then normalises its slice: read x, write y.
+//   backward: (1) reduce      - partial sums of dv and dv*xh (dv = dy * act'(v));
+//             (2) apply       - dx = rstd*gamma * (dv - mean(dv) - xh * mean(dv*xh)).
+// Algorithmic traffic: forward 2 reads + 1 write of the plane (the second read is an L2 hit for planes that
+// fit the 126 MB L2), backward 4 reads + 1 write.
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace srgan {
 
 constexpr int kNormThreads = 256;
-constexpr size_t kNormSmemMax = 200 * 1024;      // leave room for static smem
-constexpr size_t kNormSmemTwoCtas = 100 * 1024;  // slice size that still lets 2 CTAs share an SM
+constexpr int kNormMaxSlices = 64;
 
 struct NormP {
   int N, HW, C;
-  int slice;      // pixels per CTA
-  int SP;         // cluster size along z
+  int q4;         // float4 per pixel row (C / 4)
+  int TPR;        // threads per pixel row == float4 per channel chunk
+  int RPP;        // pixel rows per pass
+  int SL, slice;  // pixel slices per image, pixels per slice
   float eps, slope;
   int act;
 };
 
-// Sum `v` (one float4 per thread: 4 channels) over all threads with the same channel group,
-// then over the cluster.  Result (per channel of this thread's group) is returned to every thread.
-template <int CH>
-__device__ __forceinline__ float4 chunk_allreduce(float4 v, float4* part /*[256]*/, float* xchg /*[CH]*/,
-                                                  float* tot /*[CH]*/, int SP) {
-  constexpr int TPR = CH / 4;
-  const int tid = threadIdx.x;
-  part[tid] = v;
-  __syncthreads();
-  if (tid < TPR) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = tid; r < kNormThreads; r += TPR) {
-      float4 p = part[r];
-      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
-    }
-    reinterpret_cast<float4*>(xchg)[tid] = s;
-  }
-  if (SP > 1) {
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();                       // xchg of every CTA is written
-    if (tid < CH) {
-      float s = 0.f;
-      for (int r = 0; r < SP; ++r) s += *cluster.map_shared_rank(xchg + tid, r);
-      tot[tid] = s;
-    }
-    cluster.sync();                       // nobody still reads my xchg; tot visible
-  } else {
-    __syncthreads();
-    if (tid < CH) tot[tid] = xchg[tid];
-    __syncthreads();
-  }
-  return reinterpret_cast<float4*>(tot)[tid % TPR];
+struct NormIdx { int cg, row, c4, px0, px1; bool active; };
+
+__device__ __forceinline__ NormIdx norm_idx(const NormP& p) {
+  NormIdx i;
+  i.cg = threadIdx.x % p.TPR;
+  i.row = threadIdx.x / p.TPR;
+  i.active = i.row < p.RPP;
+  i.c4 = blockIdx.z * p.TPR + i.cg;
+  i.px0 = blockIdx.x * p.slice;
+  i.px1 = min(p.HW, i.px0 + p.slice);
+  return i;
 }
 
-template <int CH, bool CACHED>
-__global__ void __launch_bounds__(kNormThreads) inorm_fwd_kernel(
-    NormP p, const float* __restrict__ x, float* __restrict__ y, float* __restrict__ mean_out,
-    float* __restrict__ rstd_out, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ cbias, const float* __restrict__ residual) {
-  constexpr int TPR = CH / 4;                 // threads per pixel row
-  constexpr int RPP = kNormThreads / TPR;     // pixel rows per pass
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float4 part[kNormThreads];
-  __shared__ __align__(16) float xchg[CH];
-  __shared__ __align__(16) float tot[CH];
-  float4* cache = reinterpret_cast<float4*>(smem_raw);
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+__device__ __forceinline__ void acc4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-  const int tid = threadIdx.x;
-  const int cg4 = tid % TPR;                  // which float4 of the chunk
-  const int row = tid / TPR;
+// Sum (a, b) over the pixel rows of the CTA in a fixed order; threads with row == 0 get the result.
+__device__ __forceinline__ void rows_reduce(const NormP& p, const NormIdx& i, float4& a, float4& b, float4* sa,
+                                            float4* sb) {
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  if (i.row == 0) {
+    float4 ra = f4(0.f), rb = f4(0.f);
+    for (int r = 0; r < p.RPP; ++r) { acc4(ra, sa[r * p.TPR + i.cg]); acc4(rb, sb[r * p.TPR + i.cg]); }
+    a = ra; b = rb;
+  }
+}
+
+// partial layout: part[(n * SL + slice) * q4 + c4], two planes (first, second moment) of N*SL*q4 float4 each
+__global__ void __launch_bounds__(kNormThreads) inorm_stats_kernel(NormP p, const float* __restrict__ x,
+                                                                   float4* __restrict__ part) {
+  __shared__ float4 sa[kNormThreads], sb[kNormThreads];
+  const NormIdx i = norm_idx(p);
   const int n = blockIdx.y;
-  const int c0 = blockIdx.x * CH;
-  const int px0 = blockIdx.z * p.slice;
-  const int px1 = min(p.HW, px0 + p.slice);
-  const int npx = max(0, px1 - px0);
-  const float4* xg = reinterpret_cast<const float4*>(x + ((size_t)n * p.HW + px0) * p.C + c0) + cg4;
-  const int rs4 = p.C / 4;                    // float4 stride between pixels
-
-  // pass 0: sum
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = row; r < npx; r += RPP) {
-    float4 v = __ldg(xg + (size_t)r * rs4);
-    if (CACHED) cache[r * TPR + cg4] = v;
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  const float4* xg = reinterpret_cast<const float4*>(x) + (size_t)n * p.HW * p.q4 + i.c4;
+  float4 s1 = f4(0.f), s2 = f4(0.f);
+  if (i.active) {
+    const float4 pv = __ldg(xg);                       // pivot: first pixel of the plane
+    const int step = p.RPP;
+    int r = i.px0 + i.row;
+    for (; r + 3 * step < i.px1; r += 4 * step) {
+      float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
+      float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+#define SRGAN_ACC(v) { float a = v.x - pv.x, b = v.y - pv.y, c = v.z - pv.z, d = v.w - pv.w; \
+                       s1.x += a; s1.y += b; s1.z += c; s1.w += d; s2.x += a * a; s2.y += b * b; s2.z += c * c; s2.w += d * d; }
+      SRGAN_ACC(v0) SRGAN_ACC(v1) SRGAN_ACC(v2) SRGAN_ACC(v3)
+    }
+    for (; r < i.px1; r += step) { float4 v0 = __ldg(xg + (size_t)r * p.q4); SRGAN_ACC(v0) }
+#undef SRGAN_ACC
   }
-  float4 t4 = chunk_allreduce<CH>(s, part, xchg, tot, p.SP);
+  rows_reduce(p, i, s1, s2, sa, sb);
+  if (i.row == 0) {
+    const size_t o = ((size_t)n * p.SL + blockIdx.x) * p.q4 + i.c4;
+    part[o] = s1;
+    part[(size_t)p.N * p.SL * p.q4 + o] = s2;
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads) inorm_apply_kernel(
+    NormP p, const float* __restrict__ x, const float4* __restrict__ part, float* __restrict__ y,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ cbias, const float* __restrict__ residual) {
+  const NormIdx i = norm_idx(p);
+  if (!i.active) return;
+  const int n = blockIdx.y;
+  const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
+  const float4* xg = reinterpret_cast<const float4*>(x) + plane;
+  float4 s1 = f4(0.f), s2 = f4(0.f);
+  {
+    const float4* p1 = part + (size_t)n * p.SL * p.q4 + i.c4;
+    const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
+    for (int s = 0; s < p.SL; ++s) { acc4(s1, __ldg(p1 + (size_t)s * p.q4)); acc4(s2, __ldg(p2 + (size_t)s * p.q4)); }
+  }
+  const float4 pv = __ldg(xg);
   const float inv = 1.f / (float)p.HW;
-  const float4 mu = make_float4(t4.x * inv, t4.y * inv, t4.z * inv, t4.w * inv);
-
-  // pass 1: centred second moment
-  s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = row; r < npx; r += RPP) {
-    float4 v = CACHED ? cache[r * TPR + cg4] : __ldg(xg + (size_t)r * rs4);
-    float a = v.x - mu.x, b = v.y - mu.y, c = v.z - mu.z, d = v.w - mu.w;
-    s.x += a * a; s.y += b * b; s.z += c * c; s.w += d * d;
-  }
-  t4 = chunk_allreduce<CH>(s, part, xchg, tot, p.SP);
-  float4 rs;
-  rs.x = rsqrtf(t4.x * inv + p.eps); rs.y = rsqrtf(t4.y * inv + p.eps);
-  rs.z = rsqrtf(t4.z * inv + p.eps); rs.w = rsqrtf(t4.w * inv + p.eps);
-
-  const int c = c0 + cg4 * 4;
-  if (blockIdx.z == 0 && row == 0) {
+  float4 mu, rs;
+#define SRGAN_STAT(f) { float m = s1.f * inv; float var = fmaxf(s2.f * inv - m * m, 0.f); mu.f = pv.f + m; rs.f = rsqrtf(var + p.eps); }
+  SRGAN_STAT(x) SRGAN_STAT(y) SRGAN_STAT(z) SRGAN_STAT(w)
+#undef SRGAN_STAT
+  const int c = i.c4 * 4;
+  if (blockIdx.x == 0 && i.row == 0) {
     reinterpret_cast<float4*>(mean_out + (size_t)n * p.C + c)[0] = mu;
     reinterpret_cast<float4*>(rstd_out + (size_t)n * p.C + c)[0] = rs;
   }
-  float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
-  float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 tb = cbias ? __ldg(reinterpret_cast<const float4*>(cbias + (size_t)n * p.C + c))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-  // pass 2: normalise + conditional bias + affine + activation (+ residual)
-  float4* yg = reinterpret_cast<float4*>(y + ((size_t)n * p.HW + px0) * p.C + c0) + cg4;
-  const float4* rg = residual
-      ? reinterpret_cast<const float4*>(residual + ((size_t)n * p.HW + px0) * p.C + c0) + cg4 : nullptr;
-  for (int r = row; r < npx; r += RPP) {
-    float4 v = CACHED ? cache[r * TPR + cg4] : __ldg(xg + (size_t)r * rs4);
-    float4 o;
-    o.x = apply_act(((v.x - mu.x) * rs.x + tb.x) * g.x + b.x, p.act, p.slope);
-    o.y = apply_act(((v.y - mu.y) * rs.y + tb.y) * g.y + b.y, p.act, p.slope);
-    o.z = apply_act(((v.z - mu.z) * rs.z + tb.z) * g.z + b.z, p.act, p.slope);
-    o.w = apply_act(((v.w - mu.w) * rs.w + tb.w) * g.w + b.w, p.act, p.slope);
-    if (rg) {
-      float4 q = __ldg(rg + (size_t)r * rs4);
-      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+  const float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : f4(1.f);
+  const float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : f4(0.f);
+  const float4 tb = cbias ? __ldg(reinterpret_cast<const float4*>(cbias + (size_t)n * p.C + c)) : f4(0.f);
+  // y = act(x * k + o):  k = rstd*gamma, o = (cbias - mean*rstd)*gamma + beta
+  const float4 k = make_float4(rs.x * g.x, rs.y * g.y, rs.z * g.z, rs.w * g.w);
+  const float4 o = make_float4((tb.x - mu.x * rs.x) * g.x + b.x, (tb.y - mu.y * rs.y) * g.y + b.y,
+                               (tb.z - mu.z * rs.z) * g.z + b.z, (tb.w - mu.w * rs.w) * g.w + b.w);
+  float4* yg = reinterpret_cast<float4*>(y) + plane;
+  const float4* rg = residual ? reinterpret_cast<const float4*>(residual) + plane : nullptr;
+  auto one = [&](float4 v, int r) {
+    float4 t;
+    t.x = apply_act(fmaf(v.x, k.x, o.x), p.act, p.slope);
+    t.y = apply_act(fmaf(v.y, k.y, o.y), p.act, p.slope);
+    t.z = apply_act(fmaf(v.z, k.z, o.z), p.act, p.slope);
+    t.w = apply_act(fmaf(v.w, k.w, o.w), p.act, p.slope);
+    if (rg) acc4(t, __ldg(rg + (size_t)r * p.q4));
+    yg[(size_t)r * p.q4] = t;
+  };
+  const int step = p.RPP;
+  int r = i.px0 + i.row;
+  for (; r + 3 * step < i.px1; r += 4 * step) {
+    float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
+    float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+    one(v0, r); one(v1, r + step); one(v2, r + 2 * step); one(v3, r + 3 * step);
+  }
+  for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), r);
+}
+
+struct NormBwdConsts { float4 mu, rs, g, b, tb; };
+
+__device__ __forceinline__ NormBwdConsts norm_bwd_consts(const NormP& p, int n, int c, const float* mean,
+                                                         const float* rstd, const float* gamma, const float* beta,
+                                                         const float* cbias) {
+  NormBwdConsts k;
+  k.mu = __ldg(reinterpret_cast<const float4*>(mean + (size_t)n * p.C + c));
+  k.rs = __ldg(reinterpret_cast<const float4*>(rstd + (size_t)n * p.C + c));
+  k.g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : f4(1.f);
+  k.b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : f4(0.f);
+  k.tb = cbias ? __ldg(reinterpret_cast<const float4*>(cbias + (size_t)n * p.C + c)) : f4(0.f);
+  return k;
+}
+
+__device__ __forceinline__ void norm_dv_xh(const NormP& p, const NormBwdConsts& k, float4 xv, float4 dy, float4& xh,
+                                           float4& dv) {
+  xh.x = (xv.x - k.mu.x) * k.rs.x; xh.y = (xv.y - k.mu.y) * k.rs.y;
+  xh.z = (xv.z - k.mu.z) * k.rs.z; xh.w = (xv.w - k.mu.w) * k.rs.w;
+  dv.x = dy.x * act_grad_pre((xh.x + k.tb.x) * k.g.x + k.b.x, p.act, p.slope);
+  dv.y = dy.y * act_grad_pre((xh.y + k.tb.y) * k.g.y + k.b.y, p.act, p.slope);
+  dv.z = dy.z * act_grad_pre((xh.z + k.tb.z) * k.g.z + k.b.z, p.act, p.slope);
+  dv.w = dy.w * act_grad_pre((xh.w + k.tb.w) * k.g.w + k.b.w, p.act, p.slope);
+}
+
+__global__ void __launch_bounds__(kNormThreads) inorm_bwd_reduce_kernel(
+    NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ cbias, float4* __restrict__ part) {
+  __shared__ float4 sa[kNormThreads], sb[kNormThreads];
+  const NormIdx i = norm_idx(p);
+  const int n = blockIdx.y;
+  float4 a1 = f4(0.f), a2 = f4(0.f);
+  if (i.active) {
+    const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
+    const float4* xg = reinterpret_cast<const float4*>(x) + plane;
+    const float4* dg = reinterpret_cast<const float4*>(dy) + plane;
+    const NormBwdConsts k = norm_bwd_consts(p, n, i.c4 * 4, mean, rstd, gamma, beta, cbias);
+    auto one = [&](float4 xv, float4 dv_in) {
+      float4 xh, dv;
+      norm_dv_xh(p, k, xv, dv_in, xh, dv);
+      acc4(a1, dv);
+      a2.x += dv.x * xh.x; a2.y += dv.y * xh.y; a2.z += dv.z * xh.z; a2.w += dv.w * xh.w;
+    };
+    const int step = p.RPP;
+    int r = i.px0 + i.row;
+    for (; r + step < i.px1; r += 2 * step) {
+      float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
+      float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+      one(x0, d0); one(x1, d1);
     }
-    yg[(size_t)r * rs4] = o;
+    for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4));
+  }
+  rows_reduce(p, i, a1, a2, sa, sb);
+  if (i.row == 0) {
+    const size_t o = ((size_t)n * p.SL + blockIdx.x) * p.q4 + i.c4;
+    part[o] = a1;
+    part[(size_t)p.N * p.SL * p.q4 + o] = a2;
   }
 }
 
-template <int CH, bool CACHED>
-__global__ void __launch_bounds__(kNormThreads) inorm_bwd_kernel(
+__global__ void __launch_bounds__(kNormThreads) inorm_bwd_apply_kernel(
     NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ cbias, float* __restrict__ dx, float* __restrict__ s1_out,
-    float* __restrict__ s2_out) {
-  constexpr int TPR = CH / 4;
-  constexpr int RPP = kNormThreads / TPR;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float4 part[kNormThreads];
-  __shared__ __align__(16) float xchg[CH];
-  __shared__ __align__(16) float tot[CH];
-  float4* cache_dv = reinterpret_cast<float4*>(smem_raw);
-  float4* cache_xh = cache_dv + (size_t)p.slice * TPR;
-
-  const int tid = threadIdx.x;
-  const int cg4 = tid % TPR;
-  const int row = tid / TPR;
+    const float* __restrict__ cbias, const float4* __restrict__ part, float* __restrict__ dx,
+    float* __restrict__ s1_out, float* __restrict__ s2_out) {
+  const NormIdx i = norm_idx(p);
+  if (!i.active) return;
   const int n = blockIdx.y;
-  const int c0 = blockIdx.x * CH;
-  const int c = c0 + cg4 * 4;
-  const int px0 = blockIdx.z * p.slice;
-  const int px1 = min(p.HW, px0 + p.slice);
-  const int npx = max(0, px1 - px0);
-  const int rs4 = p.C / 4;
-  const size_t base = ((size_t)n * p.HW + px0) * p.C + c0;
-  const float4* xg = reinterpret_cast<const float4*>(x + base) + cg4;
-  const float4* dg = reinterpret_cast<const float4*>(dy + base) + cg4;
-  float4* og = reinterpret_cast<float4*>(dx + base) + cg4;
-
-  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + (size_t)n * p.C + c));
-  const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + (size_t)n * p.C + c));
-  const float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
-  const float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 tb = cbias ? __ldg(reinterpret_cast<const float4*>(cbias + (size_t)n * p.C + c))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-
-  auto dv_xh = [&](float4 xv, float4 dv_in, float4& xh, float4& dv) {
-    xh.x = (xv.x - mu.x) * rs.x; xh.y = (xv.y - mu.y) * rs.y;
-    xh.z = (xv.z - mu.z) * rs.z; xh.w = (xv.w - mu.w) * rs.w;
-    dv.x = dv_in.x * act_grad_pre((xh.x + tb.x) * g.x + b.x, p.act, p.slope);
-    dv.y = dv_in.y * act_grad_pre((xh.y + tb.y) * g.y + b.y, p.act, p.slope);
-    dv.z = dv_in.z * act_grad_pre((xh.z + tb.z) * g.z + b.z, p.act, p.slope);
-    dv.w = dv_in.w * act_grad_pre((xh.w + tb.w) * g.w + b.w, p.act, p.slope);
-  };
-
-  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = row; r < npx; r += RPP) {
-    float4 xh, dv;
-    dv_xh(__ldg(xg + (size_t)r * rs4), __ldg(dg + (size_t)r * rs4), xh, dv);
-    if (CACHED) { cache_dv[r * TPR + cg4] = dv; cache_xh[r * TPR + cg4] = xh; }
-    a1.x += dv.x; a1.y += dv.y; a1.z += dv.z; a1.w += dv.w;
-    a2.x += dv.x * xh.x; a2.y += dv.y * xh.y; a2.z += dv.z * xh.z; a2.w += dv.w * xh.w;
+  const int c = i.c4 * 4;
+  float4 S1 = f4(0.f), S2 = f4(0.f);
+  {
+    const float4* p1 = part + (size_t)n * p.SL * p.q4 + i.c4;
+    const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
+    for (int s = 0; s < p.SL; ++s) { acc4(S1, __ldg(p1 + (size_t)s * p.q4)); acc4(S2, __ldg(p2 + (size_t)s * p.q4)); }
   }
-  const float4 S1 = chunk_allreduce<CH>(a1, part, xchg, tot, p.SP);
-  const float4 S2 = chunk_allreduce<CH>(a2, part, xchg, tot, p.SP);
-  if (blockIdx.z == 0 && row == 0) {
+  if (blockIdx.x == 0 && i.row == 0) {
     reinterpret_cast<float4*>(s1_out + (size_t)n * p.C + c)[0] = S1;
     reinterpret_cast<float4*>(s2_out + (size_t)n * p.C + c)[0] = S2;
   }
+  const NormBwdConsts k = norm_bwd_consts(p, n, c, mean, rstd, gamma, beta, cbias);
   const float inv = 1.f / (float)p.HW;
-  const float4 k = make_float4(rs.x * g.x, rs.y * g.y, rs.z * g.z, rs.w * g.w);
+  const float4 kk = make_float4(k.rs.x * k.g.x, k.rs.y * k.g.y, k.rs.z * k.g.z, k.rs.w * k.g.w);
   const float4 m1 = make_float4(S1.x * inv, S1.y * inv, S1.z * inv, S1.w * inv);
   const float4 m2 = make_float4(S2.x * inv, S2.y * inv, S2.z * inv, S2.w * inv);
-  for (int r = row; r < npx; r += RPP) {
-    float4 xh, dv;
-    if (CACHED) { dv = cache_dv[r * TPR + cg4]; xh = cache_xh[r * TPR + cg4]; }
-    else dv_xh(__ldg(xg + (size_t)r * rs4), __ldg(dg + (size_t)r * rs4), xh, dv);
-    float4 o;
-    o.x = k.x * (dv.x - m1.x - xh.x * m2.x);
-    o.y = k.y * (dv.y - m1.y - xh.y * m2.y);
-    o.z = k.z * (dv.z - m1.z - xh.z * m2.z);
-    o.w = k.w * (dv.w - m1.w - xh.w * m2.w);
-    og[(size_t)r * rs4] = o;
+  const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
+  const float4* xg = reinterpret_cast<const float4*>(x) + plane;
+  const float4* dg = reinterpret_cast<const float4*>(dy) + plane;
+  float4* og = reinterpret_cast<float4*>(dx) + plane;
+  auto one = [&](float4 xv, float4 dv_in, int r) {
+    float4 xh, dv, o;
+    norm_dv_xh(p, k, xv, dv_in, xh, dv);
+    o.x = kk.x * (dv.x - m1.x - xh.x * m2.x);
+    o.y = kk.y * (dv.y - m1.y - xh.y * m2.y);
+    o.z = kk.z * (dv.z - m1.z - xh.z * m2.z);
+    o.w = kk.w * (dv.w - m1.w - xh.w * m2.w);
+    og[(size_t)r * p.q4] = o;
+  };
+  const int step = p.RPP;
+  int r = i.px0 + i.row;
+  for (; r + step < i.px1; r += 2 * step) {
+    float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
+    float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+    one(x0, d0, r); one(x1, d1, r + step);
   }
+  for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4), r);
 }
 
 // dgamma[c] = sum_n (s2 + cbias*s1) ; dbeta[c] = sum_n s1 ; dcbias[n][c] = gamma[c]*s1[n][c]
@@ -234,121 +271,83 @@ __global__ void inorm_param_grads_kernel(const float* __restrict__ s1, const flo
   if (dbeta) dbeta[c] = db;
 }
 
-struct NormPlan { int CH, SP, slice; bool cached; size_t smem; };
-
-// arrays = number of float planes kept in shared memory per pixel-channel (1 fwd, 2 bwd)
-static NormPlan plan_norm(int N, int HW, int C, int arrays) {
-  const int chs[3] = {32, 16, 8};
-  NormPlan best{0, 1, HW, false, 0};
-  for (int ci = 0; ci < 3; ++ci) {
-    int CH = chs[ci];
-    if (C % CH) continue;
-    if (!best.CH) best.CH = CH;
-    for (int SP = 1; SP <= 8; SP *= 2) {
-      int slice = ceil_div(HW, SP);
-      size_t bytes = (size_t)slice * CH * 4 * arrays;
-      long long ctas = (long long)N * (C / CH) * SP;
-      bool fits = bytes <= kNormSmemMax;
-      bool enough = ctas >= 2 * kNumSMs || SP == 8 || slice <= 256;
-      if (fits && (bytes <= kNormSmemTwoCtas || SP == 8) && enough) {
-        return NormPlan{CH, SP, slice, true, bytes};
-      }
-      if (fits && SP == 8) return NormPlan{CH, SP, slice, true, bytes};
-    }
+// channel chunking + pixel slicing; returns false when C cannot be mapped onto 256 threads
+static bool plan_norm(int N, int HW, int C, NormP* out) {
+  NormP p = {};
+  p.N = N; p.HW = HW; p.C = C; p.q4 = C / 4;
+  int nchunk = 1;
+  while (nchunk <= p.q4 && (p.q4 % nchunk || p.q4 / nchunk > 64)) ++nchunk;
+  if (nchunk > p.q4) {                       // no divisor gives <= 64 float4 per chunk: take rows of up to 256
+    if (p.q4 > kNormThreads) return false;
+    nchunk = 1;
   }
-  // streaming fallback: widest chunk, split for parallelism only
-  int CH = best.CH;
-  int SP = 1;
-  while (SP < 8 && (long long)N * (C / CH) * SP < 2 * kNumSMs && HW / (SP * 2) >= 256) SP *= 2;
-  return NormPlan{CH, SP, ceil_div(HW, SP), false, 0};
+  p.TPR = p.q4 / nchunk;
+  p.RPP = kNormThreads / p.TPR;
+  long long want = (8LL * kNumSMs + (long long)N * nchunk - 1) / ((long long)N * nchunk);
+  long long cap = ceil_div(HW, p.RPP * 4);   // at least 4 passes per CTA
+  long long SL = want < cap ? want : cap;
+  if (SL < 1) SL = 1;
+  if (SL > kNormMaxSlices) SL = kNormMaxSlices;
+  p.slice = ceil_div(HW, (int)SL);
+  p.SL = ceil_div(HW, p.slice);
+  *out = p;
+  return true;
 }
 
-template <class K, class... Args>
-static int launch_cluster(K kernel, dim3 grid, int SP, size_t smem, cudaStream_t st, Args... args) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNormSmemMax);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kNormThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = SP;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kernel, args...);
-  if (e != cudaSuccess) { set_error("inorm launch: %s", cudaGetErrorString(e)); return (int)e; }
-  return SRGAN_OK;
-}
-
-template <int CH>
-static int inorm_fwd_ch(const NormPlan& pl, NormP p, cudaStream_t st, const float* x, float* y, float* mean,
-                        float* rstd, const float* gamma, const float* beta, const float* cbias,
-                        const float* residual) {
-  dim3 grid(p.C / CH, p.N, pl.SP);
-  if (pl.cached)
-    return launch_cluster(inorm_fwd_kernel<CH, true>, grid, pl.SP, pl.smem, st, p, x, y, mean, rstd, gamma, beta,
-                          cbias, residual);
-  return launch_cluster(inorm_fwd_kernel<CH, false>, grid, pl.SP, (size_t)0, st, p, x, y, mean, rstd, gamma, beta,
-                        cbias, residual);
-}
-
-template <int CH>
-static int inorm_bwd_ch(const NormPlan& pl, NormP p, cudaStream_t st, const float* dy, const float* x,
-                        const float* mean, const float* rstd, const float* gamma, const float* beta,
-                        const float* cbias, float* dx, float* s1, float* s2) {
-  dim3 grid(p.C / CH, p.N, pl.SP);
-  if (pl.cached)
-    return launch_cluster(inorm_bwd_kernel<CH, true>, grid, pl.SP, pl.smem, st, p, dy, x, mean, rstd, gamma, beta,
-                          cbias, dx, s1, s2);
-  return launch_cluster(inorm_bwd_kernel<CH, false>, grid, pl.SP, (size_t)0, st, p, dy, x, mean, rstd, gamma,
-                        beta, cbias, dx, s1, s2);
-}
+static size_t norm_ws_bytes(const NormP& p) { return (size_t)2 * p.N * p.SL * p.q4 * sizeof(float4); }
+static dim3 norm_grid(const NormP& p) { return dim3(p.SL, p.N, p.q4 / p.TPR); }
 
 }  // namespace srgan
 
 using namespace srgan;
 
+extern "C" size_t srgan_inorm_workspace(int N, int HW, int C) {
+  NormP p;
+  if (N <= 0 || HW <= 0 || C <= 0 || C % 4 || !plan_norm(N, HW, C, &p)) return 0;
+  return norm_ws_bytes(p);
+}
+
 extern "C" int srgan_inorm_fwd(const float* x, float* y, float* mean, float* rstd, const float* gamma,
                                const float* beta, const float* cbias, const float* residual, int N, int HW,
-                               int C, float eps, int act, float slope, void* stream) {
+                               int C, float eps, int act, float slope, void* ws, size_t ws_bytes, void* stream) {
   SRGAN_CHECK_ARG(x && y && mean && rstd, "null pointer");
   SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
   SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
-                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)residual) % 16 == 0, "pointers must be 16-byte aligned");
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)residual | (uintptr_t)ws) % 16 == 0,
+                  "pointers must be 16-byte aligned");
   SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
   if (N == 0) return SRGAN_OK;
-  NormPlan pl = plan_norm(N, HW, C, 1);
-  NormP p{N, HW, C, pl.slice, pl.SP, eps, slope, act};
+  NormP p;
+  SRGAN_CHECK_ARG(plan_norm(N, HW, C, &p), "channel count cannot be mapped");
+  p.eps = eps; p.slope = slope; p.act = act;
+  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_fwd: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  switch (pl.CH) {
-    case 32: return inorm_fwd_ch<32>(pl, p, st, x, y, mean, rstd, gamma, beta, cbias, residual);
-    case 16: return inorm_fwd_ch<16>(pl, p, st, x, y, mean, rstd, gamma, beta, cbias, residual);
-    default: return inorm_fwd_ch<8>(pl, p, st, x, y, mean, rstd, gamma, beta, cbias, residual);
-  }
+  inorm_stats_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (float4*)ws);
+  inorm_apply_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (const float4*)ws, y, mean, rstd, gamma, beta, cbias,
+                                                            residual);
+  SRGAN_RETURN_LAUNCH();
 }
 
 extern "C" int srgan_inorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                const float* gamma, const float* beta, const float* cbias, float* dx, float* s1,
-                               float* s2, int N, int HW, int C, int act, float slope, void* stream) {
+                               float* s2, int N, int HW, int C, int act, float slope, void* ws, size_t ws_bytes,
+                               void* stream) {
   SRGAN_CHECK_ARG(dy && x && mean && rstd && dx && s1 && s2, "null pointer");
   SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
   SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
-                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)dx | (uintptr_t)s1 | (uintptr_t)s2) % 16 == 0,
-                  "pointers must be 16-byte aligned");
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)dx | (uintptr_t)s1 | (uintptr_t)s2 |
+                   (uintptr_t)ws) % 16 == 0, "pointers must be 16-byte aligned");
   SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
   if (N == 0) return SRGAN_OK;
-  NormPlan pl = plan_norm(N, HW, C, 2);
-  NormP p{N, HW, C, pl.slice, pl.SP, 0.f, slope, act};
+  NormP p;
+  SRGAN_CHECK_ARG(plan_norm(N, HW, C, &p), "channel count cannot be mapped");
+  p.eps = 0.f; p.slope = slope; p.act = act;
+  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_bwd: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  switch (pl.CH) {
-    case 32: return inorm_bwd_ch<32>(pl, p, st, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2);
-    case 16: return inorm_bwd_ch<16>(pl, p, st, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2);
-    default: return inorm_bwd_ch<8>(pl, p, st, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2);
-  }
+  inorm_bwd_reduce_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias, (float4*)ws);
+  inorm_bwd_apply_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias,
+                                                                (const float4*)ws, dx, s1, s2);
+  SRGAN_RETURN_LAUNCH();
 }
 
 extern "C" int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma,

@@ -35,8 +35,9 @@ SIGNATURES = {
     "srgan_nhwc_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "srgan_reflect_pad_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "srgan_reflect_pad_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "srgan_inorm_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_float, P]),
-    "srgan_inorm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "srgan_inorm_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "srgan_inorm_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_float, P, c_size_t, P]),
+    "srgan_inorm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, c_size_t, P]),
     "srgan_inorm_param_grads": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P]),
     "srgan_condbias_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "srgan_condbias_bwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P]),

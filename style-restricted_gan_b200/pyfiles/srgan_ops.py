@@ -415,8 +415,10 @@ class _InstanceNormFn(torch.autograd.Function):
         mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
         rstd = torch.empty((N, C), dtype=torch.float32, device=x.device)
         if x.numel():
+            nb = _lib().srgan_inorm_workspace(N, H * W, C)
+            ws = _workspace(x.device, nb)
             _call("srgan_inorm_fwd", _p(x), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias),
-                  _p(residual), N, H * W, C, eps, act, slope, _stream())
+                  _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb, _stream())
         ctx.gamma, ctx.beta = gamma, beta
         ctx.act, ctx.slope = act, slope
         ctx.has_res = residual is not None
@@ -433,8 +435,10 @@ class _InstanceNormFn(torch.autograd.Function):
         s1 = torch.empty((N, C), dtype=torch.float32, device=x.device)
         s2 = torch.empty((N, C), dtype=torch.float32, device=x.device)
         if x.numel():
+            nb = _lib().srgan_inorm_workspace(N, H * W, C)
+            ws = _workspace(x.device, nb)
             _call("srgan_inorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(dx),
-                  _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _stream())
+                  _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
         dgamma = dbeta = dcb = None
         need_g = gamma is not None and ctx.needs_input_grad[1]
         need_b = beta is not None and ctx.needs_input_grad[2]

@@ -47,7 +47,7 @@ def test_bad_arguments_fail_loudly_without_a_gpu():
     assert st == -1 and b"output size mismatch" in lib.srgan_last_error()
     with pytest.raises(_srgan_lib.SrganKernelError):
         _srgan_lib.check(st, "srgan_conv2d_fprop")
-    assert lib.srgan_inorm_fwd(16, 16, 16, 16, None, None, None, None, 1, 16, 12, 1e-5, 0, 0.0, None) == -1
+    assert lib.srgan_inorm_fwd(16, 16, 16, 16, None, None, None, None, 1, 16, 12, 1e-5, 0, 0.0, None, 0, None) == -1
 
 
 def test_product_ops_refuse_cpu_tensors():

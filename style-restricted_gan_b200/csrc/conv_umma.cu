@@ -41,22 +41,25 @@ struct UmmaConvP {
   int4 taps[kMaxTaps];           // {channel offset, dw, hp | (filter tap << 8), dh}
 };
 
-template <int BN>
+// MT = number of 128-pixel M sub-tiles a CTA accumulates against ONE filter tile per stage: the filter bytes are
+// amortised over MT*128 pixels (TF32 operands are 4 bytes, so a 128x256 tile needs 96 B/clk of shared-memory
+// fill to keep the tensor pipe busy, a 256x256 tile 64 B/clk).
+template <int BN, int MT = 1>
 struct UmmaCfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kStages = (212 * 1024) / kStageBytes < 8 ? (212 * 1024) / kStageBytes : 8;
+  static constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32, A=B=tf32, K-major both, N=BN, M=128
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
 };
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
@@ -69,14 +72,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int tap0 = p.tap_begin[cls], ntaps = p.tap_begin[cls + 1] - tap0;
   const int iters = ntaps * p.c_chunks;
 
-  // tile origin in the pixel grid
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int tn = t / p.tiles_h;
+  // tile origins in the pixel grid: this CTA owns the MT consecutive tiles MT*blockIdx.x + mt (a tile index past
+  // the grid decodes to an image index >= Nn: its loads are TMA zero-fill and its stores are masked)
   const int bw = 1 << p.lw, bh = 1 << p.lh;
   const int bn = 128 >> (p.lw + p.lh);
-  const int q0 = tw * bw, p0 = th * bh, n0 = tn * bn;
+  int q0[MT], p0[MT], n0[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    int t = blockIdx.x * MT + mt;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tn = t / p.tiles_h;
+    q0[mt] = tw * bw; p0[mt] = th * bh; n0[mt] = tn * bn;
+  }
   const int col0 = blockIdx.y * BN;
 
   if (threadIdx.x == 0) {
@@ -104,8 +112,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
         mbar_expect_tx(full + stage, Cfg::kStageBytes);
-        tma_load_5d(&map_a, full + stage, sa, cc + tp.x, q0 + tp.y, tp.z & 0xff, p0 + tp.w, n0);
-        tma_load_3d(&map_b, full + stage, sa + kABytes, cc, tp.z >> 8, col0);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+          tma_load_5d(&map_a, full + stage, sa + mt * kABytes, cc + tp.x, q0[mt] + tp.y, tp.z & 0xff, p0[mt] + tp.w,
+                      n0[mt]);
+        tma_load_3d(&map_b, full + stage, sa + MT * kABytes, cc, tp.z >> 8, col0);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -118,11 +129,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(full + stage, phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-        const uint64_t adesc = smem_desc_sw128(sa);
-        const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+        const uint64_t bdesc = smem_desc_sw128(sa + MT * kABytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)       // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
-          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc, (it | k) != 0);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t adesc = smem_desc_sw128(sa + mt * kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
+            umma_tf32(tmem_base + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc,
+                      (it | k) != 0);
+        }
         umma_commit(empty + stage);       // stage reusable once these MMAs have read it
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -133,14 +148,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
     const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
     const int wl = m & (bw - 1), hl = (m >> p.lw) & (bh - 1), nl = m >> (p.lw + p.lh);
-    const int n = n0 + nl, pp = p0 + hl, qq = q0 + wl;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    constexpr int kChunk = BN >= 32 ? 32 : 16;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+    const int n = n0[mt] + nl, pp = p0[mt] + hl, qq = q0[mt] + wl;
     const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
     float* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
                        (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    constexpr int kChunk = BN >= 32 ? 32 : 16;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * BN;
 #pragma unroll 1
     for (int c = 0; c < BN; c += kChunk) {
       float v[32];
@@ -163,6 +180,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+    }
     }
     tc_fence_before();
   }
@@ -359,18 +377,19 @@ static int pick_bn(int K) {
   return 16;
 }
 
-template <int BN>
+template <int BN, int MT = 1>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, float* y,
                      dim3 grid, cudaStream_t st) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, MT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmem);
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  conv_umma_kernel<BN><<<grid, kUmmaThreads, Cfg::kSmem, st>>>(ma, mb, p, bias, y);
+  grid.x = (grid.x + MT - 1) / MT;
+  conv_umma_kernel<BN, MT><<<grid, kUmmaThreads, Cfg::kSmem, st>>>(ma, mb, p, bias, y);
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -425,6 +444,12 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   p.out_H = pr.out_H; p.out_W = pr.out_W; p.out_C = pr.fK; p.os = pr.os; p.K = pr.fK;
   p.act = act; p.slope = slope;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
+  // two M sub-tiles per CTA once that still leaves every SM a CTA (bring-up override: SRGAN_DBG_CONV_MT=1|2)
+  static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
+  const long ctas = (long)grid.x * grid.y * grid.z;
+  const bool mt2 = e_mt ? atoi(e_mt) == 2 : ctas >= 2 * kNumSMs;
+  if (mt2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st);
+  if (mt2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st);
   switch (BN) {
     case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st);
     case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st);

@@ -24,11 +24,8 @@ def _rand(*shape, seed=0, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).to(DEV)
 
 
-def _check(prod_fn, ref_fn, inputs, tol, grad_tol=None, names=None, kink_free=None):
-    """inputs: list of fp32 cuda tensors (those with requires_grad get gradient checks).
-    kink_free(ref_inputs) -> bool mask: with a piecewise-linear activation the gradient of an element whose
-    pre-activation is within fp32 rounding of 0 is decided by rounding (a single such element out of 2M is a
-    4e-4 relative-L2 difference); the gradient w.r.t. inputs[0] is compared on the elements of the mask."""
+def _check(prod_fn, ref_fn, inputs, tol, grad_tol=None, names=None):
+    """inputs: list of fp32 cuda tensors (those with requires_grad get gradient checks)."""
     grad_tol = grad_tol or tol
     p_in = [t.detach().clone().requires_grad_(t.requires_grad) for t in inputs]
     r_in = [t.detach().double().clone().requires_grad_(t.requires_grad) for t in inputs]
@@ -42,14 +39,23 @@ def _check(prod_fn, ref_fn, inputs, tol, grad_tol=None, names=None, kink_free=No
     for i, (a, b) in enumerate(zip(p_in, r_in)):
         if b.requires_grad:
             assert a.grad is not None, i
-            ga, gb = a.grad, b.grad
-            if i == 0 and kink_free is not None:
-                keep = kink_free([t.detach() for t in r_in])
-                assert float(keep.double().mean()) > 0.999
-                ga, gb = ga * keep, gb * keep
-            e = _rel(ga, gb)
+            e = _rel(a.grad, b.grad)
             assert e < grad_tol, ("grad", names[i] if names else i, e)
     return y
+
+
+def _clear_of_kink(x, pre_fn, margin=1e-4):
+    """Nudge the few elements of x whose fp64 pre-activation pre_fn(x) lies within `margin` of 0.  With a
+    piecewise-linear activation the gradient mask of such an element is decided by fp32 rounding, and one
+    flipped element out of 2M is a 4e-4 relative-L2 difference in dx (5e-4 in dbeta) -- a property of the
+    comparison, not of the kernel.  ~2M * 0.8 * margin elements are touched."""
+    x = x.detach().clone()
+    for _ in range(8):
+        near = pre_fn(x.double()).abs() < margin
+        if not bool(near.any()):
+            return x
+        x = torch.where(near, x + 0.01, x)
+    raise AssertionError("could not move the inputs away from the activation kink")
 
 
 @pytest.fixture(autouse=True)
@@ -140,18 +146,20 @@ def test_instance_norm_cond_affine_act(shape):
                 + beta[None, :, None, None]
             return act(h)
         return f
-    away = lambda r_in: ref(lambda t: t)(*r_in).abs() > 1e-5      # pre-activation clear of the kink at 0
+    x = _clear_of_kink(x, lambda t: ref(lambda h: h)(t, gamma.detach().double(), beta.detach().double(),
+                                                     cb.detach().double()))
+    x = x.contiguous(memory_format=CL).requires_grad_(True)
     _check(lambda x, g, b, c: ops.instance_norm_act(x, g, b, c, None, 1e-5, ops.ACT_RELU),
-           ref(F.relu), [x, gamma, beta, cb], 3e-6, 2e-4, ["x", "gamma", "beta", "cbias"],
-           kink_free=away)
+           ref(F.relu), [x, gamma, beta, cb], 3e-6, 2e-4, ["x", "gamma", "beta", "cbias"])
     _check(lambda x, g, b, c: ops.instance_norm_act(x, g, b, c, None, 1e-5, ops.ACT_LRELU, 0.2),
-           ref(lambda t: F.leaky_relu(t, 0.2)), [x, gamma, beta, cb], 3e-6, 2e-4, kink_free=away)
+           ref(lambda t: F.leaky_relu(t, 0.2)), [x, gamma, beta, cb], 3e-6, 2e-4)
 
 
 def test_instance_norm_plain_and_residual():
-    x = _rand(2, 128, 64, 64, seed=17).contiguous(memory_format=CL).requires_grad_(True)
+    x = _clear_of_kink(_rand(2, 128, 64, 64, seed=17), lambda t: F.instance_norm(t, eps=1e-5))
+    x = x.contiguous(memory_format=CL).requires_grad_(True)
     _check(lambda x: ops.instance_norm_act(x, act=ops.ACT_RELU), lambda x: F.relu(F.instance_norm(x, eps=1e-5)),
-           [x], 3e-6, 2e-4, kink_free=lambda r_in: F.instance_norm(r_in[0], eps=1e-5).abs() > 1e-5)
+           [x], 3e-6, 2e-4)
     x = _rand(2, 256, 32, 32, seed=18).contiguous(memory_format=CL).requires_grad_(True)
     r = _rand(2, 256, 32, 32, seed=19).contiguous(memory_format=CL).requires_grad_(True)
     g = (_rand(256, seed=20) * 0.1 + 1).requires_grad_(True)

@@ -51,12 +51,20 @@ struct UmmaCfg {
   static constexpr int kStages = (212 * 1024) / kStageBytes < 8 ? (212 * 1024) / kStageBytes : 8;
   static constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // TMA issue: measured with tools/tma_probe.cu, the bulk-tensor loads of ONE warp execute back to back (~750-1100
+  // clk each, whatever their size) while loads of different warps overlap.  A stage is therefore cut into kBoxes
+  // boxes of <= 16 KB (MT activation sub-tiles + filter rows in blocks of <= 128), and 2*kBoxes producer warps each
+  // own one box of every second stage: no warp issues more often than once per two stages.
+  static constexpr int kBRows = BN < 128 ? BN : 128;
+  static constexpr int kBoxes = MT + BN / kBRows;
+  static constexpr int kProducers = 2 * kBoxes;
+  static constexpr int kThreads = 32 * (5 + kProducers);   // warp 0 MMA, warps 1-4 epilogue, then the producers
   // instruction descriptor: D=f32, A=B=tf32, K-major both, N=BN, M=128
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
 };
 
 template <int BN, int MT>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__((UmmaCfg<BN, MT>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y) {
   using Cfg = UmmaCfg<BN, MT>;
@@ -88,39 +96,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int col0 = blockIdx.y * BN;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kBoxes); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 0) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ TMA producers (one box each, every 2nd stage)
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
+      const int pw = warp - 5;
+      const int box = pw % Cfg::kBoxes;
+      for (int it = pw / Cfg::kBoxes; it < iters; it += 2) {
+        const int stage = it % Cfg::kStages;
+        const uint32_t phase = (uint32_t)(it / Cfg::kStages) & 1u;
         const int tap = tap0 + it / p.c_chunks;
         const int cc = (it % p.c_chunks) * 32;
         const int4 tp = p.taps[tap];
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
-        mbar_expect_tx(full + stage, Cfg::kStageBytes);
+        if (box < MT) {
+          mbar_expect_tx(full + stage, kABytes);
+          int qb = q0[0], pb = p0[0], nb = n0[0];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-          tma_load_5d(&map_a, full + stage, sa + mt * kABytes, cc + tp.x, q0[mt] + tp.y, tp.z & 0xff, p0[mt] + tp.w,
-                      n0[mt]);
-        tma_load_3d(&map_b, full + stage, sa + MT * kABytes, cc, tp.z >> 8, col0);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          for (int mt = 1; mt < MT; ++mt)
+            if (box == mt) { qb = q0[mt]; pb = p0[mt]; nb = n0[mt]; }
+          tma_load_5d(&map_a, full + stage, sa + box * kABytes, cc + tp.x, qb + tp.y, tp.z & 0xff, pb + tp.w, nb);
+        } else {
+          const int rb = (box - MT) * Cfg::kBRows;
+          mbar_expect_tx(full + stage, Cfg::kBRows * 128);
+          tma_load_3d(&map_b, full + stage, sa + MT * kABytes + rb * 128, cc, tp.z >> 8, col0 + rb);
+        }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       int stage = 0;
@@ -185,7 +200,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -389,7 +404,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
     attr_done = true;
   }
   grid.x = (grid.x + MT - 1) / MT;
-  conv_umma_kernel<BN, MT><<<grid, kUmmaThreads, Cfg::kSmem, st>>>(ma, mb, p, bias, y);
+  conv_umma_kernel<BN, MT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, p, bias, y);
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -433,7 +448,7 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   {
     uint64_t dims[3] = {(uint64_t)C, (uint64_t)pr.T, (uint64_t)pr.fK};
     uint64_t str[2] = {(uint64_t)C * 4, (uint64_t)pr.T * C * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)BN};
+    uint32_t box[3] = {32, 1, (uint32_t)(BN < 128 ? BN : 128)};      // == UmmaCfg::kBRows
     if (int e = encode_map(&mb, pr.filt, 3, dims, str, box)) return e;
   }
   UmmaConvP& p = pr.p;

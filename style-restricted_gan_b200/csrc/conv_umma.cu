@@ -209,22 +209,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 // ------------------------------------------------------------------------------------------ wgrad
 // dW[k][t][c] = sum over pixels m :  dY[m][k] * X_t[m][c]          (X_t = x shifted by tap t, zero outside)
-// Both operands are "MN-major": the reduction index (pixel) is the slow dimension in memory.  A stage holds
-// a chunk of 32 pixels: dY box {32 k, pixel box} x 4 (128 filters) and X box {32 c, pixel box} x BN/32, each a
-// 4 KB swizzled region whose rows are pixels.  UMMA descriptors: MN-block stride (LBO) 4096 B, 8-pixel group
-// stride (SBO) 1024 B.  grid = (k tiles * c tiles, taps, pixel splits); splits write partial sums that a
-// fixed-order reduction kernel adds (deterministic).
+// Both operands are "MN-major": the reduction index (pixel) is the slow dimension in memory.  A stage holds a
+// chunk of 32 pixels: KT*4 dY boxes {32 k, pixel box} (KT sub-tiles of 128 filters) and up to BN/32 X boxes
+// {32 c, pixel box}, each a 4 KB swizzled region whose rows are pixels.  UMMA descriptors: MN-block stride (LBO)
+// 4096 B, 4-pixel group stride (SBO) 512 B.
+// The N dimension of one MMA is a GROUP OF TAPS x channels: for C < 256 a CTA accumulates gt consecutive taps
+// (N = gt*C <= 256) against the same dY chunk, so dY is loaded and read once per gt taps; the accumulator columns
+// [j*C, (j+1)*C) are exactly dW[k][tap0+j][0..C), contiguous in the KRSC gradient.  For C >= 256, gt = 1 and the
+// channels are tiled by 256.  grid = (k tiles * c tiles, tap groups, pixel splits); splits write partial sums that
+// a fixed-order reduction kernel adds (deterministic).
 struct UmmaWgradP {
   int tiles_c;                   // c tiles per k tile (blockIdx.x = kt * tiles_c + ct)
   int tiles_w, tiles_h, tiles_n; // pixel-chunk grid
   int lw, lh;                    // log2 chunk box width / height (bw*bh*bn == 32)
   int chunks, chunks_per_split;
-  int K, C, T;                   // dW[K][T][C]
+  int K, C, T;                   // dW[K][T][C]  (row stride of the output = T*C)
+  int gt;                        // taps per group
+  int cpb;                       // 32-channel blocks per tap inside one CTA's N range
   long long split_stride;        // elements between partial results
   unsigned long long desc_hi;    // descriptor bits above the start address (LBO, SBO, version, layout type)
-  int ntapn;                     // > 0: "taps as N" mode -- the N dimension is ntapn blocks of 32 packed columns,
-                                 //      block j loaded with taps[j] (thin-tensor wgrad, see conv_wgrad_thin_launch)
-  unsigned int idesc;            // instruction descriptor override for that mode (N = 32 * ntapn)
   int4 taps[kMaxTaps];           // {channel offset, dw, hp, dh} of x for each filter tap
 };
 
@@ -240,15 +243,23 @@ __host__ __device__ inline uint64_t mn_desc_hi(uint32_t lbo_bytes, uint32_t sbo_
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+template <int BN, int KT>
+struct WgradCfg {
+  static constexpr int kStageBytes = KT * kABytes + BN * 128;
+  static constexpr int kStages = (208 * 1024) / kStageBytes < 8 ? (208 * 1024) / kStageBytes : 8;
+  static constexpr int kTmemCols = KT * BN < 32 ? 32 : KT * BN;
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
+  static constexpr int kProducers = 4;                        // TMA-issuing warps (boxes dealt round robin)
+  static constexpr int kThreads = 32 * (5 + kProducers);      // warp 0 MMA, warps 1-4 epilogue, then producers
+};
+
+template <int BN, int KT>
+__global__ void __launch_bounds__((WgradCfg<BN, KT>::kThreads), 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ UmmaWgradP p, float* __restrict__ out) {
-  using Cfg = UmmaCfg<BN>;
-  // same stage size as the forward kernel: 16 KB of dY + BN*128 B of X per 32-pixel chunk
-  constexpr uint32_t kIdescMN = Cfg::kIdesc | (1u << 15) | (1u << 16);     // A and B MN-major
+  using Cfg = WgradCfg<BN, KT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tmem_full = empty + Cfg::kStages;
@@ -256,8 +267,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x / p.tiles_c, ct = blockIdx.x % p.tiles_c;
-  const int tap = blockIdx.y;
-  const int k0 = kt * 128, c0 = ct * BN;
+  const int tap0 = blockIdx.y * p.gt;
+  const int ntaps = min(p.gt, p.T - tap0);
+  const int nblk = ntaps * p.cpb;                     // 32-column N blocks of this CTA
+  const int k0 = kt * 128 * KT, c0 = ct * BN;
   const int ch_beg = blockIdx.z * p.chunks_per_split;
   const int ch_end = min(p.chunks, ch_beg + p.chunks_per_split);
   const int iters = ch_end - ch_beg;
@@ -265,22 +278,24 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int bn = 32 >> (p.lw + p.lh);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kProducers); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_dy) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_x) : "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 0) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp >= 5) {
     if (lane == 0) {
-      const int4 tp = p.taps[tap];
-      const int nbx = p.ntapn > 0 ? p.ntapn : BN / 32;
+      const int pw = warp - 5;
+      const int nboxes = KT * 4 + nblk;
+      int mine = 0;
+      for (int b = pw; b < nboxes; b += Cfg::kProducers) ++mine;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -291,36 +306,39 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int q0 = tw * bw, p0 = th * bh, n0 = tn * bn;
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
-        mbar_expect_tx(full + stage, kABytes + nbx * 4096);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_5d(&map_dy, full + stage, sa + j * 4096, k0 + 32 * j, q0, 0, p0, n0);
-        if (p.ntapn > 0) {
-          for (int j = 0; j < nbx; ++j) {
-            const int4 tj = p.taps[j];
-            tma_load_5d(&map_x, full + stage, sa + kABytes + j * 4096, tj.x, q0 + tj.y, tj.z, p0 + tj.w, n0);
+        mbar_expect_tx(full + stage, mine * 4096);
+        for (int b = pw; b < nboxes; b += Cfg::kProducers) {
+          if (b < KT * 4) {
+            tma_load_5d(&map_dy, full + stage, sa + b * 4096, k0 + 32 * b, q0, 0, p0, n0);
+          } else {
+            const int j = b - KT * 4;
+            const int4 tj = p.taps[tap0 + j / p.cpb];
+            tma_load_5d(&map_x, full + stage, sa + KT * kABytes + j * 4096, c0 + 32 * (j % p.cpb) + tj.x, q0 + tj.y, tj.z,
+                        p0 + tj.w, n0);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_5d(&map_x, full + stage, sa + kABytes + j * 4096, c0 + 32 * j + tp.x, q0 + tp.y, tp.z, p0 + tp.w, n0);
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 0) {
     if (lane == 0) {
-      const uint32_t idesc = p.ntapn > 0 ? p.idesc : kIdescMN;
+      // D = f32, A = B = tf32, both MN-major, N = 32 * nblk, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)((nblk * 32) >> 3) << 17) | ((128u >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-        const uint64_t adesc = p.desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
-        const uint64_t bdesc = p.desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
+        const uint64_t bdesc = p.desc_hi | (uint64_t)(((sa + KT * kABytes) >> 4) & 0x3FFF);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)       // 4 x 8 pixels; 8 pixel rows = 1024 B further (+64 in the address field)
-          umma_tf32(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it | k) != 0);
+        for (int t = 0; t < KT; ++t) {
+          const uint64_t adesc = p.desc_hi | (uint64_t)(((sa + t * kABytes) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // 4 x 8 pixels; 8 pixel rows = 1024 B further (+64 in the address field)
+            umma_tf32(tmem_base + t * BN, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it | k) != 0);
+        }
         umma_commit(empty + stage);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -328,28 +346,29 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     }
   } else {
     const int quad = warp & 3;
-    const int k = k0 + quad * 32 + lane;                 // accumulator row == filter index
-    const bool valid = k < p.K && iters > 0;
-    float* orow = out + (size_t)blockIdx.z * p.split_stride + ((size_t)k * p.T + tap) * p.C;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      tmem_ld32(taddr + c, v);
-      if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int col = c0 + c + j;
-          if (col < p.C) *reinterpret_cast<float4*>(orow + col) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int t = 0; t < KT; ++t) {
+      const int k = k0 + t * 128 + quad * 32 + lane;     // accumulator row == filter index
+      const bool valid = k < p.K && iters > 0;
+      float* orow = out + (size_t)blockIdx.z * p.split_stride + ((size_t)k * p.T + tap0) * p.C + c0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * BN;
+#pragma unroll 1
+      for (int c = 0; c < nblk * 32; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        if (valid && c0 + (c % (p.cpb * 32)) < p.C) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -676,11 +695,26 @@ __global__ void pad_channels_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
-struct WgradPlan { int BN, lw, lh, tiles_w, tiles_h, tiles_n, chunks, cps, splits, tiles_k, tiles_c; };
+struct WgradPlan { int BN, KT, gt, cpb, ngroups, lw, lh, tiles_w, tiles_h, tiles_n, chunks, cps, splits, tiles_k, tiles_c; };
+
+static int pow2_at_least(int v, int lo) { int b = lo; while (b < v) b *= 2; return b; }
 
 static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
   WgradPlan w;
-  w.BN = d->C >= 256 ? 256 : (d->C >= 128 ? 128 : (d->C >= 64 ? 64 : 32));
+  const int T = d->R * d->S;
+  if (d->C >= 256) {
+    w.BN = 256; w.cpb = 8; w.gt = 1; w.ngroups = T; w.tiles_c = ceil_div(d->C, 256);
+  } else {
+    w.cpb = d->C / 32;
+    int gt_max = 256 / d->C;
+    if (gt_max < 1) gt_max = 1;
+    w.ngroups = ceil_div(T, gt_max);
+    w.gt = ceil_div(T, w.ngroups);
+    w.tiles_c = 1;
+    w.BN = pow2_at_least(w.gt * d->C, 32);
+  }
+  w.KT = d->K > 128 ? 2 : 1;
+  w.tiles_k = ceil_div(d->K, 128 * w.KT);
   int bw = 1 << ilog2(d->Q);
   if (bw > 32) bw = 32;
   int bh = 1 << ilog2(d->P);
@@ -689,10 +723,9 @@ static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
   int bn = 32 / (bw * bh);
   w.tiles_w = ceil_div(d->Q, bw); w.tiles_h = ceil_div(d->P, bh); w.tiles_n = ceil_div(d->N, bn);
   w.chunks = w.tiles_w * w.tiles_h * w.tiles_n;
-  w.tiles_k = ceil_div(d->K, 128); w.tiles_c = ceil_div(d->C, w.BN);
-  int tiles = w.tiles_k * w.tiles_c * d->R * d->S;
-  int splits = ceil_div(2 * kNumSMs, tiles);
-  if (splits > w.chunks) splits = w.chunks;
+  int tiles = w.tiles_k * w.tiles_c * w.ngroups;
+  int splits = ceil_div(2 * kNumSMs, tiles);              // one resident CTA per SM: about two rounds
+  if (splits > ceil_div(w.chunks, 8)) splits = ceil_div(w.chunks, 8);
   if (splits > 128) splits = 128;
   if (splits < 1) splits = 1;
   w.cps = ceil_div(w.chunks, splits);
@@ -793,19 +826,37 @@ void splitk_reduce_launch(const float* part, float* out, long long n, int splits
 int colsum_launch(const float* x, float* out, long long rows, int C, float* scratch, int scratch_blocks,
                   cudaStream_t st);
 
-template <int BN>
-static int launch_wgrad_bn(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
-                           cudaStream_t st) {
-  using Cfg = UmmaCfg<BN>;
+template <int BN, int KT>
+static int launch_wgrad_cfg(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
+                            cudaStream_t st) {
+  using Cfg = WgradCfg<BN, KT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmem);
     if (e != cudaSuccess) { set_error("wgrad_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  wgrad_umma_kernel<BN><<<grid, kUmmaThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
+  wgrad_umma_kernel<BN, KT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
   SRGAN_RETURN_LAUNCH();
+}
+
+static int launch_wgrad(int BN, int KT, const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out,
+                        dim3 grid, cudaStream_t st) {
+  if (KT == 2) {
+    switch (BN) {
+      case 256: return launch_wgrad_cfg<256, 2>(mdy, mx, p, out, grid, st);
+      case 128: return launch_wgrad_cfg<128, 2>(mdy, mx, p, out, grid, st);
+      case 64:  return launch_wgrad_cfg<64, 2>(mdy, mx, p, out, grid, st);
+      default:  return launch_wgrad_cfg<32, 2>(mdy, mx, p, out, grid, st);
+    }
+  }
+  switch (BN) {
+    case 256: return launch_wgrad_cfg<256, 1>(mdy, mx, p, out, grid, st);
+    case 128: return launch_wgrad_cfg<128, 1>(mdy, mx, p, out, grid, st);
+    case 64:  return launch_wgrad_cfg<64, 1>(mdy, mx, p, out, grid, st);
+    default:  return launch_wgrad_cfg<32, 1>(mdy, mx, p, out, grid, st);
+  }
 }
 
 
@@ -867,23 +918,13 @@ static int conv_wgrad_thin_launch(const srgan_conv_desc* d, const ThinPlan& t, c
   UmmaWgradP p = {};
   p.tiles_c = 1; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
   p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
-  p.K = t.fC; p.C = (int)row_elems; p.T = 1;
+  p.K = t.fC; p.C = 32; p.T = t.R;                // out[row][r][32]: the R filter rows are one tap group
+  p.gt = t.R; p.cpb = 1;
   p.split_stride = (long long)part_elems;
   p.desc_hi = mn_desc_hi(4096, 512, 1);
-  p.ntapn = t.R;
-  // D=f32, A=B=tf32, both MN-major, N = 32*R, M = 128
-  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((t.R * 32) >> 3) << 17) |
-            ((128u >> 4) << 24);
   for (int r = 0; r < t.R; ++r) p.taps[r] = make_int4(0, 0, r % t.st, r / t.st);
   dim3 grid(1, 1, w.splits);
-  int e;
-  switch (w.BN) {
-    case 256: e = launch_wgrad_bn<256>(mfat, mthin, p, part, grid, st); break;
-    case 128: e = launch_wgrad_bn<128>(mfat, mthin, p, part, grid, st); break;
-    case 64:  e = launch_wgrad_bn<64>(mfat, mthin, p, part, grid, st); break;
-    default:  e = launch_wgrad_bn<32>(mfat, mthin, p, part, grid, st); break;
-  }
-  if (e) return e;
+  if (int e = launch_wgrad(w.BN, 1, mfat, mthin, p, part, grid, st)) return e;
   thin_unpack_wgrad_kernel<<<ceil_div(d->K * d->R * d->S * d->C, 256), 256, 0, st>>>(
       part, dw, d->K, d->C, d->R, d->S, t.mode, w.splits, (long long)part_elems);
   SRGAN_RETURN_LAUNCH();
@@ -948,6 +989,7 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
   p.tiles_c = w.tiles_c; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
   p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
   p.K = d->K; p.C = C; p.T = T;
+  p.gt = w.gt; p.cpb = w.cpb;
   p.split_stride = (long long)d->K * T * C;
   p.desc_hi = mn_desc_hi(e_lbo ? atoi(e_lbo) : 4096, e_sbo ? atoi(e_sbo) : 512, e_lay ? atoi(e_lay) : 1);
   for (int r = 0; r < d->R; ++r)
@@ -957,15 +999,8 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
       else p.taps[r * d->S + s] = make_int4((((b % 2) + 2) % 2) * C, floordiv2(b), ((a % 2) + 2) % 2, floordiv2(a));
     }
   float* out = w.splits > 1 ? part : dw;
-  dim3 grid(w.tiles_k * w.tiles_c, T, w.splits);
-  int e;
-  switch (w.BN) {
-    case 256: e = launch_wgrad_bn<256>(mdy, mx, p, out, grid, st); break;
-    case 128: e = launch_wgrad_bn<128>(mdy, mx, p, out, grid, st); break;
-    case 64:  e = launch_wgrad_bn<64>(mdy, mx, p, out, grid, st); break;
-    default:  e = launch_wgrad_bn<32>(mdy, mx, p, out, grid, st); break;
-  }
-  if (e) return e;
+  dim3 grid(w.tiles_k * w.tiles_c, w.ngroups, w.splits);
+  if (int e = launch_wgrad(w.BN, w.KT, mdy, mx, p, out, grid, st)) return e;
   if (w.splits > 1) splitk_reduce_launch(part, dw, (long long)d->K * T * C, w.splits, st);
   SRGAN_RETURN_LAUNCH();
 }

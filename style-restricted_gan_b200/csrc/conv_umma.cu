@@ -37,6 +37,7 @@ struct UmmaConvP {
   int act;
   float slope;
   int cls_oph[4], cls_opw[4];    // output pixel parity of each class
+  int gx, gy, gz;                // work items: tile groups (MT tiles each) x filter tiles x parity classes
   int tap_begin[5];
   int4 taps[kMaxTaps];           // {channel offset, dw, hp | (filter tap << 8), dh}
 };
@@ -49,7 +50,8 @@ struct UmmaCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
   static constexpr int kStages = (212 * 1024) / kStageBytes < 8 ? (212 * 1024) / kStageBytes : 8;
-  static constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
+  static constexpr int kAccBufs = 2 * MT * BN <= 512 ? 2 : 1;   // accumulator double buffering when TMEM allows
+  static constexpr int kTmemCols = kAccBufs * MT * BN < 32 ? 32 : kAccBufs * MT * BN;
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   // TMA issue: measured with tools/tma_probe.cu, the bulk-tensor loads of ONE warp execute back to back (~750-1100
   // clk each, whatever their size) while loads of different warps overlap.  A stage is therefore cut into kBoxes
@@ -63,41 +65,32 @@ struct UmmaCfg {
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
 };
 
+// Persistent: gridDim.x CTAs (one per SM) walk over the work items (tile group, filter tile, parity class) with a
+// stride of gridDim.x.  The smem stage ring runs across items without draining; with 2*MT*BN <= 512 TMEM columns
+// the accumulator is double buffered, so the epilogue of item i overlaps the MMAs of item i+1 (this is what
+// matters for short reductions: a stride-2 dgrad class has 4 taps, the packed RGB stem 7 stages in total).
 template <int BN, int MT>
 __global__ void __launch_bounds__((UmmaCfg<BN, MT>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y) {
   using Cfg = UmmaCfg<BN, MT>;
+  constexpr int NBUF = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + Cfg::kStages;          // [NBUF] accumulator complete
+  uint64_t* tempty = tfull + 2;                    // [NBUF] accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.z;
-  const int tap0 = p.tap_begin[cls], ntaps = p.tap_begin[cls + 1] - tap0;
-  const int iters = ntaps * p.c_chunks;
-
-  // tile origins in the pixel grid: this CTA owns the MT consecutive tiles MT*blockIdx.x + mt (a tile index past
-  // the grid decodes to an image index >= Nn: its loads are TMA zero-fill and its stores are masked)
   const int bw = 1 << p.lw, bh = 1 << p.lh;
   const int bn = 128 >> (p.lw + p.lh);
-  int q0[MT], p0[MT], n0[MT];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    int t = blockIdx.x * MT + mt;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    const int tn = t / p.tiles_h;
-    q0[mt] = tw * bw; p0[mt] = th * bh; n0[mt] = tn * bn;
-  }
-  const int col0 = blockIdx.y * BN;
+  const int items = p.gx * p.gy * p.gz;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kBoxes); mbar_init(empty + s, 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
@@ -112,92 +105,118 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ------------------------------------------------------------------ TMA producers (one box each, every 2nd stage)
     if (lane == 0) {
       const int pw = warp - 5;
-      const int box = pw % Cfg::kBoxes;
-      for (int it = pw / Cfg::kBoxes; it < iters; it += 2) {
-        const int stage = it % Cfg::kStages;
-        const uint32_t phase = (uint32_t)(it / Cfg::kStages) & 1u;
-        const int tap = tap0 + it / p.c_chunks;
-        const int cc = (it % p.c_chunks) * 32;
-        const int4 tp = p.taps[tap];
-        mbar_wait(empty + stage, phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
+      const int box = pw % Cfg::kBoxes, par = pw / Cfg::kBoxes;
+      int gi0 = 0;                                   // ring index of the first stage of the current item
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
+        const int tap0 = p.tap_begin[cls];
+        const int iters = (p.tap_begin[cls + 1] - tap0) * p.c_chunks;
+        int qb = 0, pb = 0, nb = 0;
         if (box < MT) {
-          mbar_expect_tx(full + stage, kABytes);
-          int qb = q0[0], pb = p0[0], nb = n0[0];
-#pragma unroll
-          for (int mt = 1; mt < MT; ++mt)
-            if (box == mt) { qb = q0[mt]; pb = p0[mt]; nb = n0[mt]; }
-          tma_load_5d(&map_a, full + stage, sa + box * kABytes, cc + tp.x, qb + tp.y, tp.z & 0xff, pb + tp.w, nb);
-        } else {
-          const int rb = (box - MT) * Cfg::kBRows;
-          mbar_expect_tx(full + stage, Cfg::kBRows * 128);
-          tma_load_3d(&map_b, full + stage, sa + MT * kABytes + rb * 128, cc, tp.z >> 8, col0 + rb);
+          int t = bx * MT + box;
+          const int tw = t % p.tiles_w; t /= p.tiles_w;
+          qb = tw * bw; pb = (t % p.tiles_h) * bh; nb = (t / p.tiles_h) * bn;
         }
+        for (int it = (gi0 + par) & 1; it < iters; it += 2) {       // stages with (gi0 + it) % 2 == par
+          const int gi = gi0 + it;
+          const int stage = gi % Cfg::kStages;
+          const uint32_t phase = (uint32_t)(gi / Cfg::kStages) & 1u;
+          const int4 tp = p.taps[tap0 + it / p.c_chunks];
+          const int cc = (it % p.c_chunks) * 32;
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
+          if (box < MT) {
+            mbar_expect_tx(full + stage, kABytes);
+            tma_load_5d(&map_a, full + stage, sa + box * kABytes, cc + tp.x, qb + tp.y, tp.z & 0xff, pb + tp.w, nb);
+          } else {
+            const int rb = (box - MT) * Cfg::kBRows;
+            mbar_expect_tx(full + stage, Cfg::kBRows * 128);
+            tma_load_3d(&map_b, full + stage, sa + MT * kABytes + rb * 128, cc, tp.z >> 8, by * BN + rb);
+          }
+        }
+        gi0 += iters;
       }
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, li = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(full + stage, phase);
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+        const int cls = item / (p.gx * p.gy);
+        const int iters = (p.tap_begin[cls + 1] - p.tap_begin[cls]) * p.c_chunks;
+        const int buf = li % NBUF;
+        mbar_wait(tempty + buf, (((uint32_t)(li / NBUF)) & 1u) ^ 1u);       // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-        const uint64_t bdesc = smem_desc_sw128(sa + MT * kABytes);
+        const uint32_t acc = tmem_base + buf * (MT * BN);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+          const uint64_t bdesc = smem_desc_sw128(sa + MT * kABytes);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint64_t adesc = smem_desc_sw128(sa + mt * kABytes);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = smem_desc_sw128(sa + mt * kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)     // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
-            umma_tf32(tmem_base + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc,
-                      (it | k) != 0);
+            for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
+              umma_tf32(acc + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc, (it | k) != 0);
+          }
+          umma_commit(empty + stage);     // stage reusable once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(empty + stage);       // stage reusable once these MMAs have read it
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        umma_commit(tfull + buf);         // accumulator complete
       }
-      umma_commit(tmem_full);             // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
     const int m = quad * 32 + lane;                    // accumulator row == pixel within the tile
     const int wl = m & (bw - 1), hl = (m >> p.lw) & (bh - 1), nl = m >> (p.lw + p.lh);
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     constexpr int kChunk = BN >= 32 ? 32 : 16;
+    int li = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+      const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
+      const int col0 = by * BN;
+      const int buf = li % NBUF;
+      mbar_wait(tfull + buf, ((uint32_t)(li / NBUF)) & 1u);
+      tc_fence_after();
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-    const int n = n0[mt] + nl, pp = p0[mt] + hl, qq = q0[mt] + wl;
-    const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
-    float* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
-                       (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * BN;
+      for (int mt = 0; mt < MT; ++mt) {
+        int t = bx * MT + mt;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int n = (t / p.tiles_h) * bn + nl, pp = (t % p.tiles_h) * bh + hl, qq = tw * bw + wl;
+        const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
+        float* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
+                           (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MT * BN) + mt * BN;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += kChunk) {
-      float v[32];
-      if (kChunk == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
-      if (valid) {
+        for (int c = 0; c < BN; c += kChunk) {
+          float v[32];
+          if (kChunk == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
+          if (valid) {
 #pragma unroll
-        for (int j = 0; j < kChunk; j += 4) {
-          const int col = col0 + c + j;
-          if (col + 3 < p.K && (p.out_C & 3) == 0) {
-            float4 o;
-            o.x = apply_act(v[j + 0] + (bias ? __ldg(bias + col + 0) : 0.f), p.act, p.slope);
-            o.y = apply_act(v[j + 1] + (bias ? __ldg(bias + col + 1) : 0.f), p.act, p.slope);
-            o.z = apply_act(v[j + 2] + (bias ? __ldg(bias + col + 2) : 0.f), p.act, p.slope);
-            o.w = apply_act(v[j + 3] + (bias ? __ldg(bias + col + 3) : 0.f), p.act, p.slope);
-            *reinterpret_cast<float4*>(yrow + col) = o;
-          } else {
-            for (int e = 0; e < 4; ++e)
-              if (col + e < p.K)
-                yrow[col + e] = apply_act(v[j + e] + (bias ? __ldg(bias + col + e) : 0.f), p.act, p.slope);
+            for (int j = 0; j < kChunk; j += 4) {
+              const int col = col0 + c + j;
+              if (col + 3 < p.K && (p.out_C & 3) == 0) {
+                float4 o;
+                o.x = apply_act(v[j + 0] + (bias ? __ldg(bias + col + 0) : 0.f), p.act, p.slope);
+                o.y = apply_act(v[j + 1] + (bias ? __ldg(bias + col + 1) : 0.f), p.act, p.slope);
+                o.z = apply_act(v[j + 2] + (bias ? __ldg(bias + col + 2) : 0.f), p.act, p.slope);
+                o.w = apply_act(v[j + 3] + (bias ? __ldg(bias + col + 3) : 0.f), p.act, p.slope);
+                *reinterpret_cast<float4*>(yrow + col) = o;
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.K)
+                    yrow[col + e] = apply_act(v[j + e] + (bias ? __ldg(bias + col + e) : 0.f), p.act, p.slope);
+              }
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + buf);
     }
-    }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 0) {
@@ -422,8 +441,11 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  grid.x = (grid.x + MT - 1) / MT;
-  conv_umma_kernel<BN, MT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, p, bias, y);
+  UmmaConvP q = p;
+  q.gx = (grid.x + MT - 1) / MT; q.gy = grid.y; q.gz = grid.z;
+  const long items = (long)q.gx * q.gy * q.gz;
+  const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);     // persistent: one CTA per SM
+  conv_umma_kernel<BN, MT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y);
   SRGAN_RETURN_LAUNCH();
 }
 

@@ -12,6 +12,7 @@
 // staging buffer; the row shift is a ring of partial output rows in shared memory (a CTA walks down a band
 // of rows, so each input row is read from global memory once per band).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2..5 epilogue.
+#include <stdlib.h>
 #include "umma_ptx.cuh"
 
 namespace srgan {
@@ -175,6 +176,187 @@ conv_thinout_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant 2: the column shift is done by the tensor core.  For filter column s the A operand is the SAME smem row
+// buffer read through a descriptor whose start address is advanced by s pixel rows (s*128 B; the row buffer holds
+// pixels -padW .. 127+S-1-padW, TMA zero-fills outside the image), multiplied by the 32-row filter slice
+// Bs[s][(r*4+t)][f]:   D[q][(r,t)] = sum_s sum_f in[q + s - padW][f] * W[(r,s,t)][f].
+// D has only 32 columns, the epilogue is one tcgen05.ld per image row plus the row ring -- no shared-memory
+// transpose.  The row-shifted start is not 1024-byte aligned; measured on B200: the 128-byte swizzle XOR is taken
+// from the absolute shared-memory address bits, so the shifted descriptor reads exactly the rows TMA wrote (the
+// descriptor's base-offset field must stay 0 -- setting it to (start >> 7) & 7 gives wrong results).
+constexpr int kTO2ARows = 144;                              // smem rows per chunk: 128 + S-1 (<= 7) pixels, padded
+constexpr int kTO2ABytes = kTO2ARows * 128;                 // 18 KB, multiple of 1024
+
+struct ThinOut2P {
+  int Hi, Wi, Ho, Wo;
+  int tc, R, S, padH, padW;
+  int nchunks, bands, BH;
+  int act;
+  float slope;
+};
+
+__global__ void __launch_bounds__(kTOThreads, 1)
+conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ ThinOut2P p, const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int b_bytes = p.S * p.nchunks * 4096;           // Bs[s][chunk][32 rows][32 f]
+  const int a_bytes = p.nchunks * kTO2ABytes;
+  uint8_t* sb = smem;
+  uint8_t* sa = smem + b_bytes;
+  float* accs = reinterpret_cast<float*>(sa + kTOStages * a_bytes);      // [8 rows][4][128]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(accs + 8 * 4 * 128);
+  uint64_t* a_empty = a_full + kTOStages;
+  uint64_t* t_full = a_empty + kTOStages;
+  uint64_t* t_empty = t_full + 2;
+  uint64_t* b_full = t_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x / p.bands, band = blockIdx.x % p.bands;
+  const int h0 = band * p.BH, h1 = min(p.Ho, h0 + p.BH);
+  const int hp_beg = h0 - p.padH, hp_end = (h1 - 1) - p.padH + (p.R - 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTOStages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4); }
+    mbar_init(b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+  }
+  for (int i = threadIdx.x; i < 8 * 4 * 128; i += kTOThreads) accs[i] = 0.f;
+  // rows 128+S-1 .. 143 of every A buffer are never written by TMA: zero them once (they are only read by
+  // accumulator rows that do not exist, but NaN garbage must not reach the tensor core's exception paths)
+  for (int i = threadIdx.x; i < kTOStages * a_bytes / 4; i += kTOThreads) reinterpret_cast<float*>(sa)[i] = 0.f;
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zero fill before TMA writes
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int box_bytes = (128 + p.S - 1) * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, b_bytes);
+      for (int j = 0; j < p.S * p.nchunks; ++j) tma_load_2d(&map_b, b_full, sb + j * 4096, 0, j * 32);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int hp = hp_beg; hp <= hp_end; ++hp) {
+        if (hp < 0 || hp >= p.Hi) continue;
+        mbar_wait(a_empty + stage, phase ^ 1);
+        uint8_t* dst = sa + stage * a_bytes;
+        mbar_expect_tx(a_full + stage, p.nchunks * box_bytes);
+        for (int j = 0; j < p.nchunks; ++j)
+          tma_load_4d(&map_in, a_full + stage, dst + j * kTO2ABytes, 32 * j, -p.padW, hp, n);
+        if (++stage == kTOStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = B = tf32, both K-major, N = 32, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      mbar_wait(b_full, 0);
+      int stage = 0, i = 0;
+      uint32_t phase = 0;
+      for (int hp = hp_beg; hp <= hp_end; ++hp) {
+        if (hp < 0 || hp >= p.Hi) continue;
+        const int buf = i & 1;
+        mbar_wait(a_full + stage, phase);
+        mbar_wait(t_empty + buf, ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sa + stage * a_bytes), b0 = smem_u32(sb);
+        // (measured: one accumulator per s, summed in the epilogue, is slower -- 242 vs 208 us -- the 56 N=32 MMAs per
+        //  image row are bound by their issue rate, not by the accumulate dependency)
+        uint32_t first = 1;
+        for (int s = 0; s < p.S; ++s)
+          for (int j = 0; j < p.nchunks; ++j) {
+            const uint32_t astart = a0 + j * kTO2ABytes + s * 128;        // row-shifted start (see above)
+            const uint64_t adesc = smem_desc_sw128(astart);
+            const uint64_t bdesc = smem_desc_sw128(b0 + (s * p.nchunks + j) * 4096);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_tf32(tmem_base + buf * 32, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ^ 1);
+              first = 0;
+            }
+          }
+        umma_commit(a_empty + stage);
+        umma_commit(t_full + buf);
+        if (++stage == kTOStages) { stage = 0; phase ^= 1; }
+        ++i;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int qq = quad * 32 + lane;                    // TMEM lane == output pixel q
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float bv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) bv[t] = (bias && t < p.tc) ? __ldg(bias + t) : 0.f;
+    int i = 0;
+    for (int hp = hp_beg; hp <= hp_end; ++hp) {
+      if (hp >= 0 && hp < p.Hi) {
+        const int buf = i & 1;
+        mbar_wait(t_full + buf, (i >> 1) & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(taddr + buf * 32, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + buf);      // accumulator is in registers: release it right away
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int h = hp - r + p.padH;
+          if (r < p.R && h >= h0 && h < h1) {
+            float* ar = accs + (h & 7) * 4 * 128 + qq;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (t < p.tc) ar[t * 128] += v[r * 4 + t];
+          }
+        }
+        ++i;
+      }
+      const int hd = hp + p.padH - (p.R - 1);
+      if (hd >= h0 && hd < h1) {
+        float* ar = accs + (hd & 7) * 4 * 128 + qq;
+        float* o = out + (((size_t)n * p.Ho + hd) * p.Wo + qq) * p.tc;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (t < p.tc) {
+            if (qq < p.Wo) o[t] = apply_act(ar[t * 128] + bv[t], p.act, p.slope);
+            ar[t * 128] = 0.f;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// Bs[s][chunk][r*4 + t][f32]  (rows of 32 floats = one 128-byte swizzle row)
+// mode 0: = w[t][r][s][chunk*32 + f] ; mode 1: = w[chunk*32 + f][R-1-r][S-1-s][t]
+__global__ void thinout2_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ bp, int K, int C, int R,
+                                            int S, int mode) {
+  const int F = mode == 0 ? C : K, tc = mode == 0 ? K : C;
+  const int nch = F / 32;
+  const int total = S * nch * 32 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int f = i & 31, row = (i >> 5) & 31, j = (i >> 10) % nch, s = i / (1024 * nch);
+    const int r = row >> 2, t = row & 3, ff = j * 32 + f;
+    float v = 0.f;
+    if (r < R && t < tc) {
+      if (mode == 0) v = w[(((size_t)t * R + r) * S + s) * C + ff];
+      else           v = w[(((size_t)ff * R + (R - 1 - r)) * S + (S - 1 - s)) * C + t];
+    }
+    bp[i] = v;
+  }
+}
+
 // mode 0 (fprop, K <= 4):  bp[r*32 + s*4 + k][c] = w[k][r][s][c]                    rows of C floats
 // mode 1 (dgrad, C <= 4):  bp[r'*32 + s'*4 + c][k] = w[k][R-1-r'][S-1-s'][c]        rows of K floats
 __global__ void thinout_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ bp, int K, int C, int R,
@@ -232,7 +414,8 @@ bool conv_thinout_supported(const srgan_conv_desc* d, int pass) {
 size_t conv_thinout_workspace(const srgan_conv_desc* d, int pass) {
   ThinOutPlan t;
   if (!thinout_plan(d, pass, &t)) return 0;
-  return (size_t)d->R * 32 * t.F * sizeof(float);
+  const int rs = d->R > d->S ? d->R : d->S;
+  return (size_t)rs * 32 * t.F * sizeof(float);
 }
 
 // pass 0: in = x, out = y (bias/activation fused);  pass 1: in = dy, out = dx
@@ -244,6 +427,38 @@ int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, con
   if (!ws || ws_bytes < need) { set_error("thin-output conv: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
   if (((uintptr_t)in | (uintptr_t)ws) % 16) { set_error("thin-output conv: tensors must be 16-byte aligned"); return SRGAN_E_BADARG; }
   float* bp = (float*)ws;
+  static const char* e_var = getenv("SRGAN_DBG_THINOUT");       // bring-up: 1 = transpose epilogue, 2 = MMA column shift
+  const int variant = e_var ? atoi(e_var) : 2;
+  if (variant >= 2) {
+    thinout2_pack_filter_kernel<<<ceil_div(d->S * t.F * 32, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
+    CUtensorMap min2, mb2;
+    {
+      uint64_t dims[4] = {(uint64_t)t.F, (uint64_t)t.Wi, (uint64_t)t.Hi, (uint64_t)d->N};
+      uint64_t str[3] = {(uint64_t)t.F * 4, (uint64_t)t.Wi * t.F * 4, (uint64_t)t.Hi * t.Wi * t.F * 4};
+      uint32_t box[4] = {32, (uint32_t)(128 + d->S - 1), 1, 1};
+      if (int e = encode_map(&min2, in, 4, dims, str, box)) return e;
+    }
+    {
+      uint64_t dims[2] = {32, (uint64_t)d->S * (t.F / 32) * 32};
+      uint64_t str[1] = {128};
+      uint32_t box[2] = {32, 32};
+      if (int e = encode_map(&mb2, bp, 2, dims, str, box)) return e;
+    }
+    ThinOut2P q = {};
+    q.Hi = t.Hi; q.Wi = t.Wi; q.Ho = t.Ho; q.Wo = t.Wo; q.tc = t.tc; q.R = d->R; q.S = d->S;
+    q.padH = t.padH; q.padW = t.padW; q.nchunks = t.F / 32; q.bands = t.bands; q.BH = t.BH;
+    q.act = act; q.slope = slope;
+    const size_t smem2 = 1024 + (size_t)d->S * q.nchunks * 4096 + (size_t)kTOStages * q.nchunks * kTO2ABytes +
+                         8 * 4 * 128 * sizeof(float) + 256;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(conv_thinout2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) { set_error("conv_thinout2 smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+      attr2 = true;
+    }
+    conv_thinout2_kernel<<<d->N * t.bands, kTOThreads, smem2, st>>>(min2, mb2, q, bias, out);
+    SRGAN_RETURN_LAUNCH();
+  }
   thinout_pack_filter_kernel<<<ceil_div(d->R * 32 * t.F, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
   CUtensorMap min, mb;
   {

@@ -500,12 +500,15 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   p.out_H = pr.out_H; p.out_W = pr.out_W; p.out_C = pr.fK; p.os = pr.os; p.K = pr.fK;
   p.act = act; p.slope = slope;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
-  // two M sub-tiles per CTA once that still leaves every SM a CTA (bring-up override: SRGAN_DBG_CONV_MT=1|2)
+  // Two M sub-tiles per CTA (one filter tile feeds 256 pixels) when TMEM can still double-buffer the accumulator
+  // (2 x 2 x 128 columns) and every SM keeps work; 256-wide tiles stay at MT = 1: overlapping the epilogue with the
+  // next item's MMAs is worth more than sharing the filter tile (res conv 139 us vs 165 us).
+  // Bring-up override: SRGAN_DBG_CONV_MT=1|2.
   static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
   const long ctas = (long)grid.x * grid.y * grid.z;
-  const bool mt2 = e_mt ? atoi(e_mt) == 2 : ctas >= 2 * kNumSMs;
-  if (mt2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st);
-  if (mt2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st);
+  const int mt = e_mt ? atoi(e_mt) : (BN == 128 && ctas >= 2 * kNumSMs ? 2 : 1);
+  if (mt == 2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st);
+  if (mt == 2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st);
   switch (BN) {
     case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st);
     case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st);

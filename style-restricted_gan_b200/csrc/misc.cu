@@ -248,43 +248,47 @@ __global__ void condbias_fwd_kernel(const float* __restrict__ con, const float* 
     t[i] = tanhf(s);
   }
 }
-// one block per channel tile is overkill at these sizes: one thread per (c,j) for dw, per c for db,
-// per (n,j) for dcon; all loops run in a fixed order.
+// One WARP per output element (dw[c][j], db[c], dcon[n][j]): lanes stride over the reduction index and a
+// butterfly shuffle adds them in a fixed order (deterministic); the loads of a warp are independent, so the
+// kernel is no longer a chain of 64-256 dependent loads per thread.
 __global__ void condbias_bwd_kernel(const float* __restrict__ dt, const float* __restrict__ t,
                                     const float* __restrict__ con, const float* __restrict__ w,
                                     float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dcon,
                                     int N, int J, int C) {
   const size_t nw = (size_t)C * J, nb = C, nc = (size_t)N * J;
   const size_t total = nw + nb + nc;
-  GRID_STRIDE(i, total) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += warps) {
+    float s = 0.f;
     if (i < nw) {
       if (!dw) continue;
-      int c = (int)(i / J), j = (int)(i % J);
-      float s = 0.f;
-      for (int n = 0; n < N; ++n) {
-        float tv = __ldg(t + (size_t)n * C + c);
+      const int c = (int)(i / J), j = (int)(i % J);
+      for (int n = lane; n < N; n += 32) {
+        const float tv = __ldg(t + (size_t)n * C + c);
         s = fmaf(__ldg(dt + (size_t)n * C + c) * (1.f - tv * tv), __ldg(con + (size_t)n * J + j), s);
       }
-      dw[i] = s;
+      s = warp_sum(s);
+      if (lane == 0) dw[i] = s;
     } else if (i < nw + nb) {
       if (!db) continue;
-      int c = (int)(i - nw);
-      float s = 0.f;
-      for (int n = 0; n < N; ++n) {
-        float tv = __ldg(t + (size_t)n * C + c);
+      const int c = (int)(i - nw);
+      for (int n = lane; n < N; n += 32) {
+        const float tv = __ldg(t + (size_t)n * C + c);
         s += __ldg(dt + (size_t)n * C + c) * (1.f - tv * tv);
       }
-      db[c] = s;
+      s = warp_sum(s);
+      if (lane == 0) db[c] = s;
     } else {
       if (!dcon) continue;
-      size_t k = i - nw - nb;
-      int n = (int)(k / J), j = (int)(k % J);
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) {
-        float tv = __ldg(t + (size_t)n * C + c);
+      const size_t k = i - nw - nb;
+      const int n = (int)(k / J), j = (int)(k % J);
+      for (int c = lane; c < C; c += 32) {
+        const float tv = __ldg(t + (size_t)n * C + c);
         s = fmaf(__ldg(dt + (size_t)n * C + c) * (1.f - tv * tv), __ldg(w + (size_t)c * J + j), s);
       }
-      dcon[k] = s;
+      s = warp_sum(s);
+      if (lane == 0) dcon[k] = s;
     }
   }
 }
@@ -432,8 +436,8 @@ extern "C" int srgan_condbias_fwd(const float* con, const float* w, const float*
 extern "C" int srgan_condbias_bwd(const float* dt, const float* t, const float* con, const float* w, float* dw,
                                   float* db, float* dcon, int N, int J, int C, void* stream) {
   SRGAN_CHECK_ARG(dt && t && con && w && J > 0 && C > 0, "bad argument");
-  size_t total = (size_t)C * J + C + (size_t)N * J;
-  condbias_bwd_kernel<<<grid_for(total, 128), 128, 0, ST>>>(dt, t, con, w, dw, db, dcon, N, J, C);
+  size_t total = (size_t)C * J + C + (size_t)N * J;            // one warp per output
+  condbias_bwd_kernel<<<grid_for(total * 32, 256), 256, 0, ST>>>(dt, t, con, w, dw, db, dcon, N, J, C);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_softmax_fwd(const float* x, float* y, int N, int J, void* stream) {

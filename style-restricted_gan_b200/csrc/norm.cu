@@ -252,23 +252,29 @@ __global__ void __launch_bounds__(kNormThreads) inorm_bwd_apply_kernel(
 }
 
 // dgamma[c] = sum_n (s2 + cbias*s1) ; dbeta[c] = sum_n s1 ; dcbias[n][c] = gamma[c]*s1[n][c]
+// one warp per channel: lanes stride over the images, fixed-order butterfly reduction
 __global__ void inorm_param_grads_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
                                          const float* __restrict__ gamma, const float* __restrict__ cbias,
                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          float* __restrict__ dcbias, int N, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  float g = gamma ? gamma[c] : 1.f;
+  const float g = gamma ? gamma[c] : 1.f;
   float dg = 0.f, db = 0.f;
-  for (int n = 0; n < N; ++n) {
-    float a = s1[(size_t)n * C + c], b = s2[(size_t)n * C + c];
-    float t = cbias ? cbias[(size_t)n * C + c] : 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float a = s1[(size_t)n * C + c], b = s2[(size_t)n * C + c];
+    const float t = cbias ? cbias[(size_t)n * C + c] : 0.f;
     dg += b + t * a;
     db += a;
     if (dcbias) dcbias[(size_t)n * C + c] = g * a;
   }
-  if (dgamma) dgamma[c] = dg;
-  if (dbeta) dbeta[c] = db;
+  dg = warp_sum(dg);
+  db = warp_sum(db);
+  if (lane == 0) {
+    if (dgamma) dgamma[c] = dg;
+    if (dbeta) dbeta[c] = db;
+  }
 }
 
 // channel chunking + pixel slicing; returns false when C cannot be mapped onto 256 threads
@@ -355,7 +361,7 @@ extern "C" int srgan_inorm_param_grads(const float* s1, const float* s2, const f
                                        int C, void* stream) {
   SRGAN_CHECK_ARG(s1 && s2, "null pointer");
   if (C == 0) return SRGAN_OK;
-  inorm_param_grads_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(s1, s2, gamma, cbias, dgamma,
+  inorm_param_grads_kernel<<<ceil_div(C * 32, 256), 256, 0, (cudaStream_t)stream>>>(s1, s2, gamma, cbias, dgamma,
                                                                                   dbeta, dcbias, N, C);
   SRGAN_RETURN_LAUNCH();
 }

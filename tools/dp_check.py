@@ -80,7 +80,11 @@ def main():
             ok &= abs(got - r) <= 2e-4 * max(1.0, abs(r))
         for key in sorted(k for k in ref if k not in ("errs", "abi_calls")):
             rel = float((rec[key].double() - ref[key].double()).norm() / ref[key].double().norm().clamp_min(1e-30))
-            tol = 5e-2 if key in ("G1",) else (2e-2 if key.startswith("G") or key.startswith("E") else 2e-3)
+            # G1 = generator gradients of phase 2, taken AFTER the phase-1 Adam step: Adam turns 1e-4 relative
+            # gradient differences into sign-level weight differences, so this quantity is ill-conditioned; two
+            # fp32 CPU runs of the reference itself that differ only in thread count disagree by 8.5e-2
+            # (SURVEY F12).  Everything up to that step is held to 2e-3 / 2e-2.
+            tol = 2e-1 if key in ("G1",) else (2e-2 if key.startswith("G") or key.startswith("E") else 2e-3)
             print("  grads at %-3s rel-L2 vs 1-GPU = %.3e (tol %.0e)" % (key, rel, tol))
             ok &= rel < tol
         print("DP_CHECK", "PASS" if ok else "FAIL")

@@ -129,7 +129,8 @@ def test_linear():
 
 
 NORM_SHAPES = [(2, 64, 128, 128), (2, 128, 64, 64), (3, 256, 32, 32), (2, 64, 62, 62), (2, 128, 31, 31),
-               (2, 256, 15, 15), (5, 512, 7, 7), (1, 8, 3, 5), (2, 16, 9, 9), (40, 32, 16, 16)]
+               (2, 256, 15, 15), (5, 512, 7, 7), (1, 8, 3, 5), (2, 16, 9, 9), (40, 32, 16, 16),
+               (2, 24, 10, 10), (150, 64, 32, 32), (1, 64, 200, 200), (3, 1024, 3, 3)]
 
 
 @pytest.mark.parametrize("shape", NORM_SHAPES, ids=[str(s) for s in NORM_SHAPES])

@@ -36,6 +36,7 @@ struct UmmaConvP {
   int K;                         // valid output channels (columns)
   int act;
   float slope;
+  int epi_vec;                   // widest aligned vector store of a row: 8, 4 or 0 (scalar) floats
   int cls_oph[4], cls_opw[4];    // output pixel parity of each class
   int gx, gy, gz;                // work items: tile groups (MT tiles each) x filter tiles x parity classes
   int tap_begin[5];
@@ -69,6 +70,75 @@ struct UmmaCfg {
 // stride of gridDim.x.  The smem stage ring runs across items without draining; with 2*MT*BN <= 512 TMEM columns
 // the accumulator is double buffered, so the epilogue of item i overlaps the MMAs of item i+1 (this is what
 // matters for short reductions: a stride-2 dgrad class has 4 taps, the packed RGB stem 7 stages in total).
+// ---- epilogue helpers: straight-line code per activation (a per-element switch made the four epilogue warps the
+// bottleneck of every short-reduction layer), 32-byte stores so a thread always writes whole sectors
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float slope) {
+  if (ACT == SRGAN_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == SRGAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (ACT == SRGAN_ACT_TANH) return tanhf(v);
+  return v;
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float* o) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+               "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+}
+// act(v[0..N) + bias) -> dst[0..N), N a multiple of 8, dst aligned to VEC floats
+template <int ACT, int N, int VEC>
+__device__ __forceinline__ void epi_row_chunk(const float (&v)[32], float* __restrict__ dst,
+                                              const float* __restrict__ bias, float slope) {
+#pragma unroll
+  for (int j = 0; j < N; j += 8) {
+    float o[8];
+    if (bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j + 4));
+      o[0] = v[j] + b0.x; o[1] = v[j + 1] + b0.y; o[2] = v[j + 2] + b0.z; o[3] = v[j + 3] + b0.w;
+      o[4] = v[j + 4] + b1.x; o[5] = v[j + 5] + b1.y; o[6] = v[j + 6] + b1.z; o[7] = v[j + 7] + b1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = v[j + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = act_t<ACT>(o[e], slope);
+    if (VEC == 8) {
+      st_global_v8(dst + j, o);
+    } else {
+      *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void epi_row_chunk_any(const float (&v)[32], float* dst, const float* bias, int act,
+                                                  float slope, int vec) {
+#define SRGAN_EPI_CASE(A)                                                         \
+  case A:                                                                         \
+    if (vec == 8) epi_row_chunk<A, N, 8>(v, dst, bias, slope);                    \
+    else epi_row_chunk<A, N, 4>(v, dst, bias, slope);                             \
+    break;
+  switch (act) {
+    SRGAN_EPI_CASE(SRGAN_ACT_RELU)
+    SRGAN_EPI_CASE(SRGAN_ACT_LRELU)
+    SRGAN_EPI_CASE(SRGAN_ACT_TANH)
+    default:
+      if (vec == 8) epi_row_chunk<SRGAN_ACT_NONE, N, 8>(v, dst, bias, slope);
+      else epi_row_chunk<SRGAN_ACT_NONE, N, 4>(v, dst, bias, slope);
+  }
+#undef SRGAN_EPI_CASE
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 template <int BN, int MT>
 __global__ void __launch_bounds__((UmmaCfg<BN, MT>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -189,26 +259,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
                            (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MT * BN) + mt * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += kChunk) {
-          float v[32];
-          if (kChunk == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
-          if (valid) {
+        const float* brow = bias ? bias + col0 : nullptr;
+        if (kChunk == 32) {
+          // the TMEM load of chunk c + 1 is in flight while chunk c is converted and stored
+          uint32_t ra[32], rb[32];
+          tmem_ld32_issue(taddr, ra);
 #pragma unroll
-            for (int j = 0; j < kChunk; j += 4) {
-              const int col = col0 + c + j;
-              if (col + 3 < p.K && (p.out_C & 3) == 0) {
-                float4 o;
-                o.x = apply_act(v[j + 0] + (bias ? __ldg(bias + col + 0) : 0.f), p.act, p.slope);
-                o.y = apply_act(v[j + 1] + (bias ? __ldg(bias + col + 1) : 0.f), p.act, p.slope);
-                o.z = apply_act(v[j + 2] + (bias ? __ldg(bias + col + 2) : 0.f), p.act, p.slope);
-                o.w = apply_act(v[j + 3] + (bias ? __ldg(bias + col + 3) : 0.f), p.act, p.slope);
-                *reinterpret_cast<float4*>(yrow + col) = o;
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t (&cur)[32] = ((c >> 5) & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = ((c >> 5) & 1) ? ra : rb;
+            tmem_ld_wait();
+            if (c + 32 < BN) tmem_ld32_issue(taddr + c + 32, nxt);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
+            if (valid) {
+              if (col0 + c + 32 <= p.K && p.epi_vec) {
+                epi_row_chunk_any<32>(v, yrow + col0 + c, brow ? brow + c : nullptr, p.act, p.slope, p.epi_vec);
               } else {
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.K)
-                    yrow[col + e] = apply_act(v[j + e] + (bias ? __ldg(bias + col + e) : 0.f), p.act, p.slope);
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + c + j < p.K)
+                    yrow[col0 + c + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f), p.act, p.slope);
               }
+            }
+          }
+        } else {
+          float v[32];
+          tmem_ld16(taddr, v);
+          if (valid) {
+            if (col0 + 16 <= p.K && p.epi_vec) {
+              epi_row_chunk_any<16>(v, yrow + col0, brow, p.act, p.slope, p.epi_vec);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.K)
+                  yrow[col0 + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + j) : 0.f), p.act, p.slope);
             }
           }
         }
@@ -499,6 +583,8 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   p.Nn = pr.Nn; p.P = pr.P; p.Q = pr.Q;
   p.out_H = pr.out_H; p.out_W = pr.out_W; p.out_C = pr.fK; p.os = pr.os; p.K = pr.fK;
   p.act = act; p.slope = slope;
+  p.epi_vec = (pr.fK % 8 == 0 && (uintptr_t)y % 32 == 0) ? 8 : (pr.fK % 4 == 0 ? 4 : 0);
+  if (bias && (uintptr_t)bias % 16) p.epi_vec = 0;            // vector bias loads need an aligned bias
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
   // Two M sub-tiles per CTA (one filter tile feeds 256 pixels) when TMEM can still double-buffer the accumulator
   // (2 x 2 x 128 columns) and every SM keeps work; 256-wide tiles stay at MT = 1: overlapping the epilogue with the

@@ -1,3 +1,4 @@
 set -x
-timeout 600 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "instance_norm" > gpurun_out/pytest_norm.log 2>&1; tail -5 gpurun_out/pytest_norm.log
-timeout 300 python tools/conv_bench.py --only IN > gpurun_out/norm_resident.log 2>&1; cat gpurun_out/norm_resident.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu12.log 2>&1; tail -5 gpurun_out/pytest_gpu12.log
+timeout 600 python tools/conv_bench.py > gpurun_out/conv_bench_epi.log 2>&1; grep -E "^G\.|^D1\.[0-3]|^E\.first|total|top" gpurun_out/conv_bench_epi.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1h.log 2>&1; tail -1 gpurun_out/bench_r1h.log | cut -c1-400

@@ -39,6 +39,8 @@ struct UmmaConvP {
   int epi_vec;                   // widest aligned vector store of a row: 8, 4 or 0 (scalar) floats
   int cls_oph[4], cls_opw[4];    // output pixel parity of each class
   int gx, gy, gz;                // work items: tile groups (MT tiles each) x filter tiles x parity classes
+  int n_full, n_items;           // the first n_full items are whole tiles; the rest are half-width (BN/2 column)
+                                 // tiles, two per remaining tile (balances the last partial wave of CTAs)
   int tap_begin[5];
   int4 taps[kMaxTaps];           // {channel offset, dw, hp | (filter tap << 8), dh}
 };
@@ -139,6 +141,16 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// work item -> linear tile index, first column and width of the column range it covers
+struct UmmaItem { int lin, n_off, width; };
+template <int BN>
+__device__ __forceinline__ UmmaItem umma_item(const UmmaConvP& p, int item) {
+  UmmaItem u;
+  if (item < p.n_full) { u.lin = item; u.n_off = 0; u.width = BN; }
+  else { const int h = item - p.n_full; u.lin = p.n_full + (h >> 1); u.n_off = (h & 1) * (BN / 2); u.width = BN / 2; }
+  return u;
+}
+
 template <int BN, int MT>
 __global__ void __launch_bounds__((UmmaCfg<BN, MT>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -156,7 +168,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bw = 1 << p.lw, bh = 1 << p.lh;
   const int bn = 128 >> (p.lw + p.lh);
-  const int items = p.gx * p.gy * p.gz;
+  const int items = p.n_items;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kBoxes); mbar_init(empty + s, 1); }
@@ -178,7 +190,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int box = pw % Cfg::kBoxes, par = pw / Cfg::kBoxes;
       int gi0 = 0;                                   // ring index of the first stage of the current item
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
+        const UmmaItem u = umma_item<BN>(p, item);
+        const int bx = u.lin % p.gx, by = (u.lin / p.gx) % p.gy, cls = u.lin / (p.gx * p.gy);
         const int tap0 = p.tap_begin[cls];
         const int iters = (p.tap_begin[cls + 1] - tap0) * p.c_chunks;
         int qb = 0, pb = 0, nb = 0;
@@ -200,8 +213,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tma_load_5d(&map_a, full + stage, sa + box * kABytes, cc + tp.x, qb + tp.y, tp.z & 0xff, pb + tp.w, nb);
           } else {
             const int rb = (box - MT) * Cfg::kBRows;
-            mbar_expect_tx(full + stage, Cfg::kBRows * 128);
-            tma_load_3d(&map_b, full + stage, sa + MT * kABytes + rb * 128, cc, tp.z >> 8, by * BN + rb);
+            if (rb < u.width) {
+              mbar_expect_tx(full + stage, Cfg::kBRows * 128);
+              tma_load_3d(&map_b, full + stage, sa + MT * kABytes + rb * 128, cc, tp.z >> 8, by * BN + u.n_off + rb);
+            } else {
+              mbar_arrive(full + stage);         // half-width item: this filter box is not needed
+            }
           }
         }
         gi0 += iters;
@@ -213,8 +230,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0, li = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-        const int cls = item / (p.gx * p.gy);
+        const UmmaItem u = umma_item<BN>(p, item);
+        const int cls = u.lin / (p.gx * p.gy);
         const int iters = (p.tap_begin[cls + 1] - p.tap_begin[cls]) * p.c_chunks;
+        const uint32_t idesc = (Cfg::kIdesc & ~(0x3Fu << 17)) | ((uint32_t)(u.width >> 3) << 17);
         const int buf = li % NBUF;
         mbar_wait(tempty + buf, (((uint32_t)(li / NBUF)) & 1u) ^ 1u);       // epilogue drained this accumulator
         tc_fence_after();
@@ -229,7 +248,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint64_t adesc = smem_desc_sw128(sa + mt * kABytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
-              umma_tf32(acc + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc, (it | k) != 0);
+              umma_tf32(acc + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
           }
           umma_commit(empty + stage);     // stage reusable once these MMAs have read it
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -245,8 +264,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int kChunk = BN >= 32 ? 32 : 16;
     int li = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-      const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
-      const int col0 = by * BN;
+      const UmmaItem u = umma_item<BN>(p, item);
+      const int bx = u.lin % p.gx, by = (u.lin / p.gx) % p.gy, cls = u.lin / (p.gx * p.gy);
+      const int col0 = by * BN + u.n_off;
       const int buf = li % NBUF;
       mbar_wait(tfull + buf, ((uint32_t)(li / NBUF)) & 1u);
       tc_fence_after();
@@ -266,10 +286,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tmem_ld32_issue(taddr, ra);
 #pragma unroll
           for (int c = 0; c < BN; c += 32) {
+            if (c >= u.width) break;
             uint32_t (&cur)[32] = ((c >> 5) & 1) ? rb : ra;
             uint32_t (&nxt)[32] = ((c >> 5) & 1) ? ra : rb;
             tmem_ld_wait();
-            if (c + 32 < BN) tmem_ld32_issue(taddr + c + 32, nxt);
+            if (c + 32 < u.width) tmem_ld32_issue(taddr + c + 32, nxt);
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
@@ -330,6 +351,7 @@ struct UmmaWgradP {
   int gt;                        // taps per group
   int cpb;                       // 32-channel blocks per tap inside one CTA's N range
   long long split_stride;        // elements between partial results
+  int vec8;                      // every output row segment is 32-byte aligned (set by launch_wgrad)
   unsigned long long desc_hi;    // descriptor bits above the start address (LBO, SBO, version, layout type)
   int4 taps[kMaxTaps];           // {channel offset, dw, hp, dh} of x for each filter tap
 };
@@ -346,21 +368,21 @@ __host__ __device__ inline uint64_t mn_desc_hi(uint32_t lbo_bytes, uint32_t sbo_
   return d;
 }
 
-template <int BN, int KT>
+template <int BN, int KT, int PW = 4>
 struct WgradCfg {
   static constexpr int kStageBytes = KT * kABytes + BN * 128;
   static constexpr int kStages = (208 * 1024) / kStageBytes < 8 ? (208 * 1024) / kStageBytes : 8;
   static constexpr int kTmemCols = KT * BN < 32 ? 32 : KT * BN;
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
-  static constexpr int kProducers = 4;                        // TMA-issuing warps (boxes dealt round robin)
+  static constexpr int kProducers = PW;                       // TMA-issuing warps (boxes dealt round robin)
   static constexpr int kThreads = 32 * (5 + kProducers);      // warp 0 MMA, warps 1-4 epilogue, then producers
 };
 
-template <int BN, int KT>
-__global__ void __launch_bounds__((WgradCfg<BN, KT>::kThreads), 1)
+template <int BN, int KT, int PW>
+__global__ void __launch_bounds__((WgradCfg<BN, KT, PW>::kThreads), 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ UmmaWgradP p, float* __restrict__ out) {
-  using Cfg = WgradCfg<BN, KT>;
+  using Cfg = WgradCfg<BN, KT, PW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
@@ -457,14 +479,27 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       const bool valid = k < p.K && iters > 0;
       float* orow = out + (size_t)blockIdx.z * p.split_stride + ((size_t)k * p.T + tap0) * p.C + c0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * BN;
-#pragma unroll 1
-      for (int c = 0; c < nblk * 32; c += 32) {
+      // two 32-column chunks per trip: the TMEM load of the next chunk is in flight while this one is stored
+      const int ncols = nblk * 32;
+      auto put = [&](const uint32_t (&r)[32], int c) {
+        if (!(valid && c0 + (c % (p.cpb * 32)) < p.C)) return;
         float v[32];
-        tmem_ld32(taddr + c, v);
-        if (valid && c0 + (c % (p.cpb * 32)) < p.C) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.vec8) epi_row_chunk<SRGAN_ACT_NONE, 32, 8>(v, orow + c, nullptr, 0.f);
+        else epi_row_chunk<SRGAN_ACT_NONE, 32, 4>(v, orow + c, nullptr, 0.f);
+      };
+      uint32_t ra[32], rb[32];
+      tmem_ld32_issue(taddr, ra);
+#pragma unroll 1
+      for (int c = 0; c < ncols; c += 64) {
+        tmem_ld_wait();
+        if (c + 32 < ncols) tmem_ld32_issue(taddr + c + 32, rb);
+        put(ra, c);
+        if (c + 32 < ncols) {
+          tmem_ld_wait();
+          if (c + 64 < ncols) tmem_ld32_issue(taddr + c + 64, ra);
+          put(rb, c + 32);
         }
       }
     }
@@ -527,7 +562,19 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
   }
   UmmaConvP q = p;
   q.gx = (grid.x + MT - 1) / MT; q.gy = grid.y; q.gz = grid.z;
-  const long items = (long)q.gx * q.gy * q.gz;
+  long items = (long)q.gx * q.gy * q.gz;
+  q.n_full = (int)items;
+  // The CTAs of the last, partial wave would each run a whole tile while the other SMs idle.  With 256-wide tiles
+  // (two filter boxes) a tile splits into two half-width items at no extra operand traffic per FLOP on the filter
+  // side: when the tail fills at most half of the SMs, run it as twice as many half-width items.
+  // Bring-up override: SRGAN_DBG_CONV_TAIL=0.
+  static const bool tail_split = !(getenv("SRGAN_DBG_CONV_TAIL") && atoi(getenv("SRGAN_DBG_CONV_TAIL")) == 0);
+  const long rem = items % kNumSMs;
+  if (BN == 256 && MT == 1 && tail_split && rem > 0 && 2 * rem <= kNumSMs) {
+    q.n_full = (int)(items - rem);
+    items += rem;
+  }
+  q.n_items = (int)items;
   const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);     // persistent: one CTA per SM
   conv_umma_kernel<BN, MT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y);
   SRGAN_RETURN_LAUNCH();
@@ -937,23 +984,37 @@ void splitk_reduce_launch(const float* part, float* out, long long n, int splits
 int colsum_launch(const float* x, float* out, long long rows, int C, float* scratch, int scratch_blocks,
                   cudaStream_t st);
 
-template <int BN, int KT>
-static int launch_wgrad_cfg(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
-                            cudaStream_t st) {
-  using Cfg = WgradCfg<BN, KT>;
+template <int BN, int KT, int PW>
+static int launch_wgrad_pw(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
+                           cudaStream_t st) {
+  using Cfg = WgradCfg<BN, KT, PW>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN, KT, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::kSmem);
     if (e != cudaSuccess) { set_error("wgrad_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
-  wgrad_umma_kernel<BN, KT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
+  wgrad_umma_kernel<BN, KT, PW><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
   SRGAN_RETURN_LAUNCH();
 }
 
-static int launch_wgrad(int BN, int KT, const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out,
-                        dim3 grid, cudaStream_t st) {
+// Producer warps: a stage of the widest tiles is 16 boxes of 4 KB; boxes issued by one warp complete one after the
+// other, so the wide tiles deal them to 8 warps.  Bring-up override: SRGAN_DBG_WGRAD_PW=4|8.
+template <int BN, int KT>
+static int launch_wgrad_cfg(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
+                            cudaStream_t st) {
+  static const char* e_pw = getenv("SRGAN_DBG_WGRAD_PW");
+  const int pw = e_pw ? atoi(e_pw) : (KT * 4 + BN / 32 >= 12 ? 8 : 4);
+  if (pw == 16) return launch_wgrad_pw<BN, KT, 16>(mdy, mx, p, out, grid, st);
+  if (pw == 8) return launch_wgrad_pw<BN, KT, 8>(mdy, mx, p, out, grid, st);
+  return launch_wgrad_pw<BN, KT, 4>(mdy, mx, p, out, grid, st);
+}
+
+static int launch_wgrad(int BN, int KT, const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p_in,
+                        float* out, dim3 grid, cudaStream_t st) {
+  UmmaWgradP p = p_in;
+  p.vec8 = (uintptr_t)out % 32 == 0 && p.C % 8 == 0 && p.split_stride % 8 == 0;
   if (KT == 2) {
     switch (BN) {
       case 256: return launch_wgrad_cfg<256, 2>(mdy, mx, p, out, grid, st);

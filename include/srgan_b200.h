@@ -115,6 +115,38 @@ int srgan_inorm_bwd(const float* dy, const float* x, const float* mean, const fl
 int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma, const float* cbias,
                             float* dgamma, float* dbeta, float* dcbias, int N, int C, void* stream);
 
+/* ---------------------------------------------------------------- batch-statistics norms
+ * ref: CBBNorm2d / _CBBNorm.forward pyfiles/model.py:75-171 and nn.BatchNorm2d(affine=True) chosen by
+ *      get_norm_layer("batch", ...) :173-177.
+ *   CBBNorm2d (cond = 1):  y = act(((x - m_nc) * r_c + cbias[n][c]) * gamma[c] + beta[c])
+ *   BatchNorm2d (cond = 0): y = act((x - mu_c) * r_c * gamma[c] + beta[c])
+ * m_nc = mean over the pixels of image n, mu_c / r_c = batch mean / rsqrt(biased batch variance + eps) in training,
+ * the running statistics otherwise (training updates them: momentum, unbiased variance).
+ * Staged so that data-parallel ranks can all-gather the [N][C] tables between stages (N_all rows, this rank owns
+ * rows [n0, n0 + N_loc)):
+ *   forward : image_stats(x) -> mean_nc, m2_nc ; batch_stats(tables) -> mean, rstd, batch_mean ; apply
+ *   backward: bwd_sums(dy, x) -> s1 = sum dv, s2 = sum dv*xh ; bwd_coeffs(tables) -> m1, m2 ;
+ *             bwd_apply: dx = rstd*gamma*(dv - m1 - xh*m2) ; parameter gradients: srgan_inorm_param_grads(s1, s2). */
+int srgan_bnorm_image_stats(const float* x, float* mean_nc, float* m2_nc, int N, int HW, int C,
+                            void* workspace, size_t workspace_bytes, void* stream);   /* srgan_inorm_workspace */
+int srgan_bnorm_batch_stats(const float* mean_nc_all, const float* m2_nc_all, int N_all, int n0, int N_loc,
+                            int HW, int C, float eps, int cond, int training, float* running_mean,
+                            float* running_var, float momentum, float* mean, float* rstd, float* batch_mean,
+                            void* stream);
+int srgan_bnorm_apply(const float* x, float* y, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, const float* cbias, const float* residual, int N, int HW, int C,
+                      int act, float slope, void* stream);
+int srgan_bnorm_bwd_sums(const float* dy, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, const float* cbias, float* s1, float* s2,
+                         int N, int HW, int C, int act, float slope, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int srgan_bnorm_bwd_coeffs(const float* s1_all, const float* s2_all, const float* mean, const float* rstd,
+                           const float* batch_mean, int N_all, int n0, int N_loc, int HW, int C, int cond,
+                           int training, float* m1, float* m2, void* stream);
+int srgan_bnorm_bwd_apply(const float* dy, const float* x, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, const float* cbias, const float* m1,
+                          const float* m2, float* dx, int N, int HW, int C, int act, float slope, void* stream);
+
 /* ---------------------------------------------------------------- conditional bias
  * ref: ConBias = nn.Sequential(nn.Linear(num_con, C), nn.Tanh()) pyfiles/model.py:16-19,57
  *   t[n][c] = tanh(sum_j con[n][j] * w[c][j] + b[c])

@@ -30,6 +30,27 @@ def _cbin(sd, pre, x, con, eps=1e-5):
     return h * sd[pre + "weight"][None, :, None, None] + sd[pre + "bias"][None, :, None, None]
 
 
+
+def cbbn(x, con, weight, bias, lin_w, lin_b, running_mean, running_var, training=True, momentum=0.1, eps=1e-5):
+    """CBBNorm2d, affine=True (ref model.py:121-148), written out instead of calling F.batch_norm:
+    out = (x - mean_c) / sqrt(var_c + eps) with batch statistics (biased variance) when training, running statistics
+    otherwise; result = (out - mean_hw(out) + tanh(Linear(con))) * weight + bias.
+    Returns (y, new_running_mean, new_running_var) -- running_var is updated with the UNBIASED variance."""
+    if training:
+        mean = x.mean(dim=(0, 2, 3))
+        var = ((x - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
+        n = x.numel() // x.shape[1]
+        new_rm = (1 - momentum) * running_mean + momentum * mean.detach()
+        new_rv = (1 - momentum) * running_var + momentum * var.detach() * n / max(n - 1, 1)
+    else:
+        mean, var, new_rm, new_rv = running_mean, running_var, running_mean, running_var
+    out = (x - mean[None, :, None, None]) * torch.rsqrt(var + eps)[None, :, None, None]
+    t = torch.tanh(F.linear(con, lin_w, lin_b))
+    y = (out - out.mean(dim=(2, 3), keepdim=True) + t[:, :, None, None]) * weight[None, :, None, None] \
+        + bias[None, :, None, None]
+    return y, new_rm, new_rv
+
+
 def generator_forward(sd, x, c, num_cls=2, res_num=6):
     """SingleGenerator.forward.  ref model.py:236-249 (layers :203-234, residual block :188-201)."""
     for i in range(num_cls + 1):

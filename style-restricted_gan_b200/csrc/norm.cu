@@ -29,6 +29,7 @@ struct NormP {
   int SL, slice;  // pixel slices per image, pixels per slice
   float eps, slope;
   int act;
+  int given;      // statistics (forward) / correction coefficients (backward) are read from the per-(n,c) arrays
 };
 
 struct NormIdx { int cg, row, c4, px0, px1; bool active; };
@@ -92,27 +93,30 @@ __global__ void __launch_bounds__(kNormThreads) inorm_stats_kernel(NormP p, cons
 
 __global__ void __launch_bounds__(kNormThreads) inorm_apply_kernel(
     NormP p, const float* __restrict__ x, const float4* __restrict__ part, float* __restrict__ y,
-    float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ gamma,
+    float* mean_out, float* rstd_out, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ cbias, const float* __restrict__ residual) {
   const NormIdx i = norm_idx(p);
   if (!i.active) return;
   const int n = blockIdx.y;
   const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
   const float4* xg = reinterpret_cast<const float4*>(x) + plane;
-  float4 s1 = f4(0.f), s2 = f4(0.f);
-  {
+  const int c = i.c4 * 4;
+  float4 mu, rs;
+  if (p.given) {
+    mu = __ldg(reinterpret_cast<const float4*>(mean_out + (size_t)n * p.C + c));
+    rs = __ldg(reinterpret_cast<const float4*>(rstd_out + (size_t)n * p.C + c));
+  } else {
+    float4 s1 = f4(0.f), s2 = f4(0.f);
     const float4* p1 = part + (size_t)n * p.SL * p.q4 + i.c4;
     const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
     for (int s = 0; s < p.SL; ++s) { acc4(s1, __ldg(p1 + (size_t)s * p.q4)); acc4(s2, __ldg(p2 + (size_t)s * p.q4)); }
-  }
-  const float4 pv = __ldg(xg);
-  const float inv = 1.f / (float)p.HW;
-  float4 mu, rs;
+    const float4 pv = __ldg(xg);
+    const float inv = 1.f / (float)p.HW;
 #define SRGAN_STAT(f) { float m = s1.f * inv; float var = fmaxf(s2.f * inv - m * m, 0.f); mu.f = pv.f + m; rs.f = rsqrtf(var + p.eps); }
-  SRGAN_STAT(x) SRGAN_STAT(y) SRGAN_STAT(z) SRGAN_STAT(w)
+    SRGAN_STAT(x) SRGAN_STAT(y) SRGAN_STAT(z) SRGAN_STAT(w)
 #undef SRGAN_STAT
-  const int c = i.c4 * 4;
-  if (blockIdx.x == 0 && i.row == 0) {
+  }
+  if (!p.given && blockIdx.x == 0 && i.row == 0) {
     reinterpret_cast<float4*>(mean_out + (size_t)n * p.C + c)[0] = mu;
     reinterpret_cast<float4*>(rstd_out + (size_t)n * p.C + c)[0] = rs;
   }
@@ -208,26 +212,30 @@ __global__ void __launch_bounds__(kNormThreads) inorm_bwd_apply_kernel(
     NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ cbias, const float4* __restrict__ part, float* __restrict__ dx,
-    float* __restrict__ s1_out, float* __restrict__ s2_out) {
+    float* s1_out, float* s2_out) {
   const NormIdx i = norm_idx(p);
   if (!i.active) return;
   const int n = blockIdx.y;
   const int c = i.c4 * 4;
-  float4 S1 = f4(0.f), S2 = f4(0.f);
-  {
+  const NormBwdConsts k = norm_bwd_consts(p, n, c, mean, rstd, gamma, beta, cbias);
+  const float4 kk = make_float4(k.rs.x * k.g.x, k.rs.y * k.g.y, k.rs.z * k.g.z, k.rs.w * k.g.w);
+  float4 m1, m2;
+  if (p.given) {                       // dx = rstd*gamma * (dv - m1 - xh * m2) with caller-provided m1, m2
+    m1 = __ldg(reinterpret_cast<const float4*>(s1_out + (size_t)n * p.C + c));
+    m2 = __ldg(reinterpret_cast<const float4*>(s2_out + (size_t)n * p.C + c));
+  } else {
+    float4 S1 = f4(0.f), S2 = f4(0.f);
     const float4* p1 = part + (size_t)n * p.SL * p.q4 + i.c4;
     const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
     for (int s = 0; s < p.SL; ++s) { acc4(S1, __ldg(p1 + (size_t)s * p.q4)); acc4(S2, __ldg(p2 + (size_t)s * p.q4)); }
+    if (blockIdx.x == 0 && i.row == 0) {
+      reinterpret_cast<float4*>(s1_out + (size_t)n * p.C + c)[0] = S1;
+      reinterpret_cast<float4*>(s2_out + (size_t)n * p.C + c)[0] = S2;
+    }
+    const float inv = 1.f / (float)p.HW;
+    m1 = make_float4(S1.x * inv, S1.y * inv, S1.z * inv, S1.w * inv);
+    m2 = make_float4(S2.x * inv, S2.y * inv, S2.z * inv, S2.w * inv);
   }
-  if (blockIdx.x == 0 && i.row == 0) {
-    reinterpret_cast<float4*>(s1_out + (size_t)n * p.C + c)[0] = S1;
-    reinterpret_cast<float4*>(s2_out + (size_t)n * p.C + c)[0] = S2;
-  }
-  const NormBwdConsts k = norm_bwd_consts(p, n, c, mean, rstd, gamma, beta, cbias);
-  const float inv = 1.f / (float)p.HW;
-  const float4 kk = make_float4(k.rs.x * k.g.x, k.rs.y * k.g.y, k.rs.z * k.g.z, k.rs.w * k.g.w);
-  const float4 m1 = make_float4(S1.x * inv, S1.y * inv, S1.z * inv, S1.w * inv);
-  const float4 m2 = make_float4(S2.x * inv, S2.y * inv, S2.z * inv, S2.w * inv);
   const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
   const float4* xg = reinterpret_cast<const float4*>(x) + plane;
   const float4* dg = reinterpret_cast<const float4*>(dy) + plane;
@@ -274,6 +282,112 @@ __global__ void inorm_param_grads_kernel(const float* __restrict__ s1, const flo
   if (lane == 0) {
     if (dgamma) dgamma[c] = dg;
     if (dbeta) dbeta[c] = db;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Batch-statistics norms: nn.BatchNorm2d (norm_type="batch") and CBBNorm2d (ref pyfiles/model.py:75-171):
+//   CBBNorm2d:   out = BN_batch(x);  y = (out - mean_hw(out) + tanh(Linear(con))) * w + b
+//              = ((x - m_nc) * r_c + cbias_nc) * w_c + b_c       (m_nc instance mean, r_c batch rstd)
+//   BatchNorm2d: y = (x - mu_c) * r_c * w_c + b_c
+// Both are the instance-norm apply kernel with per-(n,c) statistics GIVEN: (m_nc, r_c) resp. (mu_c, r_c).  The
+// small per-(image, channel) tables are produced / consumed by the kernels below, in stages, so that data-parallel
+// ranks can all-gather them between stages and evaluate the batch statistics in the single-GPU order.
+
+// slice partials -> per-(n,c) tables.  pivot != nullptr: a = instance mean, b = sum of squared deviations (partials
+// are sums about the first pixel of the plane); else a, b = plain sums of the two partial planes.
+__global__ void norm_fold_kernel(NormP p, const float4* __restrict__ part, const float* __restrict__ pivot_x,
+                                 float* __restrict__ a_out, float* __restrict__ b_out) {
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (c4 >= p.q4) return;
+  float4 s1 = f4(0.f), s2 = f4(0.f);
+  const float4* p1 = part + (size_t)n * p.SL * p.q4 + c4;
+  const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
+  for (int s = 0; s < p.SL; ++s) { acc4(s1, __ldg(p1 + (size_t)s * p.q4)); acc4(s2, __ldg(p2 + (size_t)s * p.q4)); }
+  if (pivot_x) {
+    const float4 pv = __ldg(reinterpret_cast<const float4*>(pivot_x) + (size_t)n * p.HW * p.q4 + c4);
+    const float inv = 1.f / (float)p.HW;
+#define SRGAN_CONV(f) { const float m = s1.f * inv; s2.f = fmaxf(s2.f - s1.f * m, 0.f); s1.f = pv.f + m; }
+    SRGAN_CONV(x) SRGAN_CONV(y) SRGAN_CONV(z) SRGAN_CONV(w)
+#undef SRGAN_CONV
+  }
+  reinterpret_cast<float4*>(a_out + (size_t)n * p.C)[c4] = s1;
+  reinterpret_cast<float4*>(b_out + (size_t)n * p.C)[c4] = s2;
+}
+
+// One warp per channel over the (all-gathered) tables of N_all images; rows [n0, n0 + N_loc) are this rank's.
+// training: batch mean / biased variance (Chan's combination of the per-image moments, fixed butterfly order),
+// running statistics updated with the unbiased variance; else the running statistics are used.
+__global__ void bnorm_batch_stats_kernel(const float* __restrict__ mean_nc, const float* __restrict__ m2_nc,
+                                         int N_all, int n0, int N_loc, int HW, int C, float eps, int cond,
+                                         int training, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, float momentum,
+                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                         float* __restrict__ batch_mean) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= C) return;
+  float mu, var;
+  if (training) {
+    float sm = 0.f;
+    for (int n = lane; n < N_all; n += 32) sm += mean_nc[(size_t)n * C + c];
+    mu = warp_sum(sm) / (float)N_all;
+    float sq = 0.f;
+    for (int n = lane; n < N_all; n += 32) {
+      const float d = mean_nc[(size_t)n * C + c] - mu;
+      sq += m2_nc[(size_t)n * C + c] + (float)HW * d * d;
+    }
+    const float M2 = warp_sum(sq);
+    const float cnt = (float)N_all * (float)HW;
+    var = M2 / cnt;
+    if (lane == 0 && running_mean && running_var) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (M2 / fmaxf(cnt - 1.f, 1.f));
+    }
+  } else {
+    mu = running_mean[c];
+    var = running_var[c];
+  }
+  const float rs = rsqrtf(var + eps);
+  if (lane == 0) batch_mean[c] = mu;
+  for (int n = lane; n < N_loc; n += 32) {
+    mean_out[(size_t)n * C + c] = cond ? mean_nc[(size_t)(n0 + n) * C + c] : mu;
+    rstd_out[(size_t)n * C + c] = rs;
+  }
+}
+
+// dx = rstd*gamma * (dv - m1 - xh * m2): per-(n,c) coefficients from the (all-gathered) sums s1 = sum dv,
+// s2 = sum dv*xh.   CBBNorm2d: m1 = s1_nc/HW + delta_nc * M, m2 = M, M = sum_n s2 / (N*HW),
+// delta_nc = (m_nc - mu_c) * r_c;  BatchNorm2d: m1 = sum_n s1 / (N*HW), m2 = M.  Evaluation mode (constant r_c):
+// CBBNorm2d m1 = s1_nc/HW, m2 = 0; BatchNorm2d m1 = m2 = 0.
+__global__ void bnorm_bwd_coeffs_kernel(const float* __restrict__ s1_all, const float* __restrict__ s2_all,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const float* __restrict__ batch_mean, int N_all, int n0, int N_loc, int HW,
+                                        int C, int cond, int training, float* __restrict__ m1_out,
+                                        float* __restrict__ m2_out) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= C) return;
+  float S1 = 0.f, S2 = 0.f;
+  if (training) {
+    for (int n = lane; n < N_all; n += 32) { S1 += s1_all[(size_t)n * C + c]; S2 += s2_all[(size_t)n * C + c]; }
+    S1 = warp_sum(S1);
+    S2 = warp_sum(S2);
+  }
+  const float inv_all = 1.f / ((float)N_all * (float)HW), inv = 1.f / (float)HW;
+  const float M = training ? S2 * inv_all : 0.f;
+  const float mu = batch_mean[c];
+  for (int n = lane; n < N_loc; n += 32) {
+    const size_t o = (size_t)n * C + c;
+    float m1;
+    if (cond) {
+      const float delta = (mean[o] - mu) * rstd[o];
+      m1 = s1_all[(size_t)(n0 + n) * C + c] * inv + delta * M;
+    } else {
+      m1 = training ? S1 * inv_all : 0.f;
+    }
+    m1_out[o] = m1;
+    m2_out[o] = M;
   }
 }
 
@@ -363,5 +477,101 @@ extern "C" int srgan_inorm_param_grads(const float* s1, const float* s2, const f
   if (C == 0) return SRGAN_OK;
   inorm_param_grads_kernel<<<ceil_div(C * 32, 256), 256, 0, (cudaStream_t)stream>>>(s1, s2, gamma, cbias, dgamma,
                                                                                   dbeta, dcbias, N, C);
+  SRGAN_RETURN_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------- batch-statistics norms (ABI)
+static int bn_common_checks(const char* fn, int N, int HW, int C, NormP* p) {
+  if (!(N >= 0 && HW > 0 && C > 0 && C % 8 == 0)) { set_error("%s: need C %% 8 == 0, HW > 0", fn); return SRGAN_E_BADARG; }
+  if (N > 65535) { set_error("%s: N too large for grid.y", fn); return SRGAN_E_BADARG; }
+  if (!plan_norm(N, HW, C, p)) { set_error("%s: channel count cannot be mapped", fn); return SRGAN_E_BADARG; }
+  return SRGAN_OK;
+}
+
+extern "C" int srgan_bnorm_image_stats(const float* x, float* mean_nc, float* m2_nc, int N, int HW, int C, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  SRGAN_CHECK_ARG(x && mean_nc && m2_nc, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)mean_nc | (uintptr_t)m2_nc | (uintptr_t)ws) % 16 == 0, "pointers must be 16-byte aligned");
+  NormP p;
+  if (int e = bn_common_checks(__func__, N, HW, C, &p)) return e;
+  if (N == 0) return SRGAN_OK;
+  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("bnorm_image_stats: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  inorm_stats_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (float4*)ws);
+  norm_fold_kernel<<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const float4*)ws, x, mean_nc, m2_nc);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_bnorm_batch_stats(const float* mean_nc_all, const float* m2_nc_all, int N_all, int n0, int N_loc,
+                                       int HW, int C, float eps, int cond, int training, float* running_mean,
+                                       float* running_var, float momentum, float* mean, float* rstd,
+                                       float* batch_mean, void* stream) {
+  SRGAN_CHECK_ARG(mean_nc_all && m2_nc_all && mean && rstd && batch_mean, "null pointer");
+  SRGAN_CHECK_ARG(N_all > 0 && n0 >= 0 && N_loc >= 0 && n0 + N_loc <= N_all && HW > 0 && C > 0, "bad extents");
+  SRGAN_CHECK_ARG(training || (running_mean && running_var), "evaluation mode needs running statistics");
+  bnorm_batch_stats_kernel<<<ceil_div(C * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      mean_nc_all, m2_nc_all, N_all, n0, N_loc, HW, C, eps, cond, training, running_mean, running_var, momentum, mean,
+      rstd, batch_mean);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_bnorm_apply(const float* x, float* y, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, const float* cbias, const float* residual, int N, int HW, int C,
+                                 int act, float slope, void* stream) {
+  SRGAN_CHECK_ARG(x && y && mean && rstd, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)residual) % 16 == 0, "pointers must be 16-byte aligned");
+  NormP p;
+  if (int e = bn_common_checks(__func__, N, HW, C, &p)) return e;
+  if (N == 0) return SRGAN_OK;
+  p.eps = 0.f; p.slope = slope; p.act = act; p.given = 1;
+  inorm_apply_kernel<<<norm_grid(p), kNormThreads, 0, (cudaStream_t)stream>>>(
+      p, x, nullptr, y, const_cast<float*>(mean), const_cast<float*>(rstd), gamma, beta, cbias, residual);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_bnorm_bwd_sums(const float* dy, const float* x, const float* mean, const float* rstd,
+                                    const float* gamma, const float* beta, const float* cbias, float* s1, float* s2,
+                                    int N, int HW, int C, int act, float slope, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  SRGAN_CHECK_ARG(dy && x && mean && rstd && s1 && s2, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)s1 | (uintptr_t)s2 | (uintptr_t)ws) % 16 == 0,
+                  "pointers must be 16-byte aligned");
+  NormP p;
+  if (int e = bn_common_checks(__func__, N, HW, C, &p)) return e;
+  if (N == 0) return SRGAN_OK;
+  p.eps = 0.f; p.slope = slope; p.act = act;
+  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("bnorm_bwd_sums: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  inorm_bwd_reduce_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias, (float4*)ws);
+  norm_fold_kernel<<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const float4*)ws, nullptr, s1, s2);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_bnorm_bwd_coeffs(const float* s1_all, const float* s2_all, const float* mean, const float* rstd,
+                                      const float* batch_mean, int N_all, int n0, int N_loc, int HW, int C, int cond,
+                                      int training, float* m1, float* m2, void* stream) {
+  SRGAN_CHECK_ARG(s1_all && s2_all && mean && rstd && batch_mean && m1 && m2, "null pointer");
+  SRGAN_CHECK_ARG(N_all > 0 && n0 >= 0 && N_loc >= 0 && n0 + N_loc <= N_all && HW > 0 && C > 0, "bad extents");
+  bnorm_bwd_coeffs_kernel<<<ceil_div(C * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      s1_all, s2_all, mean, rstd, batch_mean, N_all, n0, N_loc, HW, C, cond, training, m1, m2);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_bnorm_bwd_apply(const float* dy, const float* x, const float* mean, const float* rstd,
+                                     const float* gamma, const float* beta, const float* cbias, const float* m1,
+                                     const float* m2, float* dx, int N, int HW, int C, int act, float slope,
+                                     void* stream) {
+  SRGAN_CHECK_ARG(dy && x && mean && rstd && m1 && m2 && dx, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)m1 | (uintptr_t)m2 | (uintptr_t)dx) % 16 == 0,
+                  "pointers must be 16-byte aligned");
+  NormP p;
+  if (int e = bn_common_checks(__func__, N, HW, C, &p)) return e;
+  if (N == 0) return SRGAN_OK;
+  p.eps = 0.f; p.slope = slope; p.act = act; p.given = 1;
+  inorm_bwd_apply_kernel<<<norm_grid(p), kNormThreads, 0, (cudaStream_t)stream>>>(
+      p, dy, x, mean, rstd, gamma, beta, cbias, nullptr, dx, const_cast<float*>(m1), const_cast<float*>(m2));
   SRGAN_RETURN_LAUNCH();
 }

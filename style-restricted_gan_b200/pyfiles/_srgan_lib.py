@@ -38,6 +38,13 @@ SIGNATURES = {
     "srgan_inorm_workspace": (c_size_t, [c_int, c_int, c_int]),
     "srgan_inorm_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_float, P, c_size_t, P]),
     "srgan_inorm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, c_size_t, P]),
+    "srgan_bnorm_image_stats": (c_int, [P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
+    "srgan_bnorm_batch_stats": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_float,
+                                        P, P, P, P]),
+    "srgan_bnorm_apply": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "srgan_bnorm_bwd_sums": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, c_size_t, P]),
+    "srgan_bnorm_bwd_coeffs": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "srgan_bnorm_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "srgan_inorm_param_grads": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P]),
     "srgan_condbias_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "srgan_condbias_bwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P]),

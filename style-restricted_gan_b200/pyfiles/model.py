@@ -122,8 +122,9 @@ class CBINorm2d(_CBINorm):
 
 
 class _CBBNorm(nn.Module):
-    """Conditional *batch* norm variant (ref pyfiles/model.py:75-171).  Never instantiated by the
-    notebooks (they all pass norm_type="instance"); kept for API completeness."""
+    """Conditional *batch* norm variant (ref pyfiles/model.py:75-171): batch norm without affine, minus its own
+    spatial mean, plus tanh(Linear(con)), then weight / bias.  The notebooks all pass norm_type="instance"; this is
+    what norm_type="batch" selects.  Data parallel: statistics are those of the global batch."""
 
     def __init__(self, num_features, num_con, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
         super().__init__()
@@ -162,11 +163,22 @@ class _CBBNorm(nn.Module):
     def _check_input_dim(self, input):
         raise NotImplementedError
 
-    def forward(self, input, ConInfor):
+    def _factor(self):
+        """exponential_average_factor of the reference (pyfiles/model.py:124-131); bumps num_batches_tracked."""
+        if self.training and self.track_running_stats:
+            self.num_batches_tracked += 1
+            if self.momentum is None:
+                return 1.0 / float(self.num_batches_tracked.item())
+            return self.momentum
+        return 0.0
+
+    def forward(self, input, ConInfor, act=ops.ACT_NONE, slope=0.0, residual=None):
         self._check_input_dim(input)
-        raise NotImplementedError(
-            "CBBNorm2d (norm_type='batch') has no B200 kernel yet; every SingleGAN/SRGAN notebook uses "
-            "norm_type='instance'")
+        factor = self._factor()
+        lin = self.ConBias[0]
+        t = ops.cond_bias(ConInfor, lin.weight, lin.bias)
+        return ops.batch_norm_act(input, self.weight, self.bias, t, residual, self.running_mean, self.running_var,
+                                  self.training or not self.track_running_stats, factor, self.eps, True, act, slope)
 
     def extra_repr(self):
         return "{num_features}, eps={eps}, momentum={momentum}, affine={affine}, " \
@@ -179,9 +191,24 @@ class CBBNorm2d(_CBBNorm):
             raise ValueError("expected 4D input (got {}D input)".format(input.dim()))
 
 
+class _KernelBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d(affine=True) for norm_type="batch" (ref get_norm_layer pyfiles/model.py:175): same parameters,
+    buffers and state_dict keys; forward through the fused kernels (optional activation)."""
+
+    def forward(self, x, act=ops.ACT_NONE, slope=0.0):
+        self._check_input_dim(x)
+        factor = 0.0
+        if self.training and self.track_running_stats:
+            self.num_batches_tracked += 1
+            factor = 1.0 / float(self.num_batches_tracked.item()) if self.momentum is None else self.momentum
+        training = self.training or not self.track_running_stats
+        return ops.batch_norm_act(x, self.weight, self.bias, None, None, self.running_mean, self.running_var, training,
+                                  factor, self.eps, False, act, slope)
+
+
 def get_norm_layer(layer_type="instance", num_con=2):
     if layer_type == "batch":
-        norm_layer = functools.partial(nn.BatchNorm2d, affine=True)
+        norm_layer = functools.partial(_KernelBatchNorm2d, affine=True)
         c_norm_layer = functools.partial(CBBNorm2d, affine=True, num_con=num_con)
     elif layer_type == "instance":
         norm_layer = functools.partial(_KernelInstanceNorm2d, affine=False)

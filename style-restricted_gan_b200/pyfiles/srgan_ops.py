@@ -464,6 +464,116 @@ def instance_norm_act(x, gamma=None, beta=None, cbias=None, residual=None, eps=1
     return _InstanceNormFn.apply(x, gamma, beta, cbias, residual, float(eps), int(act), float(slope))
 
 
+def _gather_rows(t):
+    """[N_loc, C] table -> (all-gathered [N_all, C] table, first local row).  Ranks hold equal batch slices."""
+    rank, world = dp_rank_world()
+    if world == 1:
+        return t, 0
+    import torch.distributed as dist
+    out = torch.empty((t.shape[0] * world, t.shape[1]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out, rank * t.shape[0]
+
+
+class _BatchNormFn(torch.autograd.Function):
+    """Batch-statistics norms.  cond=True: CBBNorm2d, y = act(((x - mean_hw(x)) * r_c + cbias) * gamma + beta)
+    (ref _CBBNorm.forward pyfiles/model.py:121-148: BN without affine, minus its own spatial mean, plus the
+    conditional bias, then weight/bias); cond=False: nn.BatchNorm2d(affine=True) (ref get_norm_layer :175).
+    Data parallel: the [N, C] tables are all-gathered, so statistics and gradients equal the global-batch ones."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, cbias, residual, running_mean, running_var, training, momentum, eps, cond, act,
+                slope, sync):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        if residual is not None:
+            residual = _raw_to_nhwc(residual)
+        if cbias is not None:
+            cbias = cbias.contiguous()
+        dev = x.device
+        y = torch.empty_like(x)
+        mean = torch.empty((N, C), dtype=torch.float32, device=dev)
+        rstd = torch.empty((N, C), dtype=torch.float32, device=dev)
+        bmean = torch.empty((C,), dtype=torch.float32, device=dev)
+        if x.numel():
+            mnc = torch.empty((N, C), dtype=torch.float32, device=dev)
+            m2 = torch.empty((N, C), dtype=torch.float32, device=dev)
+            nb = _lib().srgan_inorm_workspace(N, H * W, C)
+            ws = _workspace(dev, nb)
+            _call("srgan_bnorm_image_stats", _p(x), _p(mnc), _p(m2), N, H * W, C, _p(ws), nb, _stream())
+            if sync and training:
+                both, n0 = _gather_rows(torch.cat([mnc, m2], 1))
+                mnc_all, m2_all = both[:, :C].contiguous(), both[:, C:].contiguous()
+            else:
+                mnc_all, m2_all, n0 = mnc, m2, 0
+            _call("srgan_bnorm_batch_stats", _p(mnc_all), _p(m2_all), mnc_all.shape[0], n0, N, H * W, C, eps,
+                  int(cond), int(training), _p(running_mean), _p(running_var), momentum, _p(mean), _p(rstd),
+                  _p(bmean), _stream())
+            _call("srgan_bnorm_apply", _p(x), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(residual),
+                  N, H * W, C, act, slope, _stream())
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.act, ctx.slope, ctx.cond, ctx.training, ctx.sync = act, slope, cond, training, sync
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, mean, rstd, bmean, cbias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, bmean, cbias = ctx.saved_tensors
+        gamma, beta = ctx.gamma, ctx.beta
+        N, C, H, W = x.shape
+        dev = x.device
+        dy = _raw_to_nhwc(dy)
+        dx = torch.empty_like(x)
+        s1 = torch.empty((N, C), dtype=torch.float32, device=dev)
+        s2 = torch.empty((N, C), dtype=torch.float32, device=dev)
+        if x.numel():
+            nb = _lib().srgan_inorm_workspace(N, H * W, C)
+            ws = _workspace(dev, nb)
+            _call("srgan_bnorm_bwd_sums", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(s1),
+                  _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
+            if ctx.sync and ctx.training:
+                both, n0 = _gather_rows(torch.cat([s1, s2], 1))
+                s1_all, s2_all = both[:, :C].contiguous(), both[:, C:].contiguous()
+            else:
+                s1_all, s2_all, n0 = s1, s2, 0
+            m1 = torch.empty((N, C), dtype=torch.float32, device=dev)
+            m2 = torch.empty((N, C), dtype=torch.float32, device=dev)
+            _call("srgan_bnorm_bwd_coeffs", _p(s1_all), _p(s2_all), _p(mean), _p(rstd), _p(bmean), s1_all.shape[0], n0,
+                  N, H * W, C, int(ctx.cond), int(ctx.training), _p(m1), _p(m2), _stream())
+            _call("srgan_bnorm_bwd_apply", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(m1),
+                  _p(m2), _p(dx), N, H * W, C, ctx.act, ctx.slope, _stream())
+        dgamma = dbeta = dcb = None
+        need_g = gamma is not None and ctx.needs_input_grad[1]
+        need_b = beta is not None and ctx.needs_input_grad[2]
+        need_c = cbias is not None and ctx.needs_input_grad[3]
+        if need_g or need_b or need_c:
+            dgamma = torch.empty_like(gamma) if need_g else None
+            dbeta = torch.empty_like(beta) if need_b else None
+            dcb = torch.empty_like(cbias) if need_c else None
+            _call("srgan_inorm_param_grads", _p(s1), _p(s2), _p(gamma), _p(cbias), _p(dgamma), _p(dbeta), _p(dcb),
+                  N, C, _stream())
+        dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
+        return ((dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, dcb, dres) + (None,) * 9
+
+
+def batch_norm_act(x, gamma=None, beta=None, cbias=None, residual=None, running_mean=None, running_var=None,
+                   training=True, momentum=0.1, eps=1e-5, cond=False, act=ACT_NONE, slope=0.0, sync=True):
+    """BatchNorm2d (cond=False) / CBBNorm2d (cond=True, cbias = tanh(Linear(con))) with fused activation.
+    Updates running_mean / running_var in place when training."""
+    _req(x, gamma, beta, cbias, residual, running_mean, running_var)
+    if x.dim() != 4:
+        raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
+    if x.shape[1] % 8:
+        raise SrganKernelError("batch_norm_act: channel count must be a multiple of 8 (got %d)" % x.shape[1])
+    if residual is not None and act != ACT_NONE:
+        raise ValueError("residual add is only fused with act=none")
+    if not training and (running_mean is None or running_var is None):
+        raise ValueError("evaluation mode needs running statistics")
+    return _BatchNormFn.apply(x, gamma, beta, cbias, residual, running_mean, running_var, bool(training),
+                              float(momentum), float(eps), bool(cond), int(act), float(slope), bool(sync))
+
+
 # ----------------------------------------------------------------------------- pooling
 def _pool_fn(fwd_name, bwd_name, out_hw):
     class _Pool(torch.autograd.Function):

@@ -138,3 +138,24 @@ def test_oracle_full_width_losses():
         ref = g["G0.grad." + pname]
         d = so.digest(tr.record["G0.grad"][pname]).numpy()
         assert abs(d[0] - ref[0]) <= 2e-3 * abs(ref[0]), pname
+
+
+def test_oracle_cbbnorm_matches_reference_golden():
+    """oracle.cbbn (restated _CBBNorm.forward, ref pyfiles/model.py:121-148) against outputs, gradients and running
+    statistics recorded from the unmodified reference (oracle/make_golden_norms.py): two training calls, one eval."""
+    g = np.load(os.path.join(cases.GOLDEN, "cbbnorm.npz"))
+    w, b = torch.tensor(g["weight"], requires_grad=True), torch.tensor(g["bias"], requires_grad=True)
+    lw, lb = torch.tensor(g["lin_w"], requires_grad=True), torch.tensor(g["lin_b"], requires_grad=True)
+    rm, rv = torch.zeros(w.shape[0]), torch.ones(w.shape[0])
+    for call in range(3):
+        pre = "call%d." % call
+        x = torch.tensor(g[pre + "x"], requires_grad=True)
+        con = torch.tensor(g[pre + "con"], requires_grad=True)
+        y, rm, rv = so.cbbn(x, con, w, b, lw, lb, rm, rv, training=bool(g[pre + "training"]))
+        grads = torch.autograd.grad((y * torch.tensor(g[pre + "probe"])).sum(), [x, con, w, b, lw, lb])
+        np.testing.assert_allclose(y.detach().numpy(), g[pre + "y"], rtol=2e-5, atol=2e-5)
+        for got, key in zip(grads, ("dx", "dcon", "dweight", "dbias", "dlin_w", "dlin_b")):
+            ref = g[pre + key]
+            assert np.abs(got.numpy() - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), key
+        np.testing.assert_allclose(rm.numpy(), g[pre + "running_mean"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rv.numpy(), g[pre + "running_var"], rtol=1e-5, atol=1e-6)

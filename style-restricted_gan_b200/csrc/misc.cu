@@ -15,6 +15,18 @@ static inline unsigned grid_for(size_t work, int threads) {
 #define GRID_STRIDE(i, n) \
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
 
+// element type of the streaming kernels below: float, or float4 when channels and pointers allow 16-byte accesses
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float4 vadd(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float vscale(float a, float s) { return a * s; }
+__device__ __forceinline__ float4 vscale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+template <typename T> __device__ __forceinline__ T vzero();
+template <> __device__ __forceinline__ float vzero<float>() { return 0.f; }
+template <> __device__ __forceinline__ float4 vzero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+static inline bool vec4_ok(int C, const void* a, const void* b, const void* c = nullptr) {
+  return C % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 16) == 0;
+}
+
 // ------------------------------------------------------------------ NCHW <-> NHWC (smem transpose)
 // One block transposes a [C x 32 pixels] panel; coalesced on both sides.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
@@ -56,32 +68,34 @@ __device__ __forceinline__ int reflect(int i, int n) {
   if (i >= n) i = 2 * (n - 1) - i;
   return i;
 }
-// y[N][H+2p][W+2p][C]
-__global__ void reflect_pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W,
-                                       int C, int pad) {
+// y[N][H+2p][W+2p][C]   (C counts elements of T)
+template <typename T>
+__global__ void reflect_pad_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C,
+                                       int pad) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const size_t total = (size_t)N * Hp * Wp * C;
   GRID_STRIDE(i, total) {
-    int c = (int)(i % C);
-    size_t t = i / C;
-    int w = (int)(t % Wp); t /= Wp;
-    int h = (int)(t % Hp);
-    int n = (int)(t / Hp);
+    int c = (int)(i % (unsigned)C);
+    size_t t = i / (unsigned)C;
+    int w = (int)(t % (unsigned)Wp); t /= (unsigned)Wp;
+    int h = (int)(t % (unsigned)Hp);
+    int n = (int)(t / (unsigned)Hp);
     int sh = reflect(h - pad, H), sw = reflect(w - pad, W);
     y[i] = __ldg(x + (((size_t)n * H + sh) * W + sw) * C + c);
   }
 }
 // dx[n][h][w][c] = sum over padded positions that mirror onto (h,w); gather form, fixed order
-__global__ void reflect_pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
-                                       int C, int pad) {
+template <typename T>
+__global__ void reflect_pad_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C,
+                                       int pad) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const size_t total = (size_t)N * H * W * C;
   GRID_STRIDE(i, total) {
-    int c = (int)(i % C);
-    size_t t = i / C;
-    int w = (int)(t % W); t /= W;
-    int h = (int)(t % H);
-    int n = (int)(t / H);
+    int c = (int)(i % (unsigned)C);
+    size_t t = i / (unsigned)C;
+    int w = (int)(t % (unsigned)W); t /= (unsigned)W;
+    int h = (int)(t % (unsigned)H);
+    int n = (int)(t / (unsigned)H);
     // candidate padded rows: h+pad (interior), pad-h (top mirror, 1<=h<=pad), 2(H-1)-h+pad (bottom mirror)
     int hs[3], ws[3], nh = 0, nw = 0;
     hs[nh++] = h + pad;
@@ -90,43 +104,44 @@ __global__ void reflect_pad_bwd_kernel(const float* __restrict__ dy, float* __re
     ws[nw++] = w + pad;
     if (w >= 1 && w <= pad) ws[nw++] = pad - w;
     if (w <= W - 2 && w >= W - 1 - pad) ws[nw++] = 2 * (W - 1) - w + pad;
-    float s = 0.f;
+    T s = vzero<T>();
     for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) s += __ldg(dy + (((size_t)n * Hp + hs[a]) * Wp + ws[b]) * C + c);
+      for (int b = 0; b < nw; ++b) s = vadd(s, __ldg(dy + (((size_t)n * Hp + hs[a]) * Wp + ws[b]) * C + c));
     dx[i] = s;
   }
 }
 
 // ------------------------------------------------------------------ pooling
-// AvgPool2d(2,2): floor output size, trailing row/col dropped.
-__global__ void avgpool2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ addend,
-                                    float* __restrict__ y, int N, int H, int W, int C) {
+// AvgPool2d(2,2): floor output size, trailing row/col dropped.   (C counts elements of T)
+template <typename T>
+__global__ void avgpool2_fwd_kernel(const T* __restrict__ x, const T* __restrict__ addend, T* __restrict__ y, int N,
+                                    int H, int W, int C) {
   const int P = H / 2, Q = W / 2;
   const size_t total = (size_t)N * P * Q * C;
   GRID_STRIDE(i, total) {
-    int c = (int)(i % C);
-    size_t t = i / C;
-    int q = (int)(t % Q); t /= Q;
-    int p = (int)(t % P);
-    int n = (int)(t / P);
-    const float* b = x + (((size_t)n * H + 2 * p) * W + 2 * q) * C + c;
-    float v = 0.25f * ((__ldg(b) + __ldg(b + C)) + (__ldg(b + (size_t)W * C) + __ldg(b + (size_t)W * C + C)));
-    if (addend) v += __ldg(addend + i);
+    int c = (int)(i % (unsigned)C);
+    size_t t = i / (unsigned)C;
+    int q = (int)(t % (unsigned)Q); t /= (unsigned)Q;
+    int p = (int)(t % (unsigned)P);
+    int n = (int)(t / (unsigned)P);
+    const T* b = x + (((size_t)n * H + 2 * p) * W + 2 * q) * C + c;
+    T v = vscale(vadd(vadd(__ldg(b), __ldg(b + C)), vadd(__ldg(b + (size_t)W * C), __ldg(b + (size_t)W * C + C))), 0.25f);
+    if (addend) v = vadd(v, __ldg(addend + i));
     y[i] = v;
   }
 }
-__global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W,
-                                    int C) {
+template <typename T>
+__global__ void avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C) {
   const int P = H / 2, Q = W / 2;
   const size_t total = (size_t)N * H * W * C;
   GRID_STRIDE(i, total) {
-    int c = (int)(i % C);
-    size_t t = i / C;
-    int w = (int)(t % W); t /= W;
-    int h = (int)(t % H);
-    int n = (int)(t / H);
+    int c = (int)(i % (unsigned)C);
+    size_t t = i / (unsigned)C;
+    int w = (int)(t % (unsigned)W); t /= (unsigned)W;
+    int h = (int)(t % (unsigned)H);
+    int n = (int)(t / (unsigned)H);
     int p = h >> 1, q = w >> 1;
-    dx[i] = (p < P && q < Q) ? 0.25f * __ldg(dy + (((size_t)n * P + p) * Q + q) * C + c) : 0.f;
+    dx[i] = (p < P && q < Q) ? vscale(__ldg(dy + (((size_t)n * P + p) * Q + q) * C + c), 0.25f) : vzero<T>();
   }
 }
 // AvgPool2d(3, stride 2, padding 1, count_include_pad=False)
@@ -351,21 +366,30 @@ extern "C" int srgan_reflect_pad_fwd(const float* x, float* y, int N, int H, int
   SRGAN_CHECK_ARG(x && y && pad >= 0 && pad < H && pad < W, "reflect pad needs pad < H,W");
   size_t total = (size_t)N * (H + 2 * pad) * (W + 2 * pad) * C;
   if (total == 0) return SRGAN_OK;
-  reflect_pad_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, y, N, H, W, C, pad);
+  if (vec4_ok(C, x, y))
+    reflect_pad_fwd_kernel<float4><<<grid_for(total / 4, 256), 256, 0, ST>>>((const float4*)x, (float4*)y, N, H, W, C / 4, pad);
+  else
+    reflect_pad_fwd_kernel<float><<<grid_for(total, 256), 256, 0, ST>>>(x, y, N, H, W, C, pad);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_reflect_pad_bwd(const float* dy, float* dx, int N, int H, int W, int C, int pad, void* stream) {
   SRGAN_CHECK_ARG(dy && dx && pad >= 0 && pad < H && pad < W, "reflect pad needs pad < H,W");
   size_t total = (size_t)N * H * W * C;
   if (total == 0) return SRGAN_OK;
-  reflect_pad_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C, pad);
+  if (vec4_ok(C, dy, dx))
+    reflect_pad_bwd_kernel<float4><<<grid_for(total / 4, 256), 256, 0, ST>>>((const float4*)dy, (float4*)dx, N, H, W, C / 4, pad);
+  else
+    reflect_pad_bwd_kernel<float><<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C, pad);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   SRGAN_CHECK_ARG(x && y, "null pointer");
   size_t total = (size_t)N * (H / 2) * (W / 2) * C;
   if (total == 0) return SRGAN_OK;
-  avgpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, nullptr, y, N, H, W, C);
+  if (vec4_ok(C, x, y))
+    avgpool2_fwd_kernel<float4><<<grid_for(total / 4, 256), 256, 0, ST>>>((const float4*)x, nullptr, (float4*)y, N, H, W, C / 4);
+  else
+    avgpool2_fwd_kernel<float><<<grid_for(total, 256), 256, 0, ST>>>(x, nullptr, y, N, H, W, C);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_avgpool2_add_fwd(const float* a, const float* b, float* y, int N, int H, int W, int C,
@@ -373,14 +397,20 @@ extern "C" int srgan_avgpool2_add_fwd(const float* a, const float* b, float* y, 
   SRGAN_CHECK_ARG(a && b && y, "null pointer");
   size_t total = (size_t)N * (H / 2) * (W / 2) * C;
   if (total == 0) return SRGAN_OK;
-  avgpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(a, b, y, N, H, W, C);
+  if (vec4_ok(C, a, b, y))
+    avgpool2_fwd_kernel<float4><<<grid_for(total / 4, 256), 256, 0, ST>>>((const float4*)a, (const float4*)b, (float4*)y, N, H, W, C / 4);
+  else
+    avgpool2_fwd_kernel<float><<<grid_for(total, 256), 256, 0, ST>>>(a, b, y, N, H, W, C);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_avgpool2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
   SRGAN_CHECK_ARG(dy && dx, "null pointer");
   size_t total = (size_t)N * H * W * C;
   if (total == 0) return SRGAN_OK;
-  avgpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C);
+  if (vec4_ok(C, dy, dx))
+    avgpool2_bwd_kernel<float4><<<grid_for(total / 4, 256), 256, 0, ST>>>((const float4*)dy, (float4*)dx, N, H, W, C / 4);
+  else
+    avgpool2_bwd_kernel<float><<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_avgpool3s2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {

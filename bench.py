@@ -155,6 +155,28 @@ def time_dominant_kernel(batch, dev):
     return ms, flops, ("tcgen05_tf32" if engine == 2 else "ffma_fp32")
 
 
+def time_norm_kernel(batch, dev):
+    """CUDA-event time of the fused instance-norm forward on [batch, 256, 32, 32], L2 flushed between launches."""
+    import srgan_ops as ops
+    x = torch.randn(batch, 256, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
+    g, b = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    cb = torch.randn(batch, 256, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        ops.instance_norm_act(x, g, b, cb, None, 1e-5, ops.ACT_RELU, 0.0)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.instance_norm_act(x, g, b, cb, None, 1e-5, ops.ACT_RELU, 0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts))
+
+
 def measure_tf32_peak(dev):
     a = torch.randn(8192, 8192, device=dev)
     b = torch.randn(8192, 8192, device=dev)
@@ -237,6 +259,14 @@ def run_ours(args):
             ms = float(t)
         return ms, ops.abi_calls - calls0, clocks
 
+    # one eager step first: counts the kernels of a step (a replayed CUDA graph launches them without passing
+    # through the Python-side counter) and sizes every lazily grown buffer
+    calls0 = ops.abi_calls
+    sg.train(x_dev, label_dev)
+    launches_per_step = ops.abi_calls - calls0
+    if args.graph == "on":
+        sg.enable_cuda_graph(warmup=1)
+
     def step_resident():
         sg.train(x_dev, label_dev)
 
@@ -249,6 +279,7 @@ def run_ours(args):
         sink.copy_(torch.stack([e.detach().float() for e in errs]), non_blocking=False)   # device -> host read
 
     ms, launches, clocks = timed(step_resident, args.steps, args.warmup, True)
+    launches = launches_per_step * args.steps
     value = batch * world * args.steps / (ms * 1e-3)
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1, False)
     e2e = batch * world * args.steps / (ms_e2e * 1e-3)
@@ -260,12 +291,28 @@ def run_ours(args):
         tf32_peak = measure_tf32_peak(dev)
         achieved = kflops / (kms * 1e-3) / 1e12
         peak = tf32_peak if kname == "tcgen05_tf32" else tf32_peak
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+            # (batch 64); scaled to the batch of this run
+            t = json.load(open(tpath))
+            traffic = t["res_conv_fprop_dram_bytes_b64"] * batch / 64.0
         roof = {"bound": "tensor", "kernel": "conv2d fprop 3x3 256->256 @32x32 (residual block), " + kname,
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "cuBLAS TF32 8192^3 matmul measured in this run (MEASURED_PEAKS.json has no TF32 "
                                "entry; bf16 there: %.1f TF/s, %s)" % (pk["bf16"], pk["src"]),
                 "kernel_ms": kms, "step_gflop_per_image": GF_PER_IMG[args.workload],
                 "step_tflops": value * GF_PER_IMG[args.workload] / 1e3}
+        # secondary roofline: the fused instance-norm (+ conditional bias + affine + ReLU) forward of the residual
+        # blocks, HBM bound; algorithmic bytes = read x + write y
+        nms = time_norm_kernel(batch, dev)
+        nbytes = 2.0 * 4 * batch * 256 * 1024
+        glue = {"bound": "hbm", "kernel": "instance norm + cond. bias + affine + ReLU forward, 256 ch @32x32",
+                "achieved": nbytes / (nms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": nbytes / (nms * 1e-3) / 1e9 / pk["hbm"], "kernel_ms": nms,
+                "note": "two kernels (statistics, apply) = 3 passes over the plane for 2 algorithmic ones; a plain "
+                        "device copy of the same plane reaches ~4.7 TB/s (tools/stream_probe.cu)"}
         cpu = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
@@ -281,10 +328,12 @@ def run_ours(args):
                 "config": {"workload": WORKLOADS[args.workload]["desc"], "per_gpu_batch": batch,
                            "global_batch": batch * world, "image": "3x128x128", "domains": 4,
                            "parallelism": "dp%d" % world, "conv_engine": ops.get_conv_engine(),
+                           "cuda_graph": args.graph == "on",
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_glue": glue,
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -303,6 +352,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--engine", default=None, choices=[None, "auto", "fp32", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="replay the step as one CUDA graph (sg.enable_cuda_graph) or issue every kernel from Python")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

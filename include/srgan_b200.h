@@ -246,6 +246,9 @@ int srgan_softhist_bwd(const float* x, const float* dh, int n, int bins, float h
  * One launch updates a whole flat parameter buffer.                                  */
 int srgan_adam_step(float* p, const float* g, float* m, float* v, size_t n,
                     float lr, float beta1, float beta2, float eps, int step, void* stream);
+/* Same update, step-dependent scalars in DEVICE memory: hyper = [lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t)]
+ * (the caller uploads them before each step), so the launch can be part of a replayed CUDA graph. */
+int srgan_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* hyper, void* stream);
 
 #ifdef __cplusplus
 }

@@ -397,6 +397,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Same update with the step-dependent scalars read from device memory ([lr, beta1, beta2, eps, 1 - beta1^t,
+// sqrt(1 - beta2^t)]): the launch can then live in a CUDA graph that is replayed every step.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, size_t n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2_sqrt = hyper[5];
+  const float step_size = lr / bc1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    const float wgt = 1.f - b1;
+    float mi = wgt < 0.5f ? m[i] + wgt * (gi - m[i]) : gi - (gi - m[i]) * (1.f - wgt);
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float den = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / den);
+  }
+}
+
 }  // namespace srgan
 
 using namespace srgan;
@@ -515,5 +532,13 @@ extern "C" int srgan_adam_step(float* p, const float* g, float* m, float* v, siz
   float bc1 = 1.f - (float)pow((double)beta1, step);
   float bc2 = (float)sqrt(1.0 - pow((double)beta2, step));
   adam_kernel<<<ew_grid(n), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* hyper,
+                                   void* stream) {
+  SRGAN_CHECK_ARG(p && g && m && v && hyper, "bad argument");
+  if (n == 0) return SRGAN_OK;
+  adam_dev_kernel<<<ew_grid(n), 256, 0, ST>>>(p, g, m, v, n, hyper);
   SRGAN_RETURN_LAUNCH();
 }

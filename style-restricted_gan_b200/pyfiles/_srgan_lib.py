@@ -77,6 +77,7 @@ SIGNATURES = {
     "srgan_softhist_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, P, P]),
     "srgan_softhist_bwd": (c_int, [P, P, c_int, c_int, c_float, c_float, c_float, P, P]),
     "srgan_adam_step": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_int, P]),
+    "srgan_adam_step_dev": (c_int, [P, P, P, P, c_size_t, P, P]),
 }
 
 _lib = None

@@ -12,8 +12,10 @@ torch-1.4 semantics the reference was trained with: `optG.step()` between the tw
 passes of `update_GandE` (ref: pyfiles/util_notebook.py:666 then :689) mutates the weights in
 place, and the second backward uses the updated weights with the activations saved earlier.
 """
+import math
 import os
 
+import numpy as np
 import torch
 
 import _srgan_lib as L
@@ -43,7 +45,9 @@ def _lib():
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current CUDA stream.  torch.cuda.current_stream() builds a Stream object through several
+    Python layers (15 us per call, 28 ms per training step); the two C calls below cost under a microsecond."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _req(*ts):
@@ -96,15 +100,111 @@ def dp_rank_world():
     return 0, 1
 
 
+class FeedTape(object):
+    """Host-produced inputs of a training step that is captured into a CUDA graph.  While `recording`, every host
+    feed (noise draw, Adam scalars) registers a pinned staging buffer, a static device buffer and a `fill` callable
+    instead of copying; `upload()` re-runs the fills IN PROGRAM ORDER (so the CPU generator is consumed exactly as
+    in the eager step) and enqueues the host-to-device copies ahead of the graph launch."""
+
+    def __init__(self, device="cuda", staging_floats=1 << 21):
+        self.entries = []
+        self.recording = False
+        self._done = None
+        # Both arenas are allocated BEFORE the capture starts.  Pinned staging: cudaHostAlloc is not a capturable
+        # call.  Device side: the feeds are uploaded ahead of the graph launch, so their memory must not come from
+        # the graph's private pool, where an earlier temporary of the captured step may share the address and
+        # overwrite the feed before its consumer runs.
+        self._arena = torch.empty(staging_floats, dtype=torch.float32).pin_memory()
+        self._dev_arena = torch.empty(staging_floats, dtype=torch.float32, device=device)
+        self._used = self._dev_used = 0
+
+    def device_buffer(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_pad = -(-n // 64) * 64              # 256-byte aligned slices
+        if self._dev_used + n_pad > self._dev_arena.numel():
+            raise SrganKernelError("FeedTape: device arena exhausted")
+        buf = self._dev_arena[self._dev_used:self._dev_used + n].view(*shape)
+        self._dev_used += n_pad
+        return buf
+
+    def staging(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_pad = -(-n // 16) * 16
+        if self._used + n_pad > self._arena.numel():
+            raise SrganKernelError("FeedTape: staging arena exhausted")
+        buf = self._arena[self._used:self._used + n].view(*shape)
+        self._used += n_pad
+        return buf
+
+    def add(self, pinned, dev, fill, src=None):
+        self.entries.append((pinned, dev, fill, pinned if src is None else src))
+        return dev
+
+    def upload(self):
+        if self._done is not None:
+            self._done.synchronize()          # the previous upload has left the staging buffers
+        for pinned, dev, fill, src in self.entries:
+            fill(pinned)
+            dev.copy_(src, non_blocking=True)
+        self._done = torch.cuda.Event()
+        self._done.record()
+
+
+_tape = None
+
+
+class recording(object):
+    """with recording(tape): host feeds are registered on `tape` (used while capturing a CUDA graph)."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def __enter__(self):
+        global _tape
+        self.tape.recording = True
+        _tape = self.tape
+        return self.tape
+
+    def __exit__(self, *exc):
+        global _tape
+        self.tape.recording = False
+        _tape = None
+
+
 def host_normal(rows, dim, device):
     """Standard-normal [rows, dim] from the CPU default generator, moved to `device` (the reference draws all
     of its noise this way: pyfiles/util_notebook.py:179,554, pyfiles/model.py:400,461).
     Data parallel: every rank draws the noise of the GLOBAL batch (same seed => same stream) and keeps its
     own rows, so an N-GPU run consumes the RNG exactly like the single-GPU global-batch run."""
     rank, world = dp_rank_world()
-    if world == 1:
-        return torch.randn(rows, dim).to(device)
-    return torch.randn(rows * world, dim)[rank * rows:(rank + 1) * rows].to(device)
+    pin = torch.device(device).type == "cuda"
+    if _tape is not None and _tape.recording:
+        pinned = _tape.staging(rows * world, dim)
+        dev = _tape.device_buffer(rows, dim)
+        return _tape.add(pinned, dev, lambda buf: torch.randn(buf.shape, out=buf),
+                         pinned[rank * rows:(rank + 1) * rows])
+    # pinned staging + non-blocking copy: a pageable .to(device) synchronises the stream, i.e. drains the device
+    # pipeline at every noise draw (24 times per training step)
+    z = torch.randn(rows * world, dim, pin_memory=pin)
+    if world > 1:
+        z = z[rank * rows:(rank + 1) * rows]
+    return z.to(device, non_blocking=pin)
+
+
+def to_device_async(t, device, dtype=None):
+    """Host tensor / array -> device without synchronising the stream (pinned staging, non-blocking copy).  Tensors
+    already on the device are only cast."""
+    t = torch.as_tensor(t)
+    dev = torch.device(device)
+    if t.device.type == "cpu" and dev.type == "cuda":
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.pin_memory().to(dev, non_blocking=True)
+    return t.to(device=dev, dtype=dtype) if dtype is not None else t.to(dev)
 
 
 # ----------------------------------------------------------------------------- layout
@@ -1038,6 +1138,21 @@ class FusedAdam(torch.optim.Optimizer):
                 elif p.grad.data_ptr() != gv.data_ptr():
                     gv.copy_(p.grad)
                     p.grad = gv
+            if _tape is not None and _tape.recording:
+                # captured into a CUDA graph: the step-dependent scalars come from device memory, refreshed (and the
+                # step counter advanced) by FeedTape.upload() before every replay
+                def fill(buf, st=st, group=group):
+                    st["step"] += 1
+                    b1, b2 = group["betas"]
+                    # same roundings as srgan_adam_step: float betas widened to double for pow, results cast back
+                    b1d, b2d = float(np.float32(b1)), float(np.float32(b2))
+                    buf[0], buf[1], buf[2], buf[3] = group["lr"], b1, b2, group["eps"]
+                    buf[4] = float(np.float32(1.0) - np.float32(b1d ** st["step"]))
+                    buf[5] = float(np.float32(math.sqrt(1.0 - b2d ** st["step"])))
+                hyper = _tape.add(_tape.staging(8), _tape.device_buffer(8), fill)
+                _call("srgan_adam_step_dev", _p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
+                      _p(hyper), _stream())
+                continue
             st["step"] += 1
             b1, b2 = group["betas"]
             _call("srgan_adam_step", _p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),

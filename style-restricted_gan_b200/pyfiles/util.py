@@ -124,7 +124,7 @@ def class_encode(label, device, ref_class):
     if table is None:
         table = torch.tensor(ref_class, dtype=torch.float32).to(dev)
         _ref_tables[key] = table
-    idx = torch.as_tensor(label).to(device=dev, dtype=torch.long)
+    idx = ops.to_device_async(label, dev, torch.long)
     return table[idx].view(-1, ref_class.shape[1])
 
 

@@ -272,9 +272,72 @@ class _UnrolledTrainer(object):
         return [errG + errG_ex, errE_output]
 
     def train(self, source_image, label):
+        if getattr(self, "_graph", None) is not None and torch.is_tensor(source_image) and source_image.is_cuda:
+            return self._train_graphed(source_image, label)
         self.source_image = ops.to_nhwc(source_image)
         self.label = label
         return self.UnrolledUpdate()
+
+    # ---- CUDA-graph replay of the whole step ----------------------------------------------
+    def enable_cuda_graph(self, warmup=2):
+        """After `warmup` eager calls, `train()` captures the complete step (k discriminator updates, both
+        generator/encoder phases, optimizer steps, gradient all-reduces) into ONE CUDA graph and replays it:
+        a step then costs one graph launch plus the upload of its host-drawn noise instead of ~4000 kernel
+        launches issued from Python.  The eager and the replayed step run the same kernels in the same order on
+        the same noise (the CPU generator is consumed identically), so their results are bit-identical.
+        Re-captured when the batch shape changes.  Not available with per-class discriminators (data-dependent
+        sub-batch sizes)."""
+        if isinstance(self._nD, (list, tuple)):
+            raise NotImplementedError("CUDA-graph replay needs static shapes: not with one discriminator per class")
+        self._graph = dict(warmup=int(warmup), calls=0, state=None)
+        return self
+
+    def disable_cuda_graph(self):
+        self._graph = None
+
+    def _train_graphed(self, source_image, label):
+        cfg = self._graph
+        dev = source_image.device
+        if cfg.get("stream") is None:
+            cfg["stream"] = torch.cuda.Stream(dev)
+        side = cfg["stream"]
+        if cfg["calls"] < cfg["warmup"]:
+            # warm-up on the capture stream: autograd's gradient-accumulation nodes remember the stream they were
+            # created on, and a node that runs on the default stream would invalidate the capture
+            cfg["calls"] += 1
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.source_image = ops.to_nhwc(source_image)
+                self.label = label
+                out = self.UnrolledUpdate()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            return out
+        st = cfg["state"]
+        key = (tuple(source_image.shape), str(dev))
+        if st is None or st["key"] != key:
+            st = dict(key=key, tape=ops.FeedTape(dev), graph=torch.cuda.CUDAGraph(),
+                      x=ops.to_nhwc(source_image).clone(),
+                      src=ops.to_device_async(label["source"], dev, torch.long).clone(),
+                      tgt=ops.to_device_async(label["target"], dev, torch.long).clone())
+            # nothing may keep the previous step's autograd graph (and its accumulation nodes) alive
+            self.target_image = self.c_rand = self.source_image = self.label = None
+            cfg["state"] = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(dev)
+            with ops.recording(st["tape"]):
+                with torch.cuda.graph(st["graph"], stream=side):
+                    self.source_image = st["x"]
+                    self.label = {"source": st["src"], "target": st["tgt"]}
+                    st["out"] = self.UnrolledUpdate()
+            cfg["state"] = st
+        else:
+            st["x"].copy_(ops.to_nhwc(source_image), non_blocking=True)
+            st["src"].copy_(ops.to_device_async(label["source"], dev, torch.long), non_blocking=True)
+            st["tgt"].copy_(ops.to_device_async(label["target"], dev, torch.long), non_blocking=True)
+        st["tape"].upload()
+        st["graph"].replay()
+        return [e.clone() if torch.is_tensor(e) else e for e in st["out"]]
 
     def _report(self, errs):
         """Average the reported scalars over ranks so they equal the global-batch values."""
@@ -322,7 +385,7 @@ class SingleGAN_training(_UnrolledTrainer):
         return _EncodedStyle(self._nE(image, self._onehot(label)))
 
     def _class_mask(self, which, i):
-        return torch.as_tensor(self.label[which]).to(self.device) == i
+        return ops.to_device_async(self.label[which], self.device) == i
 
     def _fool_D(self, fake, fake_label):
         if self.singleD:

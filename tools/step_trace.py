@@ -39,8 +39,11 @@ def main():
     tot = collections.defaultdict(float)
     cnt = collections.Counter()
     t0, t1 = None, None
+    spans = []
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
+            if not ev.name.startswith("Optimizer.step"):
+                spans.append((ev.time_range.start, ev.time_range.end, re.sub(r"[(<].*", "", ev.name)))
             name = re.sub(r"\(.*", "", ev.name)
             if "at::" in name:
                 name = re.sub(r"<.*", "", name)
@@ -52,6 +55,21 @@ def main():
     T = sum(tot.values())
     print("kernel time %.1f ms over %d launches; span first..last kernel %.1f ms" % (T / 1e3, sum(cnt.values()),
                                                                                    (t1 - t0) / 1e3))
+    # idle gaps of the device between consecutive kernels (launch-bound stretches), attributed to the kernel that
+    # the device was waiting for
+    spans.sort()
+    gap_by = collections.defaultdict(float)
+    gaps = []
+    end = spans[0][1]
+    for s0, e0, nm in spans[1:]:
+        if s0 > end:
+            gap_by[nm] += s0 - end
+            gaps.append((s0 - end, nm))
+        end = max(end, e0)
+    print("idle gaps: %.1f ms in total; %d gaps > 20 us" % (sum(g for g, _ in gaps) / 1e3, sum(1 for g, _ in gaps if g > 20)))
+    for k, v in sorted(gap_by.items(), key=lambda kv: -kv[1])[:15]:
+        print("  waiting for %-50s %.2f ms" % (k[:50], v / 1e3))
+    print("  largest:", [(round(g), n[:30]) for g, n in sorted(gaps, reverse=True)[:12]])
     print("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|")
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:45]:
         print("| `%s` | %d | %.2f | %.1f%% | %.1f |" % (k[:90], cnt[k], v / 1e3, 100 * v / T, v / cnt[k]))

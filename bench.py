@@ -264,7 +264,8 @@ def run_ours(args):
     calls0 = ops.abi_calls
     sg.train(x_dev, label_dev)
     launches_per_step = ops.abi_calls - calls0
-    if args.graph == "on":
+    use_graph = args.graph in ("on", "auto")
+    if use_graph:
         sg.enable_cuda_graph(warmup=1)
 
     def step_resident():
@@ -328,15 +329,25 @@ def run_ours(args):
                 "config": {"workload": WORKLOADS[args.workload]["desc"], "per_gpu_batch": batch,
                            "global_batch": batch * world, "image": "3x128x128", "domains": 4,
                            "parallelism": "dp%d" % world, "conv_engine": ops.get_conv_engine(),
-                           "cuda_graph": args.graph == "on",
+                           "cuda_graph": use_graph,
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_glue": glue,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if use_graph:
+            # a CUDA graph that holds captured NCCL kernels must not outlive its communicator, and tearing the two
+            # down in the interpreter's exit order blocks: drop the graph first, then leave without finalisers
+            sg.disable_cuda_graph()
+            import gc
+            gc.collect()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
     return line
 
@@ -352,8 +363,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--engine", default=None, choices=[None, "auto", "fp32", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--graph", default="on", choices=["on", "off"],
-                    help="replay the step as one CUDA graph (sg.enable_cuda_graph) or issue every kernel from Python")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as one CUDA graph (sg.enable_cuda_graph) or issue every kernel from Python; "
+                         "auto = on")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

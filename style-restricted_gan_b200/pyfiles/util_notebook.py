@@ -326,7 +326,10 @@ class _UnrolledTrainer(object):
             gc.collect()
             torch.cuda.synchronize(dev)
             with ops.recording(st["tape"]):
-                with torch.cuda.graph(st["graph"], stream=side):
+                # data parallel: NCCL's watchdog thread polls CUDA events while this thread captures; only the
+                # capturing thread may be restricted
+                mode = "thread_local" if _world()[1] > 1 else "global"
+                with torch.cuda.graph(st["graph"], stream=side, capture_error_mode=mode):
                     self.source_image = st["x"]
                     self.label = {"source": st["src"], "target": st["tgt"]}
                     st["out"] = self.UnrolledUpdate()

@@ -326,3 +326,17 @@ def test_fused_adam_matches_torch_adam():
     for pa, pb in zip(a, b):
         assert _rel(pa.detach(), pb.detach()) < 1e-6
         assert pa.shape == pb.shape
+
+
+def test_fused_norm_path_in_a_subprocess():
+    """SRGAN_NORM_FUSED=1 selects the single-launch two-phase norm kernels (work queues, arrival counters); the switch is
+    read once per process, so the norm parity tests are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SRGAN_NORM_FUSED="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_ops_gpu.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "instance_norm"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout

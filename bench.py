@@ -26,11 +26,14 @@ for p in (os.path.join(PKG, "pyfiles"), os.path.join(ROOT, "oracle")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-GF_PER_IMG = {"srgan_nb03": 433.09, "nb02_solo": 423.22}      # conv+linear GFLOP / image / step
+GF_PER_IMG = {"srgan_nb03": 433.09, "srgan_nb05": 433.09, "nb02_solo": 423.22}      # conv+linear GFLOP / image / step
 WORKLOADS = {
     "srgan_nb03": dict(kind="srgan", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu",
                        desc="SRGAN nb03 recipe: G(3,64,2,2,6)+Encoder+solo-multi D, proposed losses "
                             "(class1 cycle5 idt5 reg.5 idt_reg.5 bKL10 corr100 hist100), unrolled k=5"),
+    "srgan_nb05": dict(kind="srgan", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu", frozen=True,
+                       desc="SRGAN nb05 recipe: nb03 with the encoder trunk frozen while optE is built "
+                            "(Adam lr 1e-3 over fcmean / fcvar only), random-init 'pretrained' weights"),
     "nb02_solo": dict(kind="single_solo", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu",
                       desc="SingleGAN nb02 recipe: Encoder_original + solo-multi D, proposed losses, k=5"),
 }
@@ -79,7 +82,7 @@ def build_case(name, batch):
     w = WORKLOADS[name]
     lbd = dict(cases.PROPOSED, **{"class": 1})
     return dict(kind=w["kind"], nch=w["nch"], dis_nch=w["dis_nch"], enc_nch=w["enc_nch"], res_num=w["res_num"],
-                batch=batch, k=w["k"], lbd=lbd, feature=w["feature"], seed=0)
+                batch=batch, k=w["k"], lbd=lbd, feature=w["feature"], seed=0, frozen=w.get("frozen", False))
 
 
 def synthetic(batch, seed, get_target):
@@ -222,7 +225,7 @@ def run_ours(args):
     np.random.seed(0)
     nets = cases.build_nets(model, case, dev)
     G, D, E = nets
-    sg = cases.build_trainer(nb, case, (G.to(dev), D.to(dev), E.to(dev)), dev)
+    sg = cases.build_trainer(nb, case, (G.to(dev), D.to(dev), E.to(dev)), dev, adam=ops.FusedAdam)
     # every rank gets its own slice of the synthetic global batch
     xg, lab = synthetic(batch * world, 123, util.get_target)
     sl = slice(rank * batch, (rank + 1) * batch)

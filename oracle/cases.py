@@ -27,6 +27,10 @@ CASES = {
     # notebook 01 (BASELINE config 1 recipe): conventional KL, one discriminator per class, k=1
     "single_multi_small": dict(kind="single_multi", nch=8, dis_nch=8, enc_nch=8, res_num=2, batch=6, k=1,
                                lbd=dict(CONVENTIONAL), feature="latent", seed=2),
+    # notebook 05 recipe (BASELINE config 4): encoder trunk "pretrained" and frozen while the optimizer is built, so
+    # optE = Adam(lr 1e-3) over fcmean / fcvar only (05-train... cell 22); the trunk is melted again afterwards
+    "srgan_frozen_small": dict(kind="srgan", nch=8, dis_nch=8, enc_nch=8, res_num=2, batch=4, k=2,
+                               lbd=dict(PROPOSED, **{"class": 1}), feature="mu", seed=4, frozen=True),
     # notebook 03 at FULL width (nch 64, 6 residual blocks), batch 2, k=1: exercises the tensor-core shapes
     "srgan_full": dict(kind="srgan", nch=64, dis_nch=64, enc_nch=64, res_num=6, batch=2, k=1,
                        lbd=dict(PROPOSED, **{"class": 1}), feature="mu", seed=3),
@@ -63,13 +67,21 @@ def build_nets(model_mod, case, device="cpu"):
     return G, D, E
 
 
-def build_trainer(nb_mod, case, nets, device):
+def build_trainer(nb_mod, case, nets, device, adam=torch.optim.Adam):
+    """`adam`: optimizer class for the notebook-05 encoder optimizer (the notebook uses torch.optim.Adam; the product
+    arm of bench.py passes srgan_ops.FusedAdam, same signature, so the step can be replayed as a CUDA graph)."""
     c = CASES[case] if isinstance(case, str) else case
     crit = torch.nn.MSELoss()
     ref_label = np.eye(N_CLASS)
     G, D, E = nets
     if c["kind"] == "srgan":
-        sg = nb_mod.SRGAN_training([G, D, E], [None, None, None], [crit, torch.nn.MSELoss()], c["lbd"], c["k"],
+        optE = None
+        if c.get("frozen"):
+            keys = frozen_keys(E)
+            E.freeze_melt(keys, "freeze")
+            optE = adam(filter(lambda p: p.requires_grad, E.parameters()), lr=0.001, betas=(0.5, 0.999))
+            E.freeze_melt(keys, "melt")
+        sg = nb_mod.SRGAN_training([G, D, E], [None, None, optE], [crit, torch.nn.MSELoss()], c["lbd"], c["k"],
                                    device, ref_label, c["batch"], c["feature"], NDIM)
     else:
         single = c["kind"] == "single_solo"
@@ -96,8 +108,17 @@ def state_dicts(nets):
     return sd(G), ([sd(d) for d in D] if isinstance(D, (list, tuple)) else sd(D)), sd(E)
 
 
+def frozen_keys(E):
+    """state_dict keys of the classifier part of an Encoder (= Encoder_classifier's keys: everything but the
+    fcmean / fcvar heads), what notebook 05 hands to freeze_melt."""
+    return [k for k in E.state_dict().keys() if not k.startswith(("fcmean", "fcvar"))]
+
+
 def build_oracle(case, sds, oracle_mod):
     c = CASES[case] if isinstance(case, str) else case
     g_sd, d_sd, e_sd = sds
+    kw = {}
+    if c.get("frozen"):
+        kw = dict(e_trainable={k for k in e_sd if k.startswith(("fcmean", "fcvar"))}, lr_e=1e-3)
     return oracle_mod.OracleTrainer(c["kind"], g_sd, d_sd, e_sd, c["lbd"], c["k"], np.eye(N_CLASS), c["batch"],
-                                    c["feature"], NDIM, g_cfg=(2, c["res_num"]))
+                                    c["feature"], NDIM, g_cfg=(2, c["res_num"]), **kw)

@@ -1115,6 +1115,15 @@ class FusedAdam(torch.optim.Optimizer):
                 out.append(st["g"])
         return out
 
+    def owned_ids(self):
+        """ids of the parameters whose data / grad live in this optimizer's flat buffers."""
+        out = set()
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            if st is not None:
+                out.update(id(p) for p in st["params"])
+        return out
+
     def zero_grad(self, set_to_none=False):
         for gi, group in enumerate(self.param_groups):
             st = self._flat.get(gi) or self._flatten(gi, group)

@@ -93,6 +93,21 @@ def _sync_grads(module, optimizer=None):
         o += n
 
 
+def _zero_grads(module, optimizer=None):
+    """`module.zero_grad()` of the reference (pyfiles/util_notebook.py:577,613-614,670-671).  With a FusedAdam the
+    gradients of its parameters are zeroed in the optimizer's flat buffer and stay views of it, so autograd
+    accumulates straight into the buffer that the all-reduce and the Adam kernel read (no per-tensor copies);
+    parameters the optimizer does not own (notebook 05: the melted encoder trunk) are reset as usual."""
+    if isinstance(optimizer, ops.FusedAdam):
+        optimizer.zero_grad()
+        owned = optimizer.owned_ids()
+        for p in module.parameters():
+            if id(p) not in owned:
+                p.grad = None
+    else:
+        module.zero_grad()
+
+
 def _unwrap(net):
     """The notebooks hand over nn.DataParallel wrappers; compute runs on the wrapped module."""
     return net.module if isinstance(net, torch.nn.DataParallel) else net
@@ -217,8 +232,8 @@ class _UnrolledTrainer(object):
         latent-regression losses.  Returns [errG, errE_output]."""
         lbd = self.lbd
         src, lab = self.source_image, self.label
-        self._nG.zero_grad()
-        self._nE.zero_grad()
+        _zero_grads(self._nG, self.optG)
+        _zero_grads(self._nE, self.optE)
 
         recon_image, enc_info = self.G_transformation(lab["source"], self.target_image, True, src)
         errG = self._fool_D(self.target_image, lab["target"])
@@ -260,8 +275,8 @@ class _UnrolledTrainer(object):
             hook(self)
 
         # ---- phase 2: G only (E receives gradients but is not stepped) ----
-        self._nG.zero_grad()
-        self._nE.zero_grad()
+        _zero_grads(self._nG, self.optG)
+        _zero_grads(self._nE, self.optE)
         target_mu = self._encode(self.target_image, lab["target"])[1]
         errG_ex = ops.l1_mean(self.c_rand, target_mu) * lbd["reg"]
         if lbd["idt_reg"] * lbd["idt"] > 0:
@@ -289,6 +304,11 @@ class _UnrolledTrainer(object):
         sub-batch sizes)."""
         if isinstance(self._nD, (list, tuple)):
             raise NotImplementedError("CUDA-graph replay needs static shapes: not with one discriminator per class")
+        for o in (self.optG, self.optD, self.optE):
+            if not isinstance(o, ops.FusedAdam):
+                raise NotImplementedError(
+                    "CUDA-graph replay needs optimizers whose step is a capturable kernel: build them with "
+                    "srgan_ops.FusedAdam (same constructor as torch.optim.Adam) or let opt_sche_initialization() do it")
         self._graph = dict(warmup=int(warmup), calls=0, state=None)
         return self
 
@@ -407,7 +427,7 @@ class SingleGAN_training(_UnrolledTrainer):
             self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
         fake = self.target_image.detach()
         if self.singleD:
-            self._nD.zero_grad()
+            _zero_grads(self._nD, self.optD)
             output, output_class = self._nD(self.source_image)
             errD = get_loss_D(output, 1., self.criterion, self.device) + \
                 get_domainloss_D(output_class, self._onehot(self.label["source"]), self.criterion_class) \
@@ -421,7 +441,7 @@ class SingleGAN_training(_UnrolledTrainer):
         # one discriminator per class; like the reference, the LAST class's loss is what gets returned
         for i in self.classes:
             errD = 0
-            self._nD[i].zero_grad()
+            _zero_grads(self._nD[i], self.optD[i])
             real = self.source_image[self._class_mask("source", i)]
             if real.shape[0] != 0:
                 errD = errD + get_loss_D(self._nD[i](real), 1., self.criterion, self.device)
@@ -481,7 +501,7 @@ class SRGAN_training(_UnrolledTrainer):
             get_domainloss_D(output_class, self._onehot(fake_label), self.criterion_class) * self.lbd["class"]
 
     def update_D(self, keep_graph=True):
-        self._nD.zero_grad()
+        _zero_grads(self._nD, self.optD)
         with torch.set_grad_enabled(keep_graph):
             self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
         output, output_class = self._nD(self.source_image)

@@ -9,7 +9,7 @@ import torch
 import cases
 import srgan_oracle as so
 
-SMALL = ["srgan_small", "single_solo_small", "single_multi_small"]
+SMALL = ["srgan_small", "single_solo_small", "single_multi_small", "srgan_frozen_small"]
 
 
 def _golden(name):

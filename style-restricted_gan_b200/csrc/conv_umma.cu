@@ -639,9 +639,10 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   // Bring-up override: SRGAN_DBG_CONV_MT=1|2.
   static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
   const long ctas = (long)grid.x * grid.y * grid.z;
-  const int mt = e_mt ? atoi(e_mt) : (BN == 128 && ctas >= 2 * kNumSMs ? 2 : 1);
+  const int mt = e_mt ? atoi(e_mt) : ((BN == 128 || BN == 64) && ctas >= 2 * kNumSMs ? 2 : 1);
   if (mt == 2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st);
   if (mt == 2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st);
+  if (mt == 2 && BN == 64) return launch_bn<64, 2>(ma, mb, p, bias, y, grid, st);
   switch (BN) {
     case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st);
     case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st);
@@ -881,12 +882,33 @@ static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
   int bn = 32 / (bw * bh);
   w.tiles_w = ceil_div(d->Q, bw); w.tiles_h = ceil_div(d->P, bh); w.tiles_n = ceil_div(d->N, bn);
   w.chunks = w.tiles_w * w.tiles_h * w.tiles_n;
-  int tiles = w.tiles_k * w.tiles_c * w.ngroups;
-  int splits = ceil_div(2 * kNumSMs, tiles);              // one resident CTA per SM: about two rounds
-  if (splits > ceil_div(w.chunks, 8)) splits = ceil_div(w.chunks, 8);
-  if (splits > 128) splits = 128;
-  if (splits < 1) splits = 1;
-  w.cps = ceil_div(w.chunks, splits);
+  // Pixel splits (split-K): one CTA per SM is resident, so the launch runs in ceil(CTAs / 148) rounds of
+  // (chunks per split x time per chunk + prologue / epilogue), and every split adds one pass over dW to the
+  // fixed-order reduction that follows.  Pick the split count that minimises that estimate (a count that spills one
+  // CTA into a third round costs 50 %: 9 taps x 33 splits = 297 CTAs was the old choice for the residual blocks).
+  // Constants from tools/conv_bench.py: 0.29 us per 32-pixel chunk of a 128 x 256 MMA tile, ~5 us to drain a
+  // 256 x 256 accumulator, ~4 TB/s for the reduction.  Bring-up override: SRGAN_DBG_WGRAD_SPLITS.
+  const int tiles = w.tiles_k * w.tiles_c * w.ngroups;
+  const double chunk_us = 0.29 * w.KT * (w.BN / 256.0);
+  const double epi_us = 3.0 + 2.5 * w.KT * (w.BN / 256.0);
+  const double dw_mb = (double)d->K * T * d->C * 4e-6;
+  int max_splits = ceil_div(w.chunks, 8);
+  if (max_splits > 128) max_splits = 128;
+  if (max_splits < 1) max_splits = 1;
+  int best = 1;
+  double best_t = 1e30;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const int cps = ceil_div(w.chunks, sp);
+    const int eff = ceil_div(w.chunks, cps);
+    if (eff != sp) continue;
+    const int rounds = ceil_div(tiles * eff, kNumSMs);
+    double t = rounds * (cps * chunk_us + epi_us);
+    if (eff > 1) t += 3.0 + eff * dw_mb / 4.0;
+    if (t < best_t) { best_t = t; best = eff; }
+  }
+  static const char* e_sp = getenv("SRGAN_DBG_WGRAD_SPLITS");
+  if (e_sp && atoi(e_sp) >= 1 && atoi(e_sp) <= max_splits) best = atoi(e_sp);
+  w.cps = ceil_div(w.chunks, best);
   w.splits = ceil_div(w.chunks, w.cps);
   return w;
 }

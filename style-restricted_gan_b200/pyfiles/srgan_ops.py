@@ -1115,6 +1115,31 @@ class FusedAdam(torch.optim.Optimizer):
                 out.append(st["g"])
         return out
 
+    def flat_state(self):
+        """Adam moments and step counters per parameter group (CPU tensors), for checkpoints.  The weights are the
+        modules' state_dict; the moments are stored in the optimizer's flat layout, which is a pure function of the
+        parameter list."""
+        out = {}
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            if st is not None:
+                out[gi] = {"m": st["m"].detach().cpu(), "v": st["v"].detach().cpu(), "step": int(st["step"]),
+                           "lr": float(group["lr"])}
+        return out
+
+    def load_flat_state(self, state):
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi) or self._flatten(gi, group)
+            if st is None:
+                continue
+            src = state[gi] if gi in state else state[str(gi)]
+            if src["m"].numel() != st["m"].numel():
+                raise ValueError("FusedAdam.load_flat_state: parameter layout differs from the checkpoint")
+            st["m"].copy_(src["m"])
+            st["v"].copy_(src["v"])
+            st["step"] = int(src["step"])
+            group["lr"] = float(src["lr"])
+
     def owned_ids(self):
         """ids of the parameters whose data / grad live in this optimizer's flat buffers."""
         out = set()

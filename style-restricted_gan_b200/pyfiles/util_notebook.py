@@ -529,6 +529,85 @@ class SRGAN_training(_UnrolledTrainer):
         return self._report([errorG, errorD, errorE])
 
 
+# ------------------------------------------------------------------------------------------- checkpoints
+def save_checkpoint(sg, path, **extra):
+    """Everything a resumed run needs (the reference only ever saves `sg.G.module.state_dict()` etc. and
+    cannot resume): network weights under the REFERENCE's state_dict keys (each entry loads into the reference's
+    modules and vice versa), Adam moments / step counters / learning rates, scheduler state and the CPU RNG states
+    the step draws its noise from."""
+    def sd(net):
+        if isinstance(net, (list, tuple)):
+            return [sd(n) for n in net]
+        return {k: v.detach().cpu() for k, v in _unwrap(net).state_dict().items()}
+
+    def opt_state(o):
+        if isinstance(o, (list, tuple)):
+            return [opt_state(x) for x in o]
+        if o is None:
+            return None
+        return {"fused": o.flat_state()} if isinstance(o, ops.FusedAdam) else {"torch": o.state_dict()}
+
+    def sch_state(s_):
+        if isinstance(s_, (list, tuple)):
+            return [sch_state(x) for x in s_]
+        return None if s_ is None else s_.state_dict()
+    state = {"format": "srgan_b200.checkpoint.v1",
+             "G": sd(sg.G), "D": sd(sg.D), "E": sd(sg.E),
+             "optG": opt_state(sg.optG), "optD": opt_state(sg.optD), "optE": opt_state(sg.optE),
+             "scheG": sch_state(sg.scheG), "scheD": sch_state(sg.scheD), "scheE": sch_state(sg.scheE),
+             "rng": {"torch_cpu": torch.get_rng_state(), "numpy": np.random.get_state()},
+             "config": {"lbd": dict(sg.lbd), "k": sg.k, "n_batch": sg.n_batch, "encoded_feature": sg.encoded_feature,
+                        "ndim": sg.ndim},
+             "extra": extra}
+    if getattr(sg, "hi", None) is not None:
+        state["hist_target"] = sg.hi.target.detach().cpu()      # drawn from the RNG at construction (util.py:543)
+    torch.save(state, path)
+    return path
+
+
+def load_checkpoint(sg, path, restore_rng=True):
+    """Inverse of save_checkpoint on a trainer built the same way (same nets, `opt_sche_initialization()` called).
+    Returns the `extra` dictionary."""
+    state = torch.load(path, map_location="cpu", weights_only=False)
+    if state.get("format") != "srgan_b200.checkpoint.v1":
+        raise ValueError("not a srgan_b200 checkpoint: %r" % (state.get("format"),))
+
+    def load_net(net, sd_):
+        if isinstance(net, (list, tuple)):
+            for n, s_ in zip(net, sd_):
+                load_net(n, s_)
+        else:
+            _unwrap(net).load_state_dict(sd_)
+
+    def load_opt(o, st):
+        if isinstance(o, (list, tuple)):
+            for x, s_ in zip(o, st):
+                load_opt(x, s_)
+        elif o is not None and st is not None:
+            if isinstance(o, ops.FusedAdam):
+                o.load_flat_state(st["fused"])
+            else:
+                o.load_state_dict(st["torch"])
+
+    def load_sch(s_, st):
+        if isinstance(s_, (list, tuple)):
+            for x, y in zip(s_, st):
+                load_sch(x, y)
+        elif s_ is not None and st is not None:
+            s_.load_state_dict(st)
+    load_net(sg.G, state["G"]); load_net(sg.D, state["D"]); load_net(sg.E, state["E"])
+    load_opt(sg.optG, state["optG"]); load_opt(sg.optD, state["optD"]); load_opt(sg.optE, state["optE"])
+    load_sch(sg.scheG, state["scheG"]); load_sch(sg.scheD, state["scheD"]); load_sch(sg.scheE, state["scheE"])
+    if "hist_target" in state and getattr(sg, "hi", None) is not None:
+        sg.hi.target = state["hist_target"].to(sg.hi.target.device)
+    if restore_rng:
+        torch.set_rng_state(state["rng"]["torch_cpu"])
+        np.random.set_state(state["rng"]["numpy"])
+    if getattr(sg, "_graph", None) is not None:
+        sg._graph["state"] = None          # a captured step keeps pointing at the same buffers, but re-capture is cheap
+    return state.get("extra", {})
+
+
 # ------------------------------------------------------------------------------------------- visual check
 def get_output_and_plot(sg, dataset, index, class_info, random_sample_num=5, *legacy, device="cuda"):
     """Grid of translations of one sample (source / target / reconstruction / identity, by encoder style and

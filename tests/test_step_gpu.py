@@ -213,3 +213,47 @@ def test_cuda_graph_replay_is_bit_identical_to_eager_steps():
     assert le == lg, (le, lg)
     assert torch.equal(pe, pg)
     assert torch.equal(re_, rg)
+
+
+def test_checkpoint_resume_continues_bit_identically(tmp_path):
+    """save_checkpoint / load_checkpoint: weights under the reference's state_dict keys, Adam moments,
+    step counters, scheduler and RNG state.  A trainer rebuilt from scratch and resumed at step 2 reproduces steps 3-4
+    of the uninterrupted run exactly."""
+    name = "srgan_small"
+    c = dict(cases.CASES[name], batch=4, k=2)
+    model, util, nb = cases.use_product_modules()
+
+    def build(seed):
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        nets = tuple(n.to(DEV) for n in cases.build_nets(model, c, DEV))
+        sg = cases.build_trainer(nb, c, nets, DEV)
+        return nets, sg
+
+    def steps(sg, first, count):
+        out = []
+        for step in range(first, first + count):
+            x, label = cases.synthetic_batch(c["batch"], util.get_target, seed=200 + step)
+            rng = torch.get_rng_state()                       # synthetic_batch reseeds numpy only
+            errs = sg.train(x.to(DEV), {"source": label["source"].to(DEV), "target": label["target"]})
+            out.append([float(e) for e in errs])
+            assert not torch.equal(rng, torch.get_rng_state())    # the step consumed host noise
+        return out
+    nets, sg = build(0)
+    torch.manual_seed(5)
+    steps(sg, 0, 2)
+    sg.scheG.step(); sg.scheD.step(); sg.scheE.step()
+    path = str(tmp_path / "ckpt.pt")
+    nb.save_checkpoint(sg, path, epoch=7)
+    ref_losses = steps(sg, 2, 2)
+    ref_params = torch.cat([p.detach().reshape(-1) for n in nets for p in n.parameters()]).cpu()
+
+    nets2, sg2 = build(99)                                     # different init, different histogram target
+    torch.manual_seed(1234)
+    extra = nb.load_checkpoint(sg2, path)
+    assert extra == {"epoch": 7}
+    assert list(torch.load(path, weights_only=False)["G"].keys()) == list(nets[0].state_dict().keys())
+    got_losses = steps(sg2, 2, 2)
+    got_params = torch.cat([p.detach().reshape(-1) for n in nets2 for p in n.parameters()]).cpu()
+    assert got_losses == ref_losses, (got_losses, ref_losses)
+    assert torch.equal(got_params, ref_params)

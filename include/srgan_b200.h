@@ -80,6 +80,12 @@ int srgan_conv2d_dgrad(const srgan_conv_desc* d, const float* dy, const float* w
                        int engine, void* workspace, size_t workspace_bytes, void* stream);
 int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, const float* dy, float* dw,
                        float* dbias, int engine, void* workspace, size_t workspace_bytes, void* stream);
+/* dx = dgrad(dy) + addend (addend: layout of dx).  The residual blocks (ref SingleResidualBlock, pyfiles/model.py:196-201)
+ * send two gradients into their input - through c1 and through the skip connection; autograd would add them with a
+ * separate pass over the tensor, here the skip gradient is added in the dgrad epilogue.  tcgen05 engine, stride 1. */
+int srgan_conv2d_dgrad_add_supported(const srgan_conv_desc* d, int engine);
+int srgan_conv2d_dgrad_add(const srgan_conv_desc* d, const float* dy, const float* w, const float* addend,
+                           float* dx, int engine, void* workspace, size_t workspace_bytes, void* stream);
 /* which engine AUTO resolves to for this shape/pass: SRGAN_CONV_FP32 or SRGAN_CONV_TF32 */
 int srgan_conv2d_engine(const srgan_conv_desc* d, int pass);
 

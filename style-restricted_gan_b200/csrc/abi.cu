@@ -32,7 +32,8 @@ size_t conv_umma_workspace(const srgan_conv_desc* d, int pass);
 int conv_fprop_umma_launch(const srgan_conv_desc*, const float*, const float*, const float*, float*, int, float,
                            void*, size_t, cudaStream_t);
 int conv_dgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, void*, size_t,
-                           cudaStream_t);
+                           cudaStream_t, const float* addend);
+bool conv_dgrad_umma_add_supported(const srgan_conv_desc* d);
 int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
                            cudaStream_t);
 
@@ -103,8 +104,23 @@ extern "C" int srgan_conv2d_dgrad(const srgan_conv_desc* d, const float* dy, con
   SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
   int e = resolve_engine(d, 1, engine);
   if (e < 0) { set_error("conv dgrad: shape not supported by the tcgen05 engine"); return e; }
-  if (e == SRGAN_CONV_TF32) return conv_dgrad_umma_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream);
+  if (e == SRGAN_CONV_TF32) return conv_dgrad_umma_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream, nullptr);
   return conv_dgrad_ffma_launch(d, dy, w, dx, (cudaStream_t)stream);
+}
+
+// dx = dgrad(dy) + addend: the second gradient that flows into the convolution's input (residual skip) is added in
+// the epilogue instead of by a separate pass over the tensor
+extern "C" int srgan_conv2d_dgrad_add_supported(const srgan_conv_desc* d, int engine) {
+  if (check_desc(d)) return 0;
+  if (resolve_engine(d, 1, engine) != SRGAN_CONV_TF32) return 0;
+  return conv_dgrad_umma_add_supported(d) ? 1 : 0;
+}
+extern "C" int srgan_conv2d_dgrad_add(const srgan_conv_desc* d, const float* dy, const float* w, const float* addend,
+                                      float* dx, int engine, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(dy && w && dx && addend, "null pointer");
+  if (resolve_engine(d, 1, engine) != SRGAN_CONV_TF32) { set_error("conv dgrad_add: tcgen05 engine only"); return SRGAN_E_UNSUPPORTED; }
+  return conv_dgrad_umma_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream, addend);
 }
 
 extern "C" int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, const float* dy, float* dw,

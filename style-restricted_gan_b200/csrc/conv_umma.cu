@@ -88,10 +88,16 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* o) {
 // act(v[0..N) + bias) -> dst[0..N), N a multiple of 8, dst aligned to VEC floats
 template <int ACT, int N, int VEC>
 __device__ __forceinline__ void epi_row_chunk(const float (&v)[32], float* __restrict__ dst,
-                                              const float* __restrict__ bias, float slope) {
+                                              const float* __restrict__ bias, float slope,
+                                              const float* __restrict__ add = nullptr) {
 #pragma unroll
   for (int j = 0; j < N; j += 8) {
     float o[8];
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (add) {                      // same layout as dst: the other gradient that flows into this tensor
+      a0 = __ldg(reinterpret_cast<const float4*>(add + j));
+      a1 = __ldg(reinterpret_cast<const float4*>(add + j + 4));
+    }
     if (bias) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j + 4));
@@ -101,6 +107,8 @@ __device__ __forceinline__ void epi_row_chunk(const float (&v)[32], float* __res
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = v[j + e];
     }
+    o[0] += a0.x; o[1] += a0.y; o[2] += a0.z; o[3] += a0.w;
+    o[4] += a1.x; o[5] += a1.y; o[6] += a1.z; o[7] += a1.w;
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = act_t<ACT>(o[e], slope);
     if (VEC == 8) {
@@ -113,7 +121,12 @@ __device__ __forceinline__ void epi_row_chunk(const float (&v)[32], float* __res
 }
 template <int N>
 __device__ __forceinline__ void epi_row_chunk_any(const float (&v)[32], float* dst, const float* bias, int act,
-                                                  float slope, int vec) {
+                                                  float slope, int vec, const float* add = nullptr) {
+  if (add) {                                     // fused gradient accumulation: no bias, no activation
+    if (vec == 8) epi_row_chunk<SRGAN_ACT_NONE, N, 8>(v, dst, nullptr, 0.f, add);
+    else epi_row_chunk<SRGAN_ACT_NONE, N, 4>(v, dst, nullptr, 0.f, add);
+    return;
+  }
 #define SRGAN_EPI_CASE(A)                                                         \
   case A:                                                                         \
     if (vec == 8) epi_row_chunk<A, N, 8>(v, dst, bias, slope);                    \
@@ -154,7 +167,8 @@ __device__ __forceinline__ UmmaItem umma_item(const UmmaConvP& p, int item) {
 template <int BN, int MT>
 __global__ void __launch_bounds__((UmmaCfg<BN, MT>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y) {
+                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y,
+                 const float* __restrict__ addend) {
   using Cfg = UmmaCfg<BN, MT>;
   constexpr int NBUF = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -280,6 +294,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                            (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MT * BN) + mt * BN;
         const float* brow = bias ? bias + col0 : nullptr;
+        const float* arow = addend ? addend + (yrow - y) + col0 : nullptr;      // addend has the layout of y
         if (kChunk == 32) {
           // the TMEM load of chunk c + 1 is in flight while chunk c is converted and stored
           uint32_t ra[32], rb[32];
@@ -296,11 +311,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
             if (valid) {
               if (col0 + c + 32 <= p.K && p.epi_vec) {
-                epi_row_chunk_any<32>(v, yrow + col0 + c, brow ? brow + c : nullptr, p.act, p.slope, p.epi_vec);
+                epi_row_chunk_any<32>(v, yrow + col0 + c, brow ? brow + c : nullptr, p.act, p.slope, p.epi_vec,
+                                      arow ? arow + c : nullptr);
               } else {
+#pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (col0 + c + j < p.K)
-                    yrow[col0 + c + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f), p.act, p.slope);
+                    yrow[col0 + c + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f) +
+                                                   (arow ? __ldg(arow + c + j) : 0.f), p.act, p.slope);
               }
             }
           }
@@ -309,11 +327,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tmem_ld16(taddr, v);
           if (valid) {
             if (col0 + 16 <= p.K && p.epi_vec) {
-              epi_row_chunk_any<16>(v, yrow + col0, brow, p.act, p.slope, p.epi_vec);
+              epi_row_chunk_any<16>(v, yrow + col0, brow, p.act, p.slope, p.epi_vec, arow);
             } else {
+#pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (col0 + j < p.K)
-                  yrow[col0 + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + j) : 0.f), p.act, p.slope);
+                  yrow[col0 + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + j) : 0.f) +
+                                             (arow ? __ldg(arow + j) : 0.f), p.act, p.slope);
             }
           }
         }
@@ -551,7 +571,7 @@ static int pick_bn(int K) {
 
 template <int BN, int MT = 1>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, float* y,
-                     dim3 grid, cudaStream_t st) {
+                     dim3 grid, cudaStream_t st, const float* addend) {
   using Cfg = UmmaCfg<BN, MT>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -576,7 +596,7 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
   }
   q.n_items = (int)items;
   const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);     // persistent: one CTA per SM
-  conv_umma_kernel<BN, MT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y);
+  conv_umma_kernel<BN, MT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend);
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -592,7 +612,7 @@ struct Problem {
 };
 
 static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st,
-                       const CUtensorMap* ma_prebuilt = nullptr) {
+                       const CUtensorMap* ma_prebuilt = nullptr, const float* addend = nullptr) {
   if (((uintptr_t)pr.act | (uintptr_t)pr.filt | (uintptr_t)y) % 16) {
     set_error("tcgen05 conv: tensors must be 16-byte aligned");
     return SRGAN_E_BADARG;
@@ -632,6 +652,7 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   p.act = act; p.slope = slope;
   p.epi_vec = (pr.fK % 8 == 0 && (uintptr_t)y % 32 == 0) ? 8 : (pr.fK % 4 == 0 ? 4 : 0);
   if (bias && (uintptr_t)bias % 16) p.epi_vec = 0;            // vector bias loads need an aligned bias
+  if (addend && ((uintptr_t)addend % 16 || pr.fK % 4)) { set_error("conv: addend must be 16-byte aligned"); return SRGAN_E_BADARG; }
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
   // Two M sub-tiles per CTA (one filter tile feeds 256 pixels) when TMEM can still double-buffer the accumulator
   // (2 x 2 x 128 columns) and every SM keeps work; 256-wide tiles stay at MT = 1: overlapping the epilogue with the
@@ -640,15 +661,15 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
   const long ctas = (long)grid.x * grid.y * grid.z;
   const int mt = e_mt ? atoi(e_mt) : ((BN == 128 || BN == 64) && ctas >= 2 * kNumSMs ? 2 : 1);
-  if (mt == 2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st);
-  if (mt == 2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st);
-  if (mt == 2 && BN == 64) return launch_bn<64, 2>(ma, mb, p, bias, y, grid, st);
+  if (mt == 2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st, addend);
+  if (mt == 2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st, addend);
+  if (mt == 2 && BN == 64) return launch_bn<64, 2>(ma, mb, p, bias, y, grid, st, addend);
   switch (BN) {
-    case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st);
-    case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st);
-    case 64:  return launch_bn<64>(ma, mb, p, bias, y, grid, st);
-    case 32:  return launch_bn<32>(ma, mb, p, bias, y, grid, st);
-    default:  return launch_bn<16>(ma, mb, p, bias, y, grid, st);
+    case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st, addend);
+    case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st, addend);
+    case 64:  return launch_bn<64>(ma, mb, p, bias, y, grid, st, addend);
+    case 32:  return launch_bn<32>(ma, mb, p, bias, y, grid, st, addend);
+    default:  return launch_bn<16>(ma, mb, p, bias, y, grid, st, addend);
   }
 }
 
@@ -957,8 +978,15 @@ int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float
   return run_problem(pr, bias, y, act, slope, st);
 }
 
+// addend (optional, layout of dx): dx = dgrad(dy) + addend in the epilogue; only on the generic stride-1 path
+bool conv_dgrad_umma_add_supported(const srgan_conv_desc* d) {
+  ThinPlan t;
+  return d->stride == 1 && d->C % 4 == 0 && !conv_thinout_supported(d, 1) && !thin_plan(d, 1, &t);
+}
+
 int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
-                           size_t ws_bytes, cudaStream_t st) {
+                           size_t ws_bytes, cudaStream_t st, const float* addend) {
+  if (addend && !conv_dgrad_umma_add_supported(d)) { set_error("conv dgrad: fused addend not available for this shape"); return SRGAN_E_UNSUPPORTED; }
   if (conv_thinout_supported(d, 1)) return conv_thinout_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st);
   { ThinPlan t; if (thin_plan(d, 1, &t)) return conv_thin_fwdlike_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st); }
   const int T = d->R * d->S;
@@ -999,7 +1027,7 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
     }
     p.tap_begin[4] = nt;
   }
-  return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st);
+  return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st, nullptr, addend);
 }
 
 void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st);

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsrgan_b200.so")
+# SRGAN_LIB (bring-up only): load another build of the library for A/B timing
+LIB_PATH = os.environ.get("SRGAN_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsrgan_b200.so")
 
 c_int, c_float, c_size_t, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
 P = c_void_p
@@ -29,6 +30,8 @@ SIGNATURES = {
     "srgan_conv2d_workspace": (c_size_t, [DP, c_int, c_int]),
     "srgan_conv2d_fprop": (c_int, [DP, P, P, P, P, c_int, c_float, c_int, P, c_size_t, P]),
     "srgan_conv2d_dgrad": (c_int, [DP, P, P, P, c_int, P, c_size_t, P]),
+    "srgan_conv2d_dgrad_add_supported": (c_int, [DP, c_int]),
+    "srgan_conv2d_dgrad_add": (c_int, [DP, P, P, P, P, c_int, P, c_size_t, P]),
     "srgan_conv2d_wgrad": (c_int, [DP, P, P, P, P, c_int, P, c_size_t, P]),
     "srgan_conv2d_engine": (c_int, [DP, c_int]),
     "srgan_nchw_to_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
@@ -98,6 +101,8 @@ def load():
             "(the SRGAN B200 kernels have no CPU / PyTorch fallback)")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("SRGAN_LIB") and not hasattr(lib, name):
+            continue              # an older build under A/B test may lack the newest entry points
         fn = getattr(lib, name)   # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args

@@ -10,6 +10,7 @@ are stored KRSC, and norm + conditional bias + affine + activation (+ residual) 
 There is no CPU path: calling a module with CPU tensors raises `SrganKernelError`.
 """
 import functools
+import os
 
 import torch
 import torch.nn as nn
@@ -221,6 +222,9 @@ def get_norm_layer(layer_type="instance", num_con=2):
 # --------------------------------------------------------------------------------------------
 # generator   (ref: pyfiles/model.py:188-249)
 # --------------------------------------------------------------------------------------------
+_NO_SKIP_FUSE = os.environ.get("SRGAN_DBG_NO_SKIP_FUSE", "0") != "0"     # bring-up: autograd adds the skip gradient
+
+
 class SingleResidualBlock(nn.Module):
     def __init__(self, nch, c_norm_layer):
         super().__init__()
@@ -231,9 +235,15 @@ class SingleResidualBlock(nn.Module):
 
     def forward(self, x):
         data, con = x[0], x[1]
-        h = self.cn1(self.c1(data), con, act=ops.ACT_RELU)
+        if self.c1.bias is None and self.c1.padding_mode == "zeros" and not _NO_SKIP_FUSE:
+            # c1 and the skip connection leave `data` through one autograd node: their two gradients are added in
+            # the dgrad epilogue of c1 (no separate pass over the tensor)
+            h1, skip = ops.conv2d_skip(data, self.c1.weight, self.c1.stride[0], self.c1.padding[0])
+        else:
+            h1, skip = self.c1(data), data
+        h = self.cn1(h1, con, act=ops.ACT_RELU)
         # second norm has no activation; the skip connection is added inside the same kernel
-        return self.cn2(self.c2(h), con, residual=data), con
+        return self.cn2(self.c2(h), con, residual=skip), con
 
 
 class SingleGenerator(nn.Module):

@@ -290,14 +290,22 @@ def _fprop(d, x, w, bias, act, slope):
     return y
 
 
-def _dgrad(d, dy, w, like):
+def _dgrad(d, dy, w, like, addend=None):
+    """dx = dgrad(dy) (+ addend, fused into the epilogue where the engine supports it)."""
     dx = _empty_nhwc(d.N, d.C, d.H, d.W, like)
     if dx.numel() == 0:
         return dx
     lib = _lib()
     nb = lib.srgan_conv2d_workspace(d, 1, _engine)
     ws = _workspace(dy.device, nb) if nb else None
+    if addend is not None:
+        addend = _raw_to_nhwc(addend)
+        if lib.srgan_conv2d_dgrad_add_supported(d, _engine):
+            _call("srgan_conv2d_dgrad_add", d, _p(dy), _p(w), _p(addend), _p(dx), _engine, _p(ws), nb, _stream())
+            return dx
     _call("srgan_conv2d_dgrad", d, _p(dy), _p(w), _p(dx), _engine, _p(ws), nb, _stream())
+    if addend is not None:
+        dx.add_(addend)
     return dx
 
 
@@ -355,6 +363,36 @@ class _Conv2dFn(torch.autograd.Function):
         if want_w or want_b:
             dw, db = _wgrad(ctx.d, x, dz, want_w, want_b)
         return dx, dw, db, None, None, None, None
+
+
+class _Conv2dSkipFn(torch.autograd.Function):
+    """(y, x) = (conv2d(x, w), x): the first convolution of a residual block together with the skip connection that
+    leaves the same tensor (ref SingleResidualBlock.forward pyfiles/model.py:196-201).  Both gradients of x arrive in
+    ONE backward call, so the skip gradient is added in the dgrad epilogue instead of by autograd's separate add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        K, C2, R, S = weight.shape
+        if C2 != C:
+            raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
+        d = _desc(N, H, W, C, K, R, S, stride, pad)
+        y = _fprop(d, x, _krsc(weight), None, ACT_NONE, 0.0)
+        ctx.d, ctx.weight = d, weight
+        ctx.save_for_backward(x)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x, = ctx.saved_tensors
+        dz = _raw_to_nhwc(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _dgrad(ctx.d, dz, _krsc(ctx.weight), x, addend=dskip)      # live weight (see module docstring)
+        if ctx.needs_input_grad[1]:
+            dw, _ = _wgrad(ctx.d, x, dz, True, False)
+        return dx, dw, None, None
 
 
 class _ConvTranspose2dFn(torch.autograd.Function):
@@ -418,6 +456,14 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, padding_mode="zeros", act=
     elif padding_mode not in ("zeros", "reflect"):
         raise NotImplementedError("padding_mode %r" % (padding_mode,))
     return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(act), float(slope))
+
+
+def conv2d_skip(x, weight, stride=1, padding=0):
+    """Returns (conv2d(x, weight), x'): x' is x, routed through the same autograd node (see _Conv2dSkipFn)."""
+    _req(x, weight)
+    if x.dim() != 4:
+        raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
+    return _Conv2dSkipFn.apply(x, weight, int(stride), int(padding))
 
 
 def conv_transpose2d(x, weight, stride=1, padding=0):

@@ -118,3 +118,30 @@ def test_thin_output_row_gemm_tanh_and_bands():
         y = ops.conv2d(x, w, b, 1, pad, "zeros", ops.ACT_TANH, 0.0)
         ref = torch.tanh(F.conv2d(x.double(), w.double(), b.double(), 1, pad))
         assert _rel(y, ref) < TOL, (N, C, H, W, K, R, pad)
+
+
+def test_residual_skip_gradient_fused_into_dgrad_epilogue():
+    """conv2d_skip returns (conv(x), x) through one autograd node: d x = dgrad(d conv) + d skip with the add in the
+    dgrad epilogue (srgan_conv2d_dgrad_add), also for shapes where the fused form is not available (FFMA engine,
+    odd channel counts) - same values as the two separate ops."""
+    for (N, C, H, W, K, engine) in ((3, 256, 32, 32, 256, "auto"), (2, 64, 16, 16, 64, "auto"), (70, 32, 8, 8, 32, "auto"),
+                                    (2, 64, 16, 16, 64, "fp32")):
+        ops.set_conv_engine(engine)
+        try:
+            x = _rand(N, C, H, W, seed=41).contiguous(memory_format=CL).requires_grad_(True)
+            w = _rand(K, C, 3, 3, seed=42, scale=(C * 9) ** -0.5).contiguous(memory_format=CL).requires_grad_(True)
+            g1, g2 = _rand(N, K, H, W, seed=43).contiguous(memory_format=CL), _rand(N, C, H, W, seed=44).contiguous(memory_format=CL)
+            y, skip = ops.conv2d_skip(x, w, 1, 1)
+            dx, dw = torch.autograd.grad([y, skip], [x, w], [g1, g2])
+            xr, wr = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+            yr = F.conv2d(xr, wr, None, 1, 1)
+            dxr, dwr = torch.autograd.grad([yr, xr * 1.0], [xr, wr], [g1.double(), g2.double()])
+            tol = TOL if engine == "auto" else 3e-5
+            assert _rel(y, yr) < tol and _rel(dx, dxr) < tol and _rel(dw, dwr) < tol, (N, C, engine, _rel(dx, dxr))
+            # skip gradient absent (the skip output unused): plain dgrad
+            y2, _ = ops.conv2d_skip(x, w, 1, 1)
+            dx2, = torch.autograd.grad(y2, x, g1)
+            dx2r, = torch.autograd.grad(F.conv2d(xr, wr, None, 1, 1), xr, g1.double())
+            assert _rel(dx2, dx2r) < tol
+        finally:
+            ops.set_conv_engine("auto")

@@ -1,5 +1,2 @@
 set -x
-for i in 1 2; do
-SRGAN_DBG_NO_SKIP_FUSE=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/NOFUSE /'
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/FUSE /'
-done
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_r1s_8gpu.log 2>&1; echo rc=$?; grep -E '^\{' gpurun_out/bench_r1s_8gpu.log | cut -c1-600; tail -3 gpurun_out/bench_r1s_8gpu.log | cut -c1-300

@@ -733,7 +733,11 @@ static bool plan_norm(int N, int HW, int C, NormP* out) {
   }
   p.TPR = p.q4 / nchunk;
   p.RPP = kNormThreads / p.TPR;
-  long long want = (8LL * kNumSMs + (long long)N * nchunk - 1) / ((long long)N * nchunk);
+  // One full wave: the streaming kernels keep 4 CTAs of 256 threads per SM (registers), and a grid of 2.05 waves -
+  // what "8 CTAs per SM worth of slices" produced at batch 64 - leaves the SMs idle for a quarter of the launch
+  // (ncu: sm__cycles_active 57 k of 77 k elapsed).  SRGAN_DBG_NORM_CTAS_PER_SM overrides the 4.
+  static const int per_sm = getenv("SRGAN_DBG_NORM_CTAS_PER_SM") ? atoi(getenv("SRGAN_DBG_NORM_CTAS_PER_SM")) : 4;
+  long long want = ((long long)per_sm * kNumSMs) / ((long long)N * nchunk);
   long long cap = ceil_div(HW, p.RPP * 4);   // at least 4 passes per CTA
   long long SL = want < cap ? want : cap;
   if (SL < 1) SL = 1;

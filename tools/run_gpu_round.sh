@@ -1,2 +1,5 @@
 set -x
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_r1s_8gpu.log 2>&1; echo rc=$?; grep -E '^\{' gpurun_out/bench_r1s_8gpu.log | cut -c1-600; tail -3 gpurun_out/bench_r1s_8gpu.log | cut -c1-300
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu23.log 2>&1; tail -2 gpurun_out/pytest_gpu23.log
+SRGAN_DBG_NORM_CTAS_PER_SM=8 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/C8 /'
+timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/C4 /'
+timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu --batch 32 2>&1 | tail -1 | cut -c1-140 | sed 's/^/C4b32 /'

@@ -180,11 +180,12 @@ def test_module_api_surface():
     assert all(p.requires_grad for p in E.parameters())
 
 
-def test_cuda_graph_replay_is_bit_identical_to_eager_steps():
+@pytest.mark.parametrize("name", ["srgan_small", "single_solo_small"])
+def test_cuda_graph_replay_is_bit_identical_to_eager_steps(name):
     """sg.enable_cuda_graph(): the captured step (k discriminator updates + both generator/encoder phases + Adam)
     replays the same kernels in the same order on the same host-drawn noise -> identical losses and identical
-    parameters after several steps, including a learning-rate change between steps."""
-    name = "srgan_small"
+    parameters after several steps, including a learning-rate change between steps (SRGAN and the notebook-02
+    SingleGAN trainer with the class-conditioned encoder)."""
     c = dict(cases.CASES[name], batch=4, k=2)
     model, util, nb = cases.use_product_modules()
     ops.set_conv_engine("auto")

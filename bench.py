@@ -307,6 +307,7 @@ def run_ours(args):
                 "peak_source": "cuBLAS TF32 8192^3 matmul measured in this run (MEASURED_PEAKS.json has no TF32 "
                                "entry; bf16 there: %.1f TF/s, %s)" % (pk["bf16"], pk["src"]),
                 "kernel_ms": kms, "step_gflop_per_image": GF_PER_IMG[args.workload],
+                "step_gflop_per_image_executed": GF_PER_IMG[args.workload] - 16.6,   # skipped encoder work
                 "step_tflops": value * GF_PER_IMG[args.workload] / 1e3}
         # secondary roofline: the fused instance-norm (+ conditional bias + affine + ReLU) forward of the residual
         # blocks, HBM bound; algorithmic bytes = read x + write y

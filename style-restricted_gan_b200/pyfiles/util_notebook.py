@@ -22,6 +22,8 @@ replica, works on its slice of the global batch, gradients are all-reduced (mean
 the latent batch statistics are computed on the ALL-GATHERED mu so batch-KL / correlation / histogram
 losses equal their single-GPU global-batch values bit for bit.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -40,6 +42,10 @@ def get_adjustable_parameters(notebook_no=1):
 
 
 # ------------------------------------------------------------------------------------------- data parallel
+_REENCODE = os.environ.get("SRGAN_DBG_REENCODE", "0") != "0"     # bring-up: second encoder pass of phase 1, like the reference
+_SPLIT_BACKWARD = os.environ.get("SRGAN_DBG_SPLIT_BACKWARD", "0") != "0"     # bring-up: the reference's two calls
+
+
 def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -244,7 +250,17 @@ class _UnrolledTrainer(object):
         # The restriction terms do not touch the RNG, so evaluating them in one fused launch here (after the
         # identity pass) is equivalent to the reference's interleaving; they are ADDED in the reference's order.
         if lbd["idt"] > 0:
-            identity_image, _ = self.G_transformation(lab["source"], src, True, src)
+            if _REENCODE:
+                identity_image, _ = self.G_transformation(lab["source"], src, True, src)
+            else:
+                # The reference encodes the source batch a second time here (pyfiles/util_notebook.py:637-641).  The
+                # encoder is deterministic and its weights have not changed since `enc_info` was computed a few lines
+                # up, so mu / logvar would come out bit-identical: reuse them and only draw the fresh reparametrisation
+                # noise (same CPU-RNG consumption).  Both uses then back-propagate through ONE encoder graph - one
+                # encoder forward and one backward traversal less per step, same gradients up to fp32 summation order.
+                z2 = self._nE.reparametrize(enc_info[1], enc_info[2])
+                info2 = _EncodedStyle([z2] + list(enc_info[1:]))
+                identity_image = self._generate(lab["source"], src, self._style_of(info2))
             idt = ops.l1_mean(src, identity_image)
             errG = errG + idt * lbd["idt"]
         terms = self._latent_restriction(enc_info)
@@ -263,9 +279,17 @@ class _UnrolledTrainer(object):
         # gradients must be summed over ranks while _sync_grads averages -> pre-scale by the world size.
         restrict_bp = errE * world if (world > 1 and torch.is_tensor(errE)) else errE
 
-        errG.backward(retain_graph=True)
-        if torch.is_tensor(restrict_bp):
-            restrict_bp.backward(retain_graph=True)
+        # The reference calls errG.backward(retain_graph=True) and then errE.backward(retain_graph=True)
+        # (pyfiles/util_notebook.py:664-665): the second call walks the encoder graph of the source batch again.
+        # Gradients are linear in the loss, so ONE backward of the sum leaves the same G / E / D gradients (up to
+        # fp32 summation order) and saves an encoder backward traversal per step.
+        if _SPLIT_BACKWARD:
+            errG.backward(retain_graph=True)
+            if torch.is_tensor(restrict_bp):
+                restrict_bp.backward(retain_graph=True)
+        else:
+            total = errG + restrict_bp if torch.is_tensor(restrict_bp) else errG
+            total.backward(retain_graph=True)
         _sync_grads(self._nG, self.optG)
         _sync_grads(self._nE, self.optE)
         self.optG.step()

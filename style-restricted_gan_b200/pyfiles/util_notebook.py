@@ -42,6 +42,7 @@ def get_adjustable_parameters(notebook_no=1):
 
 
 # ------------------------------------------------------------------------------------------- data parallel
+_SPLIT_D = os.environ.get("SRGAN_DBG_SPLIT_D", "0") != "0"           # bring-up: D(real) and D(fake) as two passes, like the reference
 _REENCODE = os.environ.get("SRGAN_DBG_REENCODE", "0") != "0"     # bring-up: second encoder pass of phase 1, like the reference
 _SPLIT_BACKWARD = os.environ.get("SRGAN_DBG_SPLIT_BACKWARD", "0") != "0"     # bring-up: the reference's two calls
 
@@ -233,6 +234,26 @@ class _UnrolledTrainer(object):
         return terms
 
     # ---- the step --------------------------------------------------------------------------------------
+    def _solo_D_loss(self, fake):
+        """LSGAN + class loss of the single (solo-multi) discriminator on the real batch and on `fake`
+        (ref pyfiles/util_notebook.py:582-589).  The discriminator has no batch-coupled layer (convolutions, LeakyReLU,
+        average pooling), so D(real) and D(fake) are evaluated as ONE pass over the concatenated batch: every
+        output is bit-identical to the two separate passes, the weight gradients differ only in summation order, and
+        the many small layers of D run at twice the batch (fewer, better filled launches)."""
+        src = self.source_image
+        if _SPLIT_D:
+            output, output_class = self._nD(src)
+            out_fake, _ = self._nD(fake)
+        else:
+            B = src.shape[0]
+            out_all, cls_all = self._nD(torch.cat([src, ops.to_nhwc(fake)], 0))
+            output, output_class = [o[:B] for o in out_all], [c[:B] for c in cls_all]
+            out_fake = [o[B:].clone() for o in out_all]      # fresh storage: the loss kernels need 16-byte alignment
+        errD = get_loss_D(output, 1., self.criterion, self.device) + \
+            get_domainloss_D(output_class, self._onehot(self.label["source"]), self.criterion_class) \
+            * self.lbd["class"]
+        return errD + get_loss_D(out_fake, 0., self.criterion, self.device)
+
     def update_GandE(self):
         """Phase 1: one step of G and E on the SingleGAN losses; phase 2: one more step of G alone on the
         latent-regression losses.  Returns [errG, errE_output]."""
@@ -452,12 +473,7 @@ class SingleGAN_training(_UnrolledTrainer):
         fake = self.target_image.detach()
         if self.singleD:
             _zero_grads(self._nD, self.optD)
-            output, output_class = self._nD(self.source_image)
-            errD = get_loss_D(output, 1., self.criterion, self.device) + \
-                get_domainloss_D(output_class, self._onehot(self.label["source"]), self.criterion_class) \
-                * self.lbd["class"]
-            output, _ = self._nD(fake)
-            errD = errD + get_loss_D(output, 0., self.criterion, self.device)
+            errD = self._solo_D_loss(fake)
             errD.backward()
             _sync_grads(self._nD, self.optD)
             self.optD.step()
@@ -528,12 +544,7 @@ class SRGAN_training(_UnrolledTrainer):
         _zero_grads(self._nD, self.optD)
         with torch.set_grad_enabled(keep_graph):
             self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
-        output, output_class = self._nD(self.source_image)
-        errD = get_loss_D(output, 1., self.criterion, self.device) + \
-            get_domainloss_D(output_class, self._onehot(self.label["source"]), self.criterion_class) \
-            * self.lbd["class"]
-        output, _ = self._nD(self.target_image.detach())
-        errD = errD + get_loss_D(output, 0., self.criterion, self.device)
+        errD = self._solo_D_loss(self.target_image.detach())
         errD.backward()
         _sync_grads(self._nD, self.optD)
         self.optD.step()

@@ -1,7 +1,7 @@
 set -x
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu26.log 2>&1; tail -3 gpurun_out/pytest_gpu26.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu27.log 2>&1; tail -3 gpurun_out/pytest_gpu27.log
 timeout 300 python -m pytest tests/test_step_gpu.py -x -q -m gpu -s -k "fp32_engine" 2>&1 | grep -E "losses" | cut -c1-250
 for i in 1 2; do
-SRGAN_DBG_REENCODE=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/TWICE /'
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/ONCE /'
+SRGAN_DBG_SPLIT_D=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/SPLITD /'
+timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu 2>&1 | tail -1 | cut -c1-140 | sed 's/^/CATD /'
 done

@@ -1,7 +1,2 @@
 set -x
-timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke_r1w.log 2>&1; tail -1 gpurun_out/smoke_r1w.log | cut -c1-200
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu29.log 2>&1; tail -2 gpurun_out/pytest_gpu29.log
-timeout 600 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_r1w.log 2>&1; tail -1 gpurun_out/bench_r1w.log | cut -c1-200
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_r1w.csv python tools/profile_step.py --batch 64 > gpurun_out/ncu_step_r1w.log 2>&1; tail -1 gpurun_out/ncu_step_r1w.log
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu --batch 32 > gpurun_out/bench_r1w_b32.log 2>&1; tail -1 gpurun_out/bench_r1w_b32.log | cut -c1-160
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu --batch 8 > gpurun_out/bench_r1w_b8.log 2>&1; tail -1 gpurun_out/bench_r1w_b8.log | cut -c1-160
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 8 --steps 8 --warmup 3 > gpurun_out/bench_r1w_8gpu.log 2>&1; echo rc=$?; grep -E '^\{' gpurun_out/bench_r1w_8gpu.log | cut -c1-300

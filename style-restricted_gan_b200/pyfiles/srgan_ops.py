@@ -309,10 +309,45 @@ def _dgrad(d, dy, w, like, addend=None):
     return dx
 
 
-def _wgrad(d, x, dy, want_w, want_b):
-    dw = torch.empty((d.K, d.C, d.R, d.S), dtype=torch.float32, device=x.device, memory_format=CL) \
-        if want_w else None
-    db = torch.empty((d.K,), dtype=torch.float32, device=x.device) if want_b else None
+_direct_grads = False
+_NO_DIRECT_GRADS = os.environ.get("SRGAN_DBG_NO_DIRECT_GRADS", "0") != "0"      # bring-up: autograd accumulates every gradient
+
+
+class direct_param_grads(object):
+    """with direct_param_grads(): backward kernels write the FIRST gradient contribution of a parameter straight into
+    the optimizer's flat gradient buffer (FusedAdam.zero_grad() marks the buffer views as fresh) and hand autograd
+    None for it - no per-parameter accumulation kernel.  Later contributions accumulate as usual.  Only for
+    backward() calls that follow a FusedAdam.zero_grad() and accumulate into .grad (the trainers); never around
+    torch.autograd.grad()."""
+
+    def __enter__(self):
+        global _direct_grads
+        self.prev, _direct_grads = _direct_grads, not _NO_DIRECT_GRADS
+
+    def __exit__(self, *exc):
+        global _direct_grads
+        _direct_grads = self.prev
+
+
+def _grad_sink(p, wanted, channels_last=False):
+    """The flat-buffer view to write this parameter's gradient into, or None."""
+    if not (wanted and _direct_grads) or p is None or not getattr(p, "_srgan_fresh", False):
+        return None
+    g = p.grad
+    if g is None or g.shape != p.shape:
+        return None
+    if not (g.is_contiguous(memory_format=CL) if (channels_last and g.dim() == 4) else g.is_contiguous()):
+        return None
+    p._srgan_fresh = False
+    return g
+
+
+def _wgrad(d, x, dy, want_w, want_b, dw_out=None, db_out=None):
+    """dw_out / db_out: write the gradients there (dense KRSC / [K]) instead of into fresh tensors."""
+    dw = dw_out if dw_out is not None else (
+        torch.empty((d.K, d.C, d.R, d.S), dtype=torch.float32, device=x.device, memory_format=CL) if want_w else None)
+    db = db_out if db_out is not None else (
+        torch.empty((d.K,), dtype=torch.float32, device=x.device) if want_b else None)
     if d.N == 0:
         if dw is not None:
             dw.zero_()
@@ -347,7 +382,7 @@ class _Conv2dFn(torch.autograd.Function):
         d = _desc(N, H, W, C, K, R, S, stride, pad)
         y = _fprop(d, x, _krsc(weight), bias, act, slope)
         ctx.d, ctx.act, ctx.slope = d, act, slope
-        ctx.weight, ctx.has_bias = weight, bias is not None
+        ctx.weight, ctx.bias, ctx.has_bias = weight, bias, bias is not None
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
         return y
 
@@ -361,7 +396,10 @@ class _Conv2dFn(torch.autograd.Function):
         want_w = ctx.needs_input_grad[1]
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_w or want_b:
-            dw, db = _wgrad(ctx.d, x, dz, want_w, want_b)
+            sink_w, sink_b = _grad_sink(ctx.weight, want_w, True), _grad_sink(ctx.bias, want_b)
+            dw, db = _wgrad(ctx.d, x, dz, want_w, want_b, sink_w, sink_b)
+            dw = None if sink_w is not None else dw
+            db = None if sink_b is not None else db
         return dx, dw, db, None, None, None, None
 
 
@@ -391,7 +429,9 @@ class _Conv2dSkipFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _dgrad(ctx.d, dz, _krsc(ctx.weight), x, addend=dskip)      # live weight (see module docstring)
         if ctx.needs_input_grad[1]:
-            dw, _ = _wgrad(ctx.d, x, dz, True, False)
+            sink = _grad_sink(ctx.weight, True, True)
+            dw, _ = _wgrad(ctx.d, x, dz, True, False, sink)
+            dw = None if sink is not None else dw
         return dx, dw, None, None
 
 
@@ -423,7 +463,9 @@ class _ConvTranspose2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _fprop(ctx.d, dy, _krsc(ctx.weight), None, ACT_NONE, 0.0)
         if ctx.needs_input_grad[1]:
-            dw, _ = _wgrad(ctx.d, dy, x, True, False)
+            sink = _grad_sink(ctx.weight, True, True)
+            dw, _ = _wgrad(ctx.d, dy, x, True, False, sink)
+            dw = None if sink is not None else dw
         return dx, dw, None, None
 
 
@@ -482,7 +524,7 @@ class _LinearFn(torch.autograd.Function):
         J = weight.shape[0]
         d = _desc(N, 1, 1, F, J, 1, 1, 1, 0)
         y = _fprop(d, x, weight.contiguous(), bias, ACT_NONE, 0.0).view(N, J)
-        ctx.d, ctx.weight, ctx.has_bias = d, weight, bias is not None
+        ctx.d, ctx.weight, ctx.bias, ctx.has_bias = d, weight, bias, bias is not None
         ctx.save_for_backward(x)
         return y
 
@@ -497,9 +539,10 @@ class _LinearFn(torch.autograd.Function):
         want_w = ctx.needs_input_grad[1]
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_w or want_b:
-            dw, db = _wgrad(d, x, dy, want_w, want_b)
-            if dw is not None:
-                dw = dw.view(d.K, d.C)
+            sink_w, sink_b = _grad_sink(ctx.weight, want_w), _grad_sink(ctx.bias, want_b)
+            dw, db = _wgrad(d, x, dy, want_w, want_b, sink_w, sink_b)
+            dw = None if (sink_w is not None or dw is None) else dw.view(d.K, d.C)
+            db = None if sink_b is not None else db
         return dx, dw, db
 
 
@@ -520,7 +563,7 @@ class _CondBiasFn(torch.autograd.Function):
         t = torch.empty((N, C), dtype=torch.float32, device=con.device)
         if N:
             _call("srgan_condbias_fwd", _p(con), _p(weight), _p(bias), _p(t), N, J, C, _stream())
-        ctx.weight = weight
+        ctx.weight, ctx.bias = weight, bias
         ctx.save_for_backward(con, t)
         return t
 
@@ -531,11 +574,13 @@ class _CondBiasFn(torch.autograd.Function):
         N, J = con.shape
         C = w.shape[0]
         dt = dt.contiguous()
-        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
-        db = torch.empty((C,), dtype=torch.float32, device=w.device) if ctx.needs_input_grad[2] else None
+        sink_w, sink_b = _grad_sink(w, ctx.needs_input_grad[1]), _grad_sink(ctx.bias, ctx.needs_input_grad[2])
+        dw = sink_w if sink_w is not None else (torch.empty_like(w) if ctx.needs_input_grad[1] else None)
+        db = sink_b if sink_b is not None else (
+            torch.empty((C,), dtype=torch.float32, device=w.device) if ctx.needs_input_grad[2] else None)
         dcon = torch.empty_like(con) if ctx.needs_input_grad[0] else None
         _call("srgan_condbias_bwd", _p(dt), _p(t), _p(con), _p(w), _p(dw), _p(db), _p(dcon), N, J, C, _stream())
-        return dcon, dw, db
+        return dcon, (None if sink_w is not None else dw), (None if sink_b is not None else db)
 
 
 def cond_bias(con, weight, bias):
@@ -590,11 +635,14 @@ class _InstanceNormFn(torch.autograd.Function):
         need_b = beta is not None and ctx.needs_input_grad[2]
         need_c = cbias is not None and ctx.needs_input_grad[3]
         if need_g or need_b or need_c:
-            dgamma = torch.empty_like(gamma) if need_g else None
-            dbeta = torch.empty_like(beta) if need_b else None
+            sink_g, sink_b = _grad_sink(gamma, need_g), _grad_sink(beta, need_b)
+            dgamma = sink_g if sink_g is not None else (torch.empty_like(gamma) if need_g else None)
+            dbeta = sink_b if sink_b is not None else (torch.empty_like(beta) if need_b else None)
             dcb = torch.empty_like(cbias) if need_c else None
             _call("srgan_inorm_param_grads", _p(s1), _p(s2), _p(gamma), _p(cbias), _p(dgamma), _p(dbeta), _p(dcb),
                   N, C, _stream())
+            dgamma = None if sink_g is not None else dgamma
+            dbeta = None if sink_b is not None else dbeta
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
         return (dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, dcb, dres, None, None, None
 
@@ -694,11 +742,14 @@ class _BatchNormFn(torch.autograd.Function):
         need_b = beta is not None and ctx.needs_input_grad[2]
         need_c = cbias is not None and ctx.needs_input_grad[3]
         if need_g or need_b or need_c:
-            dgamma = torch.empty_like(gamma) if need_g else None
-            dbeta = torch.empty_like(beta) if need_b else None
+            sink_g, sink_b = _grad_sink(gamma, need_g), _grad_sink(beta, need_b)
+            dgamma = sink_g if sink_g is not None else (torch.empty_like(gamma) if need_g else None)
+            dbeta = sink_b if sink_b is not None else (torch.empty_like(beta) if need_b else None)
             dcb = torch.empty_like(cbias) if need_c else None
             _call("srgan_inorm_param_grads", _p(s1), _p(s2), _p(gamma), _p(cbias), _p(dgamma), _p(dbeta), _p(dcb),
                   N, C, _stream())
+            dgamma = None if sink_g is not None else dgamma
+            dbeta = None if sink_b is not None else dbeta
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
         return ((dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, dcb, dres) + (None,) * 9
 
@@ -1203,6 +1254,7 @@ class FusedAdam(torch.optim.Optimizer):
             st["g"].zero_()
             for p, view in st["views"]:
                 p.grad = view(st["g"])
+                p._srgan_fresh = True          # see direct_param_grads
 
     @torch.no_grad()
     def step(self, closure=None):

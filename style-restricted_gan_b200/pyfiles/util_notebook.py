@@ -310,7 +310,8 @@ class _UnrolledTrainer(object):
                 restrict_bp.backward(retain_graph=True)
         else:
             total = errG + restrict_bp if torch.is_tensor(restrict_bp) else errG
-            total.backward(retain_graph=True)
+            with ops.direct_param_grads():
+                total.backward(retain_graph=True)
         _sync_grads(self._nG, self.optG)
         _sync_grads(self._nE, self.optE)
         self.optG.step()
@@ -326,7 +327,8 @@ class _UnrolledTrainer(object):
         errG_ex = ops.l1_mean(self.c_rand, target_mu) * lbd["reg"]
         if lbd["idt_reg"] * lbd["idt"] > 0:
             errG_ex = errG_ex + self._identity_regression() * lbd["idt_reg"] * (lbd["idt"] / lbd["cycle"])
-        errG_ex.backward()
+        with ops.direct_param_grads():
+            errG_ex.backward()
         _sync_grads(self._nG, self.optG)
         self.optG.step()
         return [errG + errG_ex, errE_output]
@@ -474,7 +476,8 @@ class SingleGAN_training(_UnrolledTrainer):
         if self.singleD:
             _zero_grads(self._nD, self.optD)
             errD = self._solo_D_loss(fake)
-            errD.backward()
+            with ops.direct_param_grads():
+                errD.backward()
             _sync_grads(self._nD, self.optD)
             self.optD.step()
             return errD
@@ -489,7 +492,8 @@ class SingleGAN_training(_UnrolledTrainer):
             if sub.shape[0] != 0:
                 errD = errD + get_loss_D(self._nD[i](sub), 0., self.criterion, self.device)
             if torch.is_tensor(errD):
-                errD.backward()
+                with ops.direct_param_grads():
+                    errD.backward()
             self.optD[i].step()
         return errD
 
@@ -545,7 +549,8 @@ class SRGAN_training(_UnrolledTrainer):
         with torch.set_grad_enabled(keep_graph):
             self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
         errD = self._solo_D_loss(self.target_image.detach())
-        errD.backward()
+        with ops.direct_param_grads():
+            errD.backward()
         _sync_grads(self._nD, self.optD)
         self.optD.step()
         return errD

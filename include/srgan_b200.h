@@ -86,6 +86,8 @@ int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, const float* dy
 int srgan_conv2d_dgrad_add_supported(const srgan_conv_desc* d, int engine);
 int srgan_conv2d_dgrad_add(const srgan_conv_desc* d, const float* dy, const float* w, const float* addend,
                            float* dx, int engine, void* workspace, size_t workspace_bytes, void* stream);
+/* introspection (tests, tools): pixel splits and CTAs of the tcgen05 wgrad launch for this layer (host only) */
+int srgan_conv2d_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
 /* which engine AUTO resolves to for this shape/pass: SRGAN_CONV_FP32 or SRGAN_CONV_TF32 */
 int srgan_conv2d_engine(const srgan_conv_desc* d, int pass);
 

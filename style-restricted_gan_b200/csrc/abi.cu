@@ -34,6 +34,7 @@ int conv_fprop_umma_launch(const srgan_conv_desc*, const float*, const float*, c
 int conv_dgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, void*, size_t,
                            cudaStream_t, const float* addend);
 bool conv_dgrad_umma_add_supported(const srgan_conv_desc* d);
+void conv_umma_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
 int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
                            cudaStream_t);
 
@@ -132,6 +133,13 @@ extern "C" int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, cons
   if (e == SRGAN_CONV_TF32)
     return conv_wgrad_umma_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
   return conv_wgrad_ffma_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srgan_conv2d_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(splits && ctas, "null pointer");
+  conv_umma_wgrad_plan(d, splits, ctas);
+  return SRGAN_OK;
 }
 
 extern "C" int srgan_colsum(const float* x, float* out, size_t rows, int C, void* stream) {

@@ -934,6 +934,13 @@ static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
   return w;
 }
 
+// introspection for tests / tools: how the wgrad of this layer is decomposed
+void conv_umma_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas) {
+  const WgradPlan w = plan_wgrad(d);
+  *splits = w.splits;
+  *ctas = w.tiles_k * w.tiles_c * w.ngroups * w.splits;
+}
+
 static size_t thin_workspace(const srgan_conv_desc* d, int pass, const ThinPlan& t);
 
 size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {

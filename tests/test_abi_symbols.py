@@ -58,3 +58,26 @@ def test_product_ops_refuse_cpu_tensors():
         srgan_ops.instance_norm_act(x)
     with pytest.raises(_srgan_lib.SrganKernelError):
         srgan_ops.l1_mean(x, x)
+
+
+def test_wgrad_split_plan_fills_whole_waves():
+    """The tcgen05 wgrad launches one CTA per SM and round: the split count must not spill a handful of CTAs into an
+    extra round (the first heuristic gave the residual blocks 9 taps x 33 splits = 297 CTAs = 2 rounds + 1 CTA).
+    Host-side planning only: runs without a GPU."""
+    import ctypes
+    lib = _srgan_lib.load()
+    SM = 148
+
+    def plan(N, H, W, C, K, R, stride, pad):
+        P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+        d = _srgan_lib.ConvDesc(N, H, W, C, K, R, R, P, Q, stride, pad, 0, 0, 0, 0)
+        s, c = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.srgan_conv2d_wgrad_plan(ctypes.byref(d), ctypes.addressof(s), ctypes.addressof(c)) == 0
+        return s.value, c.value
+    splits, ctas = plan(64, 32, 32, 256, 256, 3, 1, 1)          # residual block at batch 64
+    assert ctas <= SM and ctas >= 0.9 * SM, (splits, ctas)
+    for shape in ((64, 64, 64, 128, 256, 4, 2, 1), (64, 16, 16, 256, 512, 4, 2, 1), (64, 17, 17, 256, 512, 3, 1, 0),
+                  (8, 32, 32, 256, 256, 3, 1, 1), (256, 32, 32, 256, 256, 3, 1, 1)):
+        splits, ctas = plan(*shape)
+        rounds = -(-ctas // SM)
+        assert splits >= 1 and ctas > (rounds - 1) * SM + 0.5 * SM or rounds == 1, (shape, splits, ctas)

@@ -111,6 +111,9 @@ int srgan_reflect_pad_bwd(const float* dy, float* dx, int N, int H, int W, int C
  * order, overwritten) and dcbias[n][c].
  */
 size_t srgan_inorm_workspace(int N, int HW, int C);   /* bytes of slice-partial scratch for fwd and bwd */
+/* 1 when the slice partials are accumulated in fp64 over fixed 4-row atoms: the statistics of an image are then
+ * independent of N (of how the grid planner slices the plane), which data-parallel reproducibility relies on. */
+int srgan_norm_partials_fp64(void);
 int srgan_inorm_fwd(const float* x, float* y, float* mean, float* rstd,
                     const float* gamma, const float* beta, const float* cbias, const float* residual,
                     int N, int HW, int C, float eps, int act, float slope,

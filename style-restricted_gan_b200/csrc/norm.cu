@@ -21,6 +21,7 @@ namespace srgan {
 
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxSlices = 64;
+constexpr bool kNormF64Default = true;
 
 struct NormP {
   int N, HW, C;
@@ -49,39 +50,87 @@ __device__ __forceinline__ NormIdx norm_idx(const NormP& p) {
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
 __device__ __forceinline__ void acc4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
+// Partial sums in double (the default): each thread sums an ATOM - its 4 (forward) or 2 (backward) rows of one
+// aligned group of 4 * RPP pixel rows - in fp32, in an order fixed by the row index alone, and everything above the
+// atom (the thread's running sum, the CTA's row reduction, the slice partials, their fold) is added in fp64.  Slices
+// start on atom boundaries, so the statistics do not depend on how many slices an image is cut into - i.e. on how
+// many images the rank holds (plan_norm sizes the grid to one wave) - up to a 2^-53 reassociation error that survives
+// the final rounding to fp32 about once in 10^9 values.  That is what makes an N-rank data-parallel step reproduce
+// the 1-GPU step on the same global batch (tools/dp_check.py); with fp32 partials the summation order leaks into the
+// statistics and TF32 operand truncation downstream amplifies it to 3e-5 on the losses.
+struct alignas(16) D4 { double x, y, z, w; };
+__device__ __forceinline__ void acc4(D4& a, const D4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void acc4(D4& a, const float4& b) {
+  a.x += (double)b.x; a.y += (double)b.y; a.z += (double)b.z; a.w += (double)b.w;
+}
+template <typename V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ float4 vzero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ D4 vzero<D4>() { return D4{0., 0., 0., 0.}; }
+__device__ __forceinline__ float4 to_f4(const float4& v) { return v; }
+__device__ __forceinline__ float4 to_f4(const D4& v) { return make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w); }
+template <typename V> __device__ __forceinline__ V ld_part(const V* q) { return *q; }
+template <> __device__ __forceinline__ float4 ld_part<float4>(const float4* q) { return __ldg(q); }
+
 // Sum (a, b) over the pixel rows of the CTA in a fixed order; threads with row == 0 get the result.
-__device__ __forceinline__ void rows_reduce(const NormP& p, const NormIdx& i, float4& a, float4& b, float4* sa,
-                                            float4* sb) {
+template <typename V>
+__device__ __forceinline__ void rows_reduce(const NormP& p, const NormIdx& i, V& a, V& b, V* sa, V* sb) {
   sa[threadIdx.x] = a;
   sb[threadIdx.x] = b;
   __syncthreads();
   if (i.row == 0) {
-    float4 ra = f4(0.f), rb = f4(0.f);
+    V ra = vzero<V>(), rb = vzero<V>();
     for (int r = 0; r < p.RPP; ++r) { acc4(ra, sa[r * p.TPR + i.cg]); acc4(rb, sb[r * p.TPR + i.cg]); }
     a = ra; b = rb;
   }
 }
 
-// partial layout: part[(n * SL + slice) * q4 + c4], two planes (first, second moment) of N*SL*q4 float4 each
-__global__ void __launch_bounds__(kNormThreads) inorm_stats_kernel(NormP p, const float* __restrict__ x,
-                                                                   float4* __restrict__ part) {
-  __shared__ float4 sa[kNormThreads], sb[kNormThreads];
+// Fold the SL slice partials of (image n, float4 column c4) in slice order.
+template <typename V>
+__device__ __forceinline__ void fold_parts(const NormP& p, const V* __restrict__ part, int n, int c4, float4& s1,
+                                           float4& s2) {
+  V t1 = vzero<V>(), t2 = vzero<V>();
+  const V* p1 = part + (size_t)n * p.SL * p.q4 + c4;
+  const V* p2 = p1 + (size_t)p.N * p.SL * p.q4;
+  for (int s = 0; s < p.SL; ++s) { acc4(t1, ld_part(p1 + (size_t)s * p.q4)); acc4(t2, ld_part(p2 + (size_t)s * p.q4)); }
+  s1 = to_f4(t1); s2 = to_f4(t2);
+}
+
+// partial layout: part[(n * SL + slice) * q4 + c4], two planes (first, second moment) of N*SL*q4 V each
+template <typename V>
+__global__ void __launch_bounds__(kNormThreads, 4) inorm_stats_kernel(NormP p, const float* __restrict__ x,
+                                                                   V* __restrict__ part) {
+  __shared__ V sa[kNormThreads], sb[kNormThreads];
   const NormIdx i = norm_idx(p);
   const int n = blockIdx.y;
   const float4* xg = reinterpret_cast<const float4*>(x) + (size_t)n * p.HW * p.q4 + i.c4;
-  float4 s1 = f4(0.f), s2 = f4(0.f);
+  V s1 = vzero<V>(), s2 = vzero<V>();
   if (i.active) {
     const float4 pv = __ldg(xg);                       // pivot: first pixel of the plane
     const int step = p.RPP;
     int r = i.px0 + i.row;
-    for (; r + 3 * step < i.px1; r += 4 * step) {
-      float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
-      float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
-#define SRGAN_ACC(v) { float a = v.x - pv.x, b = v.y - pv.y, c = v.z - pv.z, d = v.w - pv.w; \
-                       s1.x += a; s1.y += b; s1.z += c; s1.w += d; s2.x += a * a; s2.y += b * b; s2.z += c * c; s2.w += d * d; }
-      SRGAN_ACC(v0) SRGAN_ACC(v1) SRGAN_ACC(v2) SRGAN_ACC(v3)
+#define SRGAN_ACC(v, t1, t2) { float a = v.x - pv.x, b = v.y - pv.y, c = v.z - pv.z, d = v.w - pv.w; \
+                       t1.x += a; t1.y += b; t1.z += c; t1.w += d; t2.x += a * a; t2.y += b * b; t2.z += c * c; t2.w += d * d; }
+    if constexpr (sizeof(V) == sizeof(float4)) {
+      for (; r + 3 * step < i.px1; r += 4 * step) {
+        float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
+        float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+        SRGAN_ACC(v0, s1, s2) SRGAN_ACC(v1, s1, s2) SRGAN_ACC(v2, s1, s2) SRGAN_ACC(v3, s1, s2)
+      }
+      for (; r < i.px1; r += step) { float4 v0 = __ldg(xg + (size_t)r * p.q4); SRGAN_ACC(v0, s1, s2) }
+    } else {
+      for (; r + 3 * step < i.px1; r += 4 * step) {      // one atom per iteration
+        float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
+        float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+        float4 a1 = f4(0.f), a2 = f4(0.f);
+        SRGAN_ACC(v0, a1, a2) SRGAN_ACC(v1, a1, a2) SRGAN_ACC(v2, a1, a2) SRGAN_ACC(v3, a1, a2)
+        acc4(s1, a1); acc4(s2, a2);
+      }
+      if (r < i.px1) {                                   // the image's last, incomplete atom
+        float4 a1 = f4(0.f), a2 = f4(0.f);
+        for (; r < i.px1; r += step) { float4 v0 = __ldg(xg + (size_t)r * p.q4); SRGAN_ACC(v0, a1, a2) }
+        acc4(s1, a1); acc4(s2, a2);
+      }
     }
-    for (; r < i.px1; r += step) { float4 v0 = __ldg(xg + (size_t)r * p.q4); SRGAN_ACC(v0) }
 #undef SRGAN_ACC
   }
   rows_reduce(p, i, s1, s2, sa, sb);
@@ -92,8 +141,9 @@ __global__ void __launch_bounds__(kNormThreads) inorm_stats_kernel(NormP p, cons
   }
 }
 
-__global__ void __launch_bounds__(kNormThreads) inorm_apply_kernel(
-    NormP p, const float* __restrict__ x, const float4* __restrict__ part, float* __restrict__ y,
+template <typename V>
+__global__ void __launch_bounds__(kNormThreads, 4) inorm_apply_kernel(
+    NormP p, const float* __restrict__ x, const V* __restrict__ part, float* __restrict__ y,
     float* mean_out, float* rstd_out, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ cbias, const float* __restrict__ residual) {
   const NormIdx i = norm_idx(p);
@@ -107,10 +157,8 @@ __global__ void __launch_bounds__(kNormThreads) inorm_apply_kernel(
     mu = __ldg(reinterpret_cast<const float4*>(mean_out + (size_t)n * p.C + c));
     rs = __ldg(reinterpret_cast<const float4*>(rstd_out + (size_t)n * p.C + c));
   } else {
-    float4 s1 = f4(0.f), s2 = f4(0.f);
-    const float4* p1 = part + (size_t)n * p.SL * p.q4 + i.c4;
-    const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
-    for (int s = 0; s < p.SL; ++s) { acc4(s1, __ldg(p1 + (size_t)s * p.q4)); acc4(s2, __ldg(p2 + (size_t)s * p.q4)); }
+    float4 s1, s2;
+    fold_parts(p, part, n, i.c4, s1, s2);
     const float4 pv = __ldg(xg);
     const float inv = 1.f / (float)p.HW;
 #define SRGAN_STAT(f) { float m = s1.f * inv; float var = fmaxf(s2.f * inv - m * m, 0.f); mu.f = pv.f + m; rs.f = rsqrtf(var + p.eps); }
@@ -173,33 +221,49 @@ __device__ __forceinline__ void norm_dv_xh(const NormP& p, const NormBwdConsts& 
   dv.w = dy.w * act_grad_pre((xh.w + k.tb.w) * k.g.w + k.b.w, p.act, p.slope);
 }
 
-__global__ void __launch_bounds__(kNormThreads) inorm_bwd_reduce_kernel(
+template <typename V>
+__global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_reduce_kernel(
     NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ cbias, float4* __restrict__ part) {
-  __shared__ float4 sa[kNormThreads], sb[kNormThreads];
+    const float* __restrict__ cbias, V* __restrict__ part) {
+  __shared__ V sa[kNormThreads], sb[kNormThreads];
   const NormIdx i = norm_idx(p);
   const int n = blockIdx.y;
-  float4 a1 = f4(0.f), a2 = f4(0.f);
+  V a1 = vzero<V>(), a2 = vzero<V>();
   if (i.active) {
     const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
     const float4* xg = reinterpret_cast<const float4*>(x) + plane;
     const float4* dg = reinterpret_cast<const float4*>(dy) + plane;
     const NormBwdConsts k = norm_bwd_consts(p, n, i.c4 * 4, mean, rstd, gamma, beta, cbias);
-    auto one = [&](float4 xv, float4 dv_in) {
+    auto one = [&](float4 xv, float4 dv_in, auto& t1, auto& t2) {
       float4 xh, dv;
       norm_dv_xh(p, k, xv, dv_in, xh, dv);
-      acc4(a1, dv);
-      a2.x += dv.x * xh.x; a2.y += dv.y * xh.y; a2.z += dv.z * xh.z; a2.w += dv.w * xh.w;
+      t1.x += dv.x; t1.y += dv.y; t1.z += dv.z; t1.w += dv.w;
+      t2.x += dv.x * xh.x; t2.y += dv.y * xh.y; t2.z += dv.z * xh.z; t2.w += dv.w * xh.w;
     };
     const int step = p.RPP;
     int r = i.px0 + i.row;
-    for (; r + step < i.px1; r += 2 * step) {
-      float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
-      float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
-      one(x0, d0); one(x1, d1);
+    if constexpr (sizeof(V) == sizeof(float4)) {
+      for (; r + step < i.px1; r += 2 * step) {
+        float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
+        float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+        one(x0, d0, a1, a2); one(x1, d1, a1, a2);
+      }
+      for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4), a1, a2);
+    } else {
+      for (; r + step < i.px1; r += 2 * step) {          // one atom (2 rows of this thread) per iteration
+        float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
+        float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+        float4 b1 = f4(0.f), b2 = f4(0.f);
+        one(x0, d0, b1, b2); one(x1, d1, b1, b2);
+        acc4(a1, b1); acc4(a2, b2);
+      }
+      if (r < i.px1) {
+        float4 b1 = f4(0.f), b2 = f4(0.f);
+        one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4), b1, b2);
+        acc4(a1, b1); acc4(a2, b2);
+      }
     }
-    for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4));
   }
   rows_reduce(p, i, a1, a2, sa, sb);
   if (i.row == 0) {
@@ -209,10 +273,11 @@ __global__ void __launch_bounds__(kNormThreads) inorm_bwd_reduce_kernel(
   }
 }
 
-__global__ void __launch_bounds__(kNormThreads) inorm_bwd_apply_kernel(
+template <typename V>
+__global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_apply_kernel(
     NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ cbias, const float4* __restrict__ part, float* __restrict__ dx,
+    const float* __restrict__ cbias, const V* __restrict__ part, float* __restrict__ dx,
     float* s1_out, float* s2_out) {
   const NormIdx i = norm_idx(p);
   if (!i.active) return;
@@ -225,10 +290,8 @@ __global__ void __launch_bounds__(kNormThreads) inorm_bwd_apply_kernel(
     m1 = __ldg(reinterpret_cast<const float4*>(s1_out + (size_t)n * p.C + c));
     m2 = __ldg(reinterpret_cast<const float4*>(s2_out + (size_t)n * p.C + c));
   } else {
-    float4 S1 = f4(0.f), S2 = f4(0.f);
-    const float4* p1 = part + (size_t)n * p.SL * p.q4 + i.c4;
-    const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
-    for (int s = 0; s < p.SL; ++s) { acc4(S1, __ldg(p1 + (size_t)s * p.q4)); acc4(S2, __ldg(p2 + (size_t)s * p.q4)); }
+    float4 S1, S2;
+    fold_parts(p, part, n, i.c4, S1, S2);
     if (blockIdx.x == 0 && i.row == 0) {
       reinterpret_cast<float4*>(s1_out + (size_t)n * p.C + c)[0] = S1;
       reinterpret_cast<float4*>(s2_out + (size_t)n * p.C + c)[0] = S2;
@@ -626,14 +689,13 @@ __global__ void inorm_param_grads_kernel(const float* __restrict__ s1, const flo
 
 // slice partials -> per-(n,c) tables.  pivot != nullptr: a = instance mean, b = sum of squared deviations (partials
 // are sums about the first pixel of the plane); else a, b = plain sums of the two partial planes.
-__global__ void norm_fold_kernel(NormP p, const float4* __restrict__ part, const float* __restrict__ pivot_x,
+template <typename V>
+__global__ void norm_fold_kernel(NormP p, const V* __restrict__ part, const float* __restrict__ pivot_x,
                                  float* __restrict__ a_out, float* __restrict__ b_out) {
   const int c4 = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
   if (c4 >= p.q4) return;
-  float4 s1 = f4(0.f), s2 = f4(0.f);
-  const float4* p1 = part + (size_t)n * p.SL * p.q4 + c4;
-  const float4* p2 = p1 + (size_t)p.N * p.SL * p.q4;
-  for (int s = 0; s < p.SL; ++s) { acc4(s1, __ldg(p1 + (size_t)s * p.q4)); acc4(s2, __ldg(p2 + (size_t)s * p.q4)); }
+  float4 s1, s2;
+  fold_parts(p, part, n, c4, s1, s2);
   if (pivot_x) {
     const float4 pv = __ldg(reinterpret_cast<const float4*>(pivot_x) + (size_t)n * p.HW * p.q4 + c4);
     const float inv = 1.f / (float)p.HW;
@@ -721,6 +783,14 @@ __global__ void bnorm_bwd_coeffs_kernel(const float* __restrict__ s1_all, const 
   }
 }
 
+// fp64 partial sums over fixed atoms (see D4 above).  SRGAN_DBG_NORM_F32_PARTIALS=1 restores fp32 partials, whose
+// value depends on the slice count.
+static bool norm_f64() {
+  static const bool on = kNormF64Default ? !(getenv("SRGAN_DBG_NORM_F32_PARTIALS") && atoi(getenv("SRGAN_DBG_NORM_F32_PARTIALS")) != 0)
+                                         : (getenv("SRGAN_NORM_F64_PARTIALS") && atoi(getenv("SRGAN_NORM_F64_PARTIALS")) != 0);
+  return on;
+}
+
 // channel chunking + pixel slicing; returns false when C cannot be mapped onto 256 threads
 static bool plan_norm(int N, int HW, int C, NormP* out) {
   NormP p = {};
@@ -743,12 +813,15 @@ static bool plan_norm(int N, int HW, int C, NormP* out) {
   if (SL < 1) SL = 1;
   if (SL > kNormMaxSlices) SL = kNormMaxSlices;
   p.slice = ceil_div(HW, (int)SL);
+  if (norm_f64()) p.slice = ceil_div(p.slice, 4 * p.RPP) * (4 * p.RPP);   // slices start on atom boundaries
   p.SL = ceil_div(HW, p.slice);
   *out = p;
   return true;
 }
 
-static size_t norm_ws_bytes(const NormP& p) { return (size_t)2 * p.N * p.SL * p.q4 * sizeof(float4); }
+static size_t norm_ws_bytes(const NormP& p) {
+  return (size_t)2 * p.N * p.SL * p.q4 * (norm_f64() ? sizeof(D4) : sizeof(float4));
+}
 // fused kernels: [2 ticket counters | arrivals | flags] (zeroed before every launch) in front of the partials
 static size_t fused_ctl_bytes(const NormP& p) {
   const size_t groups = (size_t)p.N * (p.q4 / p.TPR);
@@ -781,6 +854,8 @@ static dim3 norm_grid(const NormP& p) { return dim3(p.SL, p.N, p.q4 / p.TPR); }
 
 using namespace srgan;
 
+extern "C" int srgan_norm_partials_fp64(void) { return norm_f64() ? 1 : 0; }
+
 extern "C" size_t srgan_inorm_workspace(int N, int HW, int C) {
   NormP p;
   if (N <= 0 || HW <= 0 || C <= 0 || C % 4 || !plan_norm(N, HW, C, &p)) return 0;
@@ -810,9 +885,15 @@ extern "C" int srgan_inorm_fwd(const float* x, float* y, float* mean, float* rst
     SRGAN_RETURN_LAUNCH();
   }
   if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_fwd: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
-  inorm_stats_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (float4*)ws);
-  inorm_apply_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (const float4*)ws, y, mean, rstd, gamma, beta, cbias,
-                                                            residual);
+  if (norm_f64()) {
+    inorm_stats_kernel<D4><<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (D4*)ws);
+    inorm_apply_kernel<D4><<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (const D4*)ws, y, mean, rstd, gamma, beta,
+                                                                  cbias, residual);
+  } else {
+    inorm_stats_kernel<float4><<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (float4*)ws);
+    inorm_apply_kernel<float4><<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (const float4*)ws, y, mean, rstd, gamma,
+                                                                      beta, cbias, residual);
+  }
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -840,9 +921,16 @@ extern "C" int srgan_inorm_bwd(const float* dy, const float* x, const float* mea
     SRGAN_RETURN_LAUNCH();
   }
   if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_bwd: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
-  inorm_bwd_reduce_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias, (float4*)ws);
-  inorm_bwd_apply_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias,
-                                                                (const float4*)ws, dx, s1, s2);
+  if (norm_f64()) {
+    inorm_bwd_reduce_kernel<D4><<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias, (D4*)ws);
+    inorm_bwd_apply_kernel<D4><<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias,
+                                                                      (const D4*)ws, dx, s1, s2);
+  } else {
+    inorm_bwd_reduce_kernel<float4><<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias,
+                                                                           (float4*)ws);
+    inorm_bwd_apply_kernel<float4><<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias,
+                                                                          (const float4*)ws, dx, s1, s2);
+  }
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -873,8 +961,13 @@ extern "C" int srgan_bnorm_image_stats(const float* x, float* mean_nc, float* m2
   if (N == 0) return SRGAN_OK;
   if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("bnorm_image_stats: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  inorm_stats_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (float4*)ws);
-  norm_fold_kernel<<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const float4*)ws, x, mean_nc, m2_nc);
+  if (norm_f64()) {
+    inorm_stats_kernel<D4><<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (D4*)ws);
+    norm_fold_kernel<D4><<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const D4*)ws, x, mean_nc, m2_nc);
+  } else {
+    inorm_stats_kernel<float4><<<norm_grid(p), kNormThreads, 0, st>>>(p, x, (float4*)ws);
+    norm_fold_kernel<float4><<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const float4*)ws, x, mean_nc, m2_nc);
+  }
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -901,7 +994,7 @@ extern "C" int srgan_bnorm_apply(const float* x, float* y, const float* mean, co
   if (int e = bn_common_checks(__func__, N, HW, C, &p)) return e;
   if (N == 0) return SRGAN_OK;
   p.eps = 0.f; p.slope = slope; p.act = act; p.given = 1;
-  inorm_apply_kernel<<<norm_grid(p), kNormThreads, 0, (cudaStream_t)stream>>>(
+  inorm_apply_kernel<float4><<<norm_grid(p), kNormThreads, 0, (cudaStream_t)stream>>>(
       p, x, nullptr, y, const_cast<float*>(mean), const_cast<float*>(rstd), gamma, beta, cbias, residual);
   SRGAN_RETURN_LAUNCH();
 }
@@ -920,8 +1013,14 @@ extern "C" int srgan_bnorm_bwd_sums(const float* dy, const float* x, const float
   p.eps = 0.f; p.slope = slope; p.act = act;
   if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("bnorm_bwd_sums: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  inorm_bwd_reduce_kernel<<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias, (float4*)ws);
-  norm_fold_kernel<<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const float4*)ws, nullptr, s1, s2);
+  if (norm_f64()) {
+    inorm_bwd_reduce_kernel<D4><<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias, (D4*)ws);
+    norm_fold_kernel<D4><<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const D4*)ws, nullptr, s1, s2);
+  } else {
+    inorm_bwd_reduce_kernel<float4><<<norm_grid(p), kNormThreads, 0, st>>>(p, dy, x, mean, rstd, gamma, beta, cbias,
+                                                                           (float4*)ws);
+    norm_fold_kernel<float4><<<dim3(ceil_div(p.q4, 64), N), 64, 0, st>>>(p, (const float4*)ws, nullptr, s1, s2);
+  }
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -947,7 +1046,7 @@ extern "C" int srgan_bnorm_bwd_apply(const float* dy, const float* x, const floa
   if (int e = bn_common_checks(__func__, N, HW, C, &p)) return e;
   if (N == 0) return SRGAN_OK;
   p.eps = 0.f; p.slope = slope; p.act = act; p.given = 1;
-  inorm_bwd_apply_kernel<<<norm_grid(p), kNormThreads, 0, (cudaStream_t)stream>>>(
+  inorm_bwd_apply_kernel<float4><<<norm_grid(p), kNormThreads, 0, (cudaStream_t)stream>>>(
       p, dy, x, mean, rstd, gamma, beta, cbias, nullptr, dx, const_cast<float*>(m1), const_cast<float*>(m2));
   SRGAN_RETURN_LAUNCH();
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "srgan_reflect_pad_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "srgan_reflect_pad_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "srgan_inorm_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "srgan_norm_partials_fp64": (c_int, []),
     "srgan_inorm_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_float, P, c_size_t, P]),
     "srgan_inorm_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, c_size_t, P]),
     "srgan_bnorm_image_stats": (c_int, [P, P, P, c_int, c_int, c_int, P, c_size_t, P]),

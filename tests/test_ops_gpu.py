@@ -340,3 +340,46 @@ def test_fused_norm_path_in_a_subprocess():
                         "-k", "instance_norm"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+def test_instance_norm_batch_split_invariance():
+    """With fp64 partial sums over fixed atoms (norm.cu: D4) the statistics of an image do not depend on how many
+    spatial slices the grid planner cuts it into, i.e. on how many images share the launch: the output and the
+    input gradient of image 0 are bit-identical whether it is normalised alone, with 3 or with 15 others.  (That is
+    what lets an N-rank data-parallel step reproduce the 1-GPU step on the global batch, tools/dp_check.py.)  The
+    switch is read once per process; skipped when the process runs with fp32 partials."""
+    import os
+    if not ops._lib().srgan_norm_partials_fp64() or os.environ.get("SRGAN_NORM_FUSED", "0") != "0":
+        pytest.skip("fp32 partials selected")
+    torch.manual_seed(11)
+    for (c, h, w) in ((64, 128, 128), (256, 32, 32), (128, 65, 63), (32, 37, 5)):
+        x = (torch.randn(16, c, h, w) * 2 + 3).to(DEV).contiguous(memory_format=CL)
+        dy = torch.randn(16, c, h, w).to(DEV).contiguous(memory_format=CL)
+        g = torch.randn(c).to(DEV)
+        b = torch.randn(c).to(DEV)
+        outs = []
+        for n in (16, 4, 1):
+            xs = x[:n].clone().contiguous(memory_format=CL).requires_grad_(True)
+            y = ops.instance_norm_act(xs, g, b, None, None, 1e-5, ops.ACT_LRELU, 0.2)
+            y.backward(dy[:n].clone().contiguous(memory_format=CL))
+            outs.append((y.detach()[:1].clone(), xs.grad[:1].clone()))
+        for y, dx in outs[1:]:
+            assert torch.equal(y, outs[0][0]), (c, h, w)
+            assert torch.equal(dx, outs[0][1]), (c, h, w)
+
+
+def test_norm_f64_partials_in_a_subprocess():
+    """Re-run the norm parity tests and the split-invariance test with SRGAN_NORM_F64_PARTIALS=1 (a no-op once that is
+    the library default)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SRGAN_NORM_F64_PARTIALS="1")
+    env.pop("SRGAN_DBG_NORM_F32_PARTIALS", None)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_ops_gpu.py"),
+                        os.path.join(here, "test_batchnorm_gpu.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "instance_norm or batchnorm or batch_norm or cbbn"], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]

@@ -23,11 +23,10 @@ def run(global_batch, width, k):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1 and 4 % world == 0 and os.environ.get("DP_CHECK_FREE_NORM_SLICES", "0") == "0":
-        # The instance-norm kernels cut each image into `4 * 148 / (images * channel chunks)` spatial slices, so a rank
-        # holding 1/world of the batch sums its statistics in a different order than the 1-GPU run (fp32 rounding;
-        # TF32 operand truncation downstream then turns some of it into 2^-11 steps).  Pin the slice count to the 1-GPU
-        # run's so that what is compared is the data-parallel logic; DP_CHECK_FREE_NORM_SLICES=1 shows the other.
+    if world > 1 and 4 % world == 0 and os.environ.get("SRGAN_DBG_NORM_F32_PARTIALS", "0") != "0":
+        # With fp32 slice partials (bring-up switch) the instance-norm statistics depend on the slice count, which the
+        # grid planner derives from the number of images a rank holds; pin it to the 1-GPU run's so that what is
+        # compared is the data-parallel logic.  The default fp64 partials over fixed atoms need no pin.
         os.environ.setdefault("SRGAN_DBG_NORM_CTAS_PER_SM", str(4 // world))
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local

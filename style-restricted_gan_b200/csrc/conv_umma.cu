@@ -1188,12 +1188,7 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
   }
   CUtensorMap mdy, mx;
   const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = 32u / (bw * bh);
-  // bring-up overrides (undocumented, debugging only)
-  static const char* e_swz = getenv("SRGAN_DBG_WGRAD_TMASWZ");
-  static const char* e_lbo = getenv("SRGAN_DBG_WGRAD_LBO");
-  static const char* e_sbo = getenv("SRGAN_DBG_WGRAD_SBO");
-  static const char* e_lay = getenv("SRGAN_DBG_WGRAD_LAYOUT");
-  const CUtensorMapSwizzle swz = e_swz ? (CUtensorMapSwizzle)atoi(e_swz) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   {
     uint64_t dims[5] = {(uint64_t)Kp, (uint64_t)d->Q, 1, (uint64_t)d->P, (uint64_t)d->N};
     uint64_t str[4] = {(uint64_t)Kp * 4, (uint64_t)d->Q * Kp * 4, (uint64_t)d->Q * Kp * 4,
@@ -1220,7 +1215,7 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
   p.K = d->K; p.C = C; p.T = T;
   p.gt = w.gt; p.cpb = w.cpb;
   p.split_stride = (long long)d->K * T * C;
-  p.desc_hi = mn_desc_hi(e_lbo ? atoi(e_lbo) : 4096, e_sbo ? atoi(e_sbo) : 512, e_lay ? atoi(e_lay) : 1);
+  p.desc_hi = mn_desc_hi(4096, 512, 1);
   for (int r = 0; r < d->R; ++r)
     for (int s = 0; s < d->S; ++s) {
       int a = r - d->pad, b = s - d->pad;

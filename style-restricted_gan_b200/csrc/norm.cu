@@ -21,7 +21,6 @@ namespace srgan {
 
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxSlices = 64;
-constexpr bool kNormF64Default = true;
 
 struct NormP {
   int N, HW, C;
@@ -783,11 +782,10 @@ __global__ void bnorm_bwd_coeffs_kernel(const float* __restrict__ s1_all, const 
   }
 }
 
-// fp64 partial sums over fixed atoms (see D4 above).  SRGAN_DBG_NORM_F32_PARTIALS=1 restores fp32 partials, whose
-// value depends on the slice count.
+// fp64 partial sums over fixed atoms (see D4 above).  SRGAN_DBG_NORM_F32_PARTIALS=1 (bring-up, A/B timing) restores
+// fp32 partials, whose value depends on the slice count.
 static bool norm_f64() {
-  static const bool on = kNormF64Default ? !(getenv("SRGAN_DBG_NORM_F32_PARTIALS") && atoi(getenv("SRGAN_DBG_NORM_F32_PARTIALS")) != 0)
-                                         : (getenv("SRGAN_NORM_F64_PARTIALS") && atoi(getenv("SRGAN_NORM_F64_PARTIALS")) != 0);
+  static const bool on = !(getenv("SRGAN_DBG_NORM_F32_PARTIALS") && atoi(getenv("SRGAN_DBG_NORM_F32_PARTIALS")) != 0);
   return on;
 }
 

@@ -216,6 +216,38 @@ def test_cuda_graph_replay_is_bit_identical_to_eager_steps(name):
     assert torch.equal(re_, rg)
 
 
+def test_cuda_graph_recaptures_when_the_batch_shape_changes():
+    """An epoch's last, smaller batch: the graph is re-captured for the new shape (and again when the full batch comes
+    back); losses, parameters and the CPU generator state stay bit-identical to the eager run of the same sequence."""
+    c = dict(cases.CASES["srgan_small"], batch=4, k=2)
+    model, util, nb = cases.use_product_modules()
+    ops.set_conv_engine("auto")
+    sizes = [4, 4, 4, 2, 4, 4]
+
+    def run(graph):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        nets = tuple(n.to(DEV) for n in cases.build_nets(model, c, DEV))
+        torch.manual_seed(1)
+        sg = cases.build_trainer(nb, c, nets, DEV)
+        if graph:
+            sg.enable_cuda_graph(warmup=1)
+        losses = []
+        torch.manual_seed(2)
+        for step, b in enumerate(sizes):
+            x, label = cases.synthetic_batch(b, util.get_target, seed=200 + step)
+            errs = sg.train(x.to(DEV), {"source": label["source"].to(DEV), "target": label["target"]})
+            losses.append([float(e) for e in errs])
+        torch.cuda.synchronize()
+        params = torch.cat([p.detach().reshape(-1) for n in nets for p in n.parameters()]).cpu()
+        return losses, params, torch.rand(1)
+    le, pe, re_ = run(False)
+    lg, pg, rg = run(True)
+    assert le == lg, (le, lg)
+    assert torch.equal(pe, pg)
+    assert torch.equal(re_, rg)
+
+
 def test_checkpoint_resume_continues_bit_identically(tmp_path):
     """save_checkpoint / load_checkpoint: weights under the reference's state_dict keys, Adam moments,
     step counters, scheduler and RNG state.  A trainer rebuilt from scratch and resumed at step 2 reproduces steps 3-4

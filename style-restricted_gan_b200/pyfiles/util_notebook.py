@@ -726,3 +726,48 @@ def get_output_and_plot(sg, dataset, index, class_info, random_sample_num=5, *le
         for i, img in enumerate(show(batch)):
             cell(4 * (i + 1) + col, img, title)
     return fig
+
+
+def dic_init(get_edge=False):
+    """Empty (data, label) containers of `get_samples` (ref pyfiles/util_notebook.py:848-856)."""
+    return {"source": [], "target": [], "recon": []}, {"source": [], "target": []}
+
+
+def get_samples(netG, netE, dataset, index, latent=None, classes=tuple(range(4)), ref_label=None,
+                ndim=8, scale=1, image_type="pil", batch=32, device="cuda", conventional_E=False):
+    """Translate sample `index` of `dataset` to every class in `classes` under the given style codes and re-encode
+    the results (ref pyfiles/util_notebook.py:858-950).  `latent`: one [num, ndim] array shared by all classes or a
+    list with one array per class value.  Returns (data, label): data["source"] the input, data["target"][c] the
+    `num` translations to class c (PIL-ready arrays for image_type="pil", one tensor for "tensor"),
+    label["latent"][c] the encoder means of those translations, one array per chunk of `batch` codes."""
+    if image_type not in ("pil", "tensor"):
+        raise ValueError("image_type must be 'pil' or 'tensor'")
+    src = dataset[index][0].view(1, 3, 128, 128).to(device)
+    data, label = dic_init(False)
+    label["source"] = cuda2numpy(torch.tensor([dataset[index][1]]))
+    data["source"] = image_from_output(src)[0] if image_type == "pil" else cuda2cpu(src)[0]
+    netG.eval()
+    netE.eval()
+    as_dev = lambda v: torch.as_tensor(np.asarray(v), dtype=torch.float32).to(device)
+    codes = [as_dev(v) for v in latent] if isinstance(latent, list) else [as_dev(latent)] * len(classes)
+    num = codes[0].shape[0]
+    label["latent"], data["target"] = {}, {}
+    with torch.no_grad():
+        for c in classes:
+            onehot = class_encode(torch.tensor([c]), device, ref_label)
+            mus, images = [], []
+            for lo in range(0, num, batch):
+                z = codes[c][lo:lo + batch]
+                n = z.shape[0]
+                out = netG(src.repeat(n, 1, 1, 1), torch.cat([onehot.repeat(n, 1), z], 1))
+                mu = netE(out, onehot.repeat(n, 1))[1] if conventional_E else netE(out)[1]
+                mus.append(cuda2numpy(mu))
+                images.append(image_from_output(out) if image_type == "pil" else cuda2numpy(out))
+            label["latent"][c] = mus
+            if image_type == "pil":
+                data["target"][c] = [im for chunk in images for im in chunk]
+            else:
+                data["target"][c] = torch.Tensor(np.concatenate(images, axis=0))
+    if image_type == "tensor":
+        data["source"] = torch.Tensor(np.asarray(data["source"])).unsqueeze(0)
+    return data, label

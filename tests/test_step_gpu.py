@@ -290,3 +290,37 @@ def test_checkpoint_resume_continues_bit_identically(tmp_path):
     got_params = torch.cat([p.detach().reshape(-1) for n in nets2 for p in n.parameters()]).cpu()
     assert got_losses == ref_losses, (got_losses, ref_losses)
     assert torch.equal(got_params, ref_params)
+
+
+@pytest.mark.parametrize("name,conventional", [("srgan_small", False), ("single_solo_small", True)])
+def test_get_samples_translates_one_sample_to_every_class(name, conventional):
+    """`get_samples` (ref pyfiles/util_notebook.py:858-950): one source image, `num` style codes, every class; the
+    translations equal direct generator calls and the re-encoded means come back per chunk of `batch` codes."""
+    c = dict(cases.CASES[name])
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    G, D, E = (n.to(DEV) for n in cases.build_nets(model, c, DEV))
+    x, label = cases.synthetic_batch(3, util.get_target, seed=5)
+    dataset = [(x[i], int(label["source"][i])) for i in range(3)]
+    ref_label = np.eye(cases.N_CLASS)
+    lat = np.random.RandomState(1).randn(5, cases.NDIM).astype(np.float32)
+    data, lab = nb.get_samples(G, E, dataset, 1, latent=lat, classes=tuple(range(cases.N_CLASS)),
+                               ref_label=ref_label, ndim=cases.NDIM, image_type="tensor", batch=2, device=DEV,
+                               conventional_E=conventional)
+    assert tuple(data["source"].shape) == (1, 3, 128, 128) and int(lab["source"][0]) == dataset[1][1]
+    assert sorted(data["target"]) == list(range(cases.N_CLASS))
+    for cls in range(cases.N_CLASS):
+        assert tuple(data["target"][cls].shape) == (5, 3, 128, 128)
+        assert [m.shape for m in lab["latent"][cls]] == [(2, cases.NDIM), (2, cases.NDIM), (1, cases.NDIM)]
+    with torch.no_grad():
+        onehot = util.class_encode(torch.tensor([2]), DEV, ref_label)
+        z = torch.from_numpy(lat[:2]).to(DEV)
+        direct = G(x[1:2].to(DEV).repeat(2, 1, 1, 1), torch.cat([onehot.repeat(2, 1), z], 1))
+    assert torch.equal(data["target"][2][:2], direct.cpu())
+    per_class = [np.random.RandomState(10 + k).randn(3, cases.NDIM).astype(np.float32) for k in range(cases.N_CLASS)]
+    data2, lab2 = nb.get_samples(G, E, dataset, 0, latent=per_class, classes=(0, 3), ref_label=ref_label,
+                                 ndim=cases.NDIM, image_type="tensor", batch=32, device=DEV,
+                                 conventional_E=conventional)
+    assert sorted(data2["target"]) == [0, 3] and tuple(data2["target"][3].shape) == (3, 3, 128, 128)
+    assert not torch.equal(data2["target"][0], data2["target"][3])

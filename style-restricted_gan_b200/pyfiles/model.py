@@ -103,8 +103,25 @@ class _CBINorm(nn.Module):
             self.register_parameter("bias", None)
         self.ConBias = nn.Sequential(nn.Linear(num_con, num_features), nn.Tanh())
 
+    _version = 2          # what nn.InstanceNorm2d-derived modules of the reference record in state_dict metadata
+
     def _check_input_dim(self, input):
         raise NotImplementedError
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        """Checkpoints without version metadata (torch < 0.4) may carry running statistics although nothing tracks
+        them: report and drop them, as the reference does (pyfiles/model.py:24-52)."""
+        if local_metadata.get("version", None) is None and not self.track_running_stats:
+            stale = [prefix + n for n in ("running_mean", "running_var") if prefix + n in state_dict]
+            if stale:
+                error_msgs.append("Unexpected running stats buffer(s) {} for {} with track_running_stats=False. "
+                                  "Remove these keys from the state_dict (checkpoint saved before torch 0.4.0?)."
+                                  .format(" and ".join('"%s"' % k for k in stale), type(self).__name__))
+                for k in stale:
+                    state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
 
     def forward(self, input, ConInfor, act=ops.ACT_NONE, slope=0.0, residual=None):
         self._check_input_dim(input)
@@ -161,8 +178,22 @@ class _CBBNorm(nn.Module):
             self.weight.data.uniform_()
             self.bias.data.zero_()
 
+    _version = 2
+
     def _check_input_dim(self, input):
         raise NotImplementedError
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        """Checkpoints older than metadata version 2 have no `num_batches_tracked`: default it to 0
+        (ref pyfiles/model.py:152-165)."""
+        version = local_metadata.get("version", None)
+        if (version is None or version < 2) and self.track_running_stats:
+            key = prefix + "num_batches_tracked"
+            if key not in state_dict:
+                state_dict[key] = torch.tensor(0, dtype=torch.long)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
 
     def _factor(self):
         """exponential_average_factor of the reference (pyfiles/model.py:124-131); bumps num_batches_tracked."""

@@ -34,6 +34,11 @@ def _worker(rank, world, port, out):
         torch.manual_seed(7)
         full = torch.randn(3 * world, 8)
         ok &= bool(torch.equal(mine, full[rank * 3:(rank + 1) * 3]))
+        # batch-norm tables: every rank ends up with the global [N_all, C] table and knows its first row
+        tab = torch.arange(2 * 3, dtype=torch.float32).view(2, 3) + 100 * rank
+        allt, row0 = ops._gather_rows(tab)
+        exp_all = torch.cat([torch.arange(6, dtype=torch.float32).view(2, 3) + 100 * r for r in range(world)])
+        ok &= bool(torch.equal(allt, exp_all)) and row0 == 2 * rank
         t = nb._UnrolledTrainer()
         rep = t._report([torch.tensor(float(rank)), 0, torch.tensor(2.0)])
         ok &= abs(float(rep[0]) - 0.5) < 1e-7 and rep[1] == 0 and float(rep[2]) == 2.0

@@ -91,8 +91,9 @@ def synthetic(batch, seed, get_target):
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def time_oracle(case, steps, warmup, threads):
-    """Reference algorithm (CPU oracle port) on the host cores: images/s over `steps` train() calls."""
+def time_oracle(case, steps, warmup, threads, budget_s=None):
+    """Reference algorithm (CPU oracle port) on the host cores: images/s over up to `steps` train() calls; stops
+    early once `budget_s` seconds of timed work have passed.  Returns (images/s, s/step, steps timed)."""
     import cases
     import srgan_oracle as so
     torch.set_num_threads(threads)
@@ -105,27 +106,39 @@ def time_oracle(case, steps, warmup, threads):
     for _ in range(warmup):
         tr.train(x, label)
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         tr.train(x, label)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return case["batch"] * steps / dt, dt / steps
+    return case["batch"] * done / dt, dt / done, done
 
 
 def run_reference(args):
+    """The reference algorithm on the host CPU (all host threads), same recipe and the same PER-GPU batch as the GPU
+    arm (64): at N = 1 this is the GPU arm's exact configuration; at N > 1 one step is a bounded sample (one rank's
+    share, 64 images) of the global batch.  K timed steps unless the time budget (--ref-budget seconds, default 1200)
+    runs out first; the number of steps actually timed is reported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = args.cpu_batch
+    batch = args.cpu_batch if args.cpu_batch else args.batch
     case = build_case(args.workload, batch)
-    steps = max(1, min(args.steps, 3))
-    ips, spt = time_oracle(case, steps, min(args.warmup, 1), threads)
-    sample = "%d step(s) of %s at batch %d on %d host threads (oracle port of the reference)" % (
-        steps, args.workload, batch, threads)
+    warm = min(args.warmup, 1)
+    ips, spt, steps = time_oracle(case, max(1, args.steps), warm, threads, budget_s=args.ref_budget)
+    sample = "%d step(s) of %s at batch %d on %d host threads (oracle port of the reference; the reference itself is " \
+             "pure PyTorch, imported from /root/reference to pin the port, and cannot travel to the GPU box)" % (
+                 steps, args.workload, batch, threads)
     line = {"impl": "reference", "metric": "srgan_train_images_per_sec", "value": ips, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": spt * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": spt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload]["desc"], "batch": batch},
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "per_gpu_batch": batch,
+                       "global_batch": batch * args.gpus, "image": "3x128x128", "domains": 4,
+                       "parallelism": "dp%d" % args.gpus, "steps_requested": args.steps,
+                       "time_budget_s": args.ref_budget},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -202,6 +215,122 @@ def measure_tf32_peak(dev):
     return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
+def time_latent_losses(batch, dev):
+    """The latent-loss pair (batch-KL + correlation + soft histogram, forward and backward: ONE kernel each) on a
+    [batch, 8] latent batch: CUDA-event microseconds per launch (latency bound: batch x 8 floats)."""
+    import srgan_ops as ops
+    import util
+    hi = util.histogram_imitation(dev)
+    g = hi.gausshist
+    mu = torch.randn(batch, 8, device=dev, requires_grad=True)
+    kw = dict(n_cfg=batch, target=hi.target, bins=g.bins, hmin=g.min, hmax=g.max, sigma=g.sigma,
+              flags=ops.LAT_BKL | ops.LAT_CORR | ops.LAT_HIST)
+    w4 = torch.tensor([10.0, 100.0, 100.0, 0.0], device=dev)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    fwd, bwd = [], []
+    for it in range(13):
+        e0, e1, e2 = ev(), ev(), ev()
+        c0 = ops.abi_calls
+        e0.record()
+        losses, _ = ops.latent_losses(mu, None, **kw)
+        e1.record()
+        c1 = ops.abi_calls
+        gmu, = torch.autograd.grad(losses, mu, w4)
+        e2.record()
+        c2 = ops.abi_calls
+        torch.cuda.synchronize()
+        if it >= 3:
+            fwd.append(e0.elapsed_time(e1) * 1e3)
+            bwd.append(e1.elapsed_time(e2) * 1e3)
+    return {"fwd_us": float(np.median(fwd)), "bwd_us": float(np.median(bwd)), "fwd_launches": c1 - c0,
+            "bwd_launches": c2 - c1, "note": "event-to-event times of eager calls (include the Python dispatch of "
+            "the autograd node); inside the replayed graph the two kernels run back to back"}
+
+
+def _fresh_trainer(workload, batch_cfg, dev, ops, cases):
+    """Nets + trainer of `workload` with the fixed parity seeds (same recipe as __graft_entry__.smoke())."""
+    case = build_case(workload, batch_cfg)
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    nets = cases.build_nets(model, case, dev)
+    sds = cases.state_dicts(nets)
+    torch.manual_seed(1)
+    sg = cases.build_trainer(nb, case, tuple(n.to(dev) for n in nets), dev, adam=ops.FusedAdam)
+    return case, sds, sg, util
+
+
+def parity_check(workload, dev, tol):
+    """Before anything is timed: ONE eager training step of the benchmarked recipe (full-width nets, k = 5) at batch 8
+    on the GPU against the CPU oracle on the same seeded weights, batch and host-drawn noise.  The three reported
+    losses must agree within `tol` (relative to max(1, |ref|)); raises otherwise."""
+    import cases
+    import srgan_ops as ops
+    import srgan_oracle as so
+    case, sds, sg, util = _fresh_trainer(workload, 8, dev, ops, cases)
+    torch.manual_seed(1)
+    oracle = cases.build_oracle(case, sds, so)
+    x, label = cases.synthetic_batch(8, util.get_target)
+    torch.manual_seed(2)
+    t0 = time.perf_counter()
+    ref = [float(e) for e in oracle.train(x, label)]
+    cpu_s = time.perf_counter() - t0
+    torch.manual_seed(2)
+    got = [float(e) for e in sg.train(x.to(dev), {"source": label["source"].to(dev), "target": label["target"]})]
+    torch.cuda.synchronize()
+    err = [abs(g - r) / max(1.0, abs(r)) for g, r in zip(got, ref)]
+    out = {"what": "one eager step of the same recipe at batch 8 vs the CPU oracle (errG, errD, errE)",
+           "gpu": got, "oracle": ref, "rel_err": err, "tol": tol, "ok": bool(max(err) <= tol),
+           "oracle_step_s": cpu_s}
+    if not out["ok"]:
+        raise SystemExit("bench.py parity check FAILED: %s" % json.dumps(out))
+    return out
+
+
+def dp_invariance_check(workload, dev, rank, world, tol=1e-5):
+    """N > 1: one eager data-parallel step at 8 images per GPU.  (1) the reported losses and the latent statistics
+    blob (mean / variance / correlation / histogram bins of the GLOBAL batch) are bit-identical on every rank;
+    (2) rank 0 repeats the step as a single-GPU job on the same global batch of 8 N images (same seeds, same host
+    noise) and the losses agree to `tol` relative (summation order of the mean over ranks vs over the batch)."""
+    import torch.distributed as dist
+    import cases
+    import srgan_ops as ops
+    B = 8
+    case, _, sg, util = _fresh_trainer(workload, B * world, dev, ops, cases)
+    xg, lab = cases.synthetic_batch(B * world, util.get_target)
+    sl = slice(rank * B, (rank + 1) * B)
+    torch.manual_seed(2)
+    errs = sg.train(xg[sl].to(dev), {"source": lab["source"][sl].to(dev), "target": lab["target"][sl]})
+    mine = torch.cat([torch.stack([e.detach().float().reshape(()) for e in errs]), sg.latent_stats.detach().float()])
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    torch.cuda.synchronize()
+    same = all(torch.equal(allv[0].view(torch.int32), v.view(torch.int32)) for v in allv)
+    out = {"what": "one eager step at 8 images/GPU: ranks bit-identical; rank 0 re-runs the global batch single-GPU",
+           "ranks_bit_identical": bool(same), "blob_floats": int(mine.numel() - 3), "tol": tol}
+    del sg
+    if rank == 0:
+        with ops.single_process():
+            _, _, sg1, _ = _fresh_trainer(workload, B * world, dev, ops, cases)
+            torch.manual_seed(2)
+            e1 = sg1.train(xg.to(dev), {"source": lab["source"].to(dev), "target": lab["target"]})
+            one = [float(e) for e in e1]
+            blob1 = sg1.latent_stats.detach().float()
+        dp = [float(v) for v in allv[0][:3]]
+        rel = [abs(a - b) / max(1.0, abs(b)) for a, b in zip(dp, one)]
+        blob_rel = float((allv[0][3:] - blob1).norm() / blob1.norm().clamp_min(1e-30))
+        out.update({"dp_losses": dp, "single_gpu_losses": one, "rel_err": rel, "latent_stats_rel_l2": blob_rel,
+                    "ok": bool(same and max(rel) <= tol and blob_rel <= tol)})
+        del sg1
+    flag = torch.tensor([1 if (rank != 0 or out.get("ok")) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag) != 1 or not same:
+        raise SystemExit("bench.py data-parallel invariance check FAILED: %s" % json.dumps(out))
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import cases
@@ -217,6 +346,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
     if args.engine:
         ops.set_conv_engine(args.engine)
+
+    checks = {}
+    if not args.skip_checks:
+        tol = 5e-3 if ops.get_conv_engine() != "bf16" else 2e-2
+        if world == 1:
+            checks["parity_check"] = parity_check(args.workload, dev, tol)
+        else:
+            checks["dp_check"] = dp_invariance_check(args.workload, dev, rank, world)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
 
     batch = args.batch                                   # per-GPU batch: weak scaling
     case = build_case(args.workload, batch * world)      # n_batch (batch-KL) = configured GLOBAL batch
@@ -292,22 +432,30 @@ def run_ours(args):
     if rank == 0:
         pk = peaks()
         kms, kflops, kname = time_dominant_kernel(batch, dev)
-        tf32_peak = measure_tf32_peak(dev)
+        cublas_tf32 = measure_tf32_peak(dev)
         achieved = kflops / (kms * 1e-3) / 1e12
-        peak = tf32_peak
+        # Denominator: MEASURED_PEAKS.json (driver-written).  It holds the dense bf16 rate; tcgen05 kind::tf32 issues
+        # at half the bf16 rate, so a TF32 kernel is measured against half of it.  (The kernel is timed alone, after a
+        # cold L2 flush: the burst figure applies.)
+        is_tf32 = kname == "tcgen05_tf32"
+        peak = 0.5 * pk["bf16"] if is_tf32 else pk["bf16"]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-            # (batch 64); scaled to the batch of this run
+            # of the SHIPPED kernel (regenerated every round, see profiles/README.md), per launch at batch 64;
+            # the kernel's traffic is linear in the batch
             t = json.load(open(tpath))
-            traffic = t["res_conv_fprop_dram_bytes_b64"] * batch / 64.0
+            key = "res_conv_fprop_dram_bytes_b64" + ("" if is_tf32 else "_bf16")
+            if key in t:
+                traffic = t[key] * batch / 64.0
         roof = {"bound": "tensor", "kernel": "conv2d fprop 3x3 256->256 @32x32 (residual block), " + kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "cuBLAS TF32 8192^3 matmul measured in this run (MEASURED_PEAKS.json has no TF32 "
-                               "entry; bf16 there: %.1f TF/s, %s)" % (pk["bf16"], pk["src"]),
-                # the same rate against half the measured dense bf16 peak (TF32 issues at half the bf16 rate)
-                "frac_of_half_bf16_peak": achieved / (0.5 * pk["bf16"]),
+                "peak_source": "%s x MEASURED_PEAKS.json bf16_tflops (%.1f TF/s, %s)" % (
+                    "0.5" if is_tf32 else "1.0", pk["bf16"], pk["src"]),
+                "algorithmic_flop": kflops,
+                "algorithmic_bytes": (2 * batch * 1024 * 256 + 256 * 2304) * (4 if is_tf32 else 2),
+                "note_cublas_tf32_tflops_this_run": cublas_tf32,
                 "kernel_ms": kms, "step_gflop_per_image": GF_PER_IMG[args.workload],
                 "step_gflop_per_image_executed": GF_PER_IMG[args.workload] - 16.6,   # skipped encoder work
                 "step_tflops": value * GF_PER_IMG[args.workload] / 1e3}
@@ -323,15 +471,16 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            cb = args.cpu_batch
-            ips, spt = time_oracle(build_case(args.workload, cb), 1, 0, threads)
+            cb = args.cpu_batch or 16
+            ips, spt, _ = time_oracle(build_case(args.workload, cb), 1, 0, threads)
             cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                   "sample": "1 step of the same recipe at batch %d (%.1f s) on %d host threads" % (cb, spt, threads)}
+                   "sample": "1 step of the same recipe at batch %d (%.1f s) on %d host threads; the --impl reference "
+                             "arm runs the full batch" % (cb, spt, threads)}
         h2d = x_host.numel() * 4 + src_host.numel() * 8 + 3 * (batch * 8 * 4)
         line = {"metric": "srgan_train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if kname == "tcgen05_tf32" else "f32", "data": "synthetic",
+                "dtype": {"tcgen05_tf32": "tf32", "tcgen05_bf16": "bf16"}.get(kname, "f32"), "data": "synthetic",
                 "config": {"workload": WORKLOADS[args.workload]["desc"], "per_gpu_batch": batch,
                            "global_batch": batch * world, "image": "3x128x128", "domains": 4,
                            "parallelism": "dp%d" % world, "conv_engine": ops.get_conv_engine(),
@@ -339,8 +488,13 @@ def run_ours(args):
                            "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_glue": glue,
+                "gpu_launches": launches,
+                "gpu_launches_note": "C-ABI kernel entry points of one eager step (%d) x steps; the timed steps replay "
+                                     "the same kernels from one CUDA graph" % launches_per_step,
+                "clocks": clocks, "roofline": roof, "roofline_glue": glue,
+                "latent_loss_pair": time_latent_losses(batch * world, dev),
                 "cpu_baseline": cpu}
+        line.update(checks)
         print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
@@ -366,8 +520,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="srgan_nb03", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
-    ap.add_argument("--engine", default=None, choices=[None, "auto", "fp32", "tf32"])
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="batch of the CPU sample (default: 16 for the cpu_baseline leg, --batch for --impl reference)")
+    ap.add_argument("--ref-budget", type=float, default=600.0,
+                    help="--impl reference: stop after this many seconds of timed steps")
+    ap.add_argument("--skip-checks", action="store_true",
+                    help="skip the pre-timing parity check (N=1: vs the CPU oracle; N>1: rank / single-GPU invariance)")
+    ap.add_argument("--engine", default=None, choices=[None, "auto", "fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (sg.enable_cuda_graph) or issue every kernel from Python; "

@@ -30,6 +30,19 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: a process that drives several GPUs
+// must set it once on each.  `done` is a per-call-site bitmask indexed by device ordinal (devices >= 64: set always).
+template <typename F>
+inline cudaError_t ensure_dyn_smem(F* fn, int bytes, unsigned long long* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((*done >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) *done |= 1ull << dev;
+  return e;
+}
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -450,11 +450,10 @@ int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, con
     q.act = act; q.slope = slope;
     const size_t smem2 = 1024 + (size_t)d->S * q.nchunks * 4096 + (size_t)kTOStages * q.nchunks * kTO2ABytes +
                          8 * 4 * 128 * sizeof(float) + 256;
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(conv_thinout2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static unsigned long long attr2 = 0;
+    {
+      cudaError_t e = ensure_dyn_smem(conv_thinout2_kernel, 227 * 1024, &attr2);
       if (e != cudaSuccess) { set_error("conv_thinout2 smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-      attr2 = true;
     }
     conv_thinout2_kernel<<<d->N * t.bands, kTOThreads, smem2, st>>>(min2, mb2, q, bias, out);
     SRGAN_RETURN_LAUNCH();
@@ -481,11 +480,10 @@ int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, con
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((d->R * 32) >> 3) << 17) | ((128u >> 4) << 24);
   const size_t smem = 1024 + (size_t)p.nchunks * d->R * 4096 + (size_t)kTOStages * p.nchunks * 16384 +
                       (2 * kTOZBuf + 8 * 4 * 128) * sizeof(float) + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_thinout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static unsigned long long attr_done = 0;
+  {
+    cudaError_t e = ensure_dyn_smem(conv_thinout_kernel, 227 * 1024, &attr_done);
     if (e != cudaSuccess) { set_error("conv_thinout smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
   }
   conv_thinout_kernel<<<d->N * t.bands, kTOThreads, smem, st>>>(min, mb, p, bias, out);
   SRGAN_RETURN_LAUNCH();

@@ -573,12 +573,10 @@ template <int BN, int MT = 1>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, float* y,
                      dim3 grid, cudaStream_t st, const float* addend) {
   using Cfg = UmmaCfg<BN, MT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmem);
+  static unsigned long long attr_done = 0;
+  {
+    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT>, (int)Cfg::kSmem, &attr_done);
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
   }
   UmmaConvP q = p;
   q.gx = (grid.x + MT - 1) / MT; q.gy = grid.y; q.gz = grid.z;
@@ -1045,12 +1043,10 @@ template <int BN, int KT, int PW>
 static int launch_wgrad_pw(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
                            cudaStream_t st) {
   using Cfg = WgradCfg<BN, KT, PW>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<BN, KT, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmem);
+  static unsigned long long attr_done = 0;
+  {
+    cudaError_t e = ensure_dyn_smem(wgrad_umma_kernel<BN, KT, PW>, (int)Cfg::kSmem, &attr_done);
     if (e != cudaSuccess) { set_error("wgrad_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
   }
   wgrad_umma_kernel<BN, KT, PW><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
   SRGAN_RETURN_LAUNCH();

@@ -51,6 +51,11 @@ def _stream():
 
 
 def _req(*ts):
+    """Operand check of every public operator: CUDA fp32 tensors that live on the CURRENT device.  Kernels are
+    launched on the current device's current stream with raw pointers, so a tensor of another device would be an
+    illegal address (or a silent peer access): callers select the device with torch.cuda.set_device() /
+    `with torch.cuda.device(...)` (one process per GPU does this once)."""
+    cur = None
     for t in ts:
         if t is None:
             continue
@@ -58,6 +63,13 @@ def _req(*ts):
             raise SrganKernelError(
                 "srgan_b200 operators need CUDA float32 tensors (got %s on %s); there is no CPU fallback"
                 % (t.dtype, t.device))
+        if cur is None:
+            cur = torch._C._cuda_getDevice()
+        if t.device.index != cur:
+            raise SrganKernelError(
+                "srgan_b200 operators launch on the current CUDA device (cuda:%d) but got a tensor on %s: call "
+                "torch.cuda.set_device(%d) or wrap the step in `with torch.cuda.device(%d)`"
+                % (cur, t.device, t.device.index, t.device.index))
 
 
 def _p(t):
@@ -70,34 +82,90 @@ def _call(name, *args):
     check(getattr(_lib(), name)(*args), name)
 
 
-_ws = {}
+class _ScratchSet(object):
+    """Kernel scratch of one launch context: the conv / norm workspace (split-K partials, transposed filters, norm
+    partials) and the reduction scratch with its ticket counter.  Kernels get RAW ADDRESSES of these buffers, so a
+    buffer must outlive everything that was launched - or captured - with it: a set never frees a block it has
+    handed out (`keep`), and a captured CUDA graph owns a private set allocated inside the capture (from the graph's
+    memory pool), see `private_scratch`."""
+
+    def __init__(self):
+        self.ws, self.red, self.keep = {}, {}, []
+
+    def workspace(self, dev, nbytes):
+        buf = self.ws.get(dev)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+            self.ws[dev] = buf
+            if self is not _global_scratch:
+                self.keep.append(buf)          # addresses are baked into the graph: nothing is ever released
+        return buf
+
+    def red_scratch(self, dev):
+        s = self.red.get(dev)
+        if s is None:
+            # zero-initialised ticket counter; inside a capture this is a captured memset, replayed with the graph
+            s = torch.zeros(_lib().srgan_reduce_scratch_bytes(0) // 4, dtype=torch.float32, device=dev)
+            self.red[dev] = s
+        return s
+
+
+_global_scratch = _ScratchSet()
+_scratch_set = _global_scratch
+
+
+class private_scratch(object):
+    """with private_scratch() as s: every operator launched inside uses `s` (a fresh _ScratchSet) instead of the
+    process-wide one.  The trainers wrap the CUDA-graph capture of a step in it and keep `s` with the graph, so an
+    eager call that later grows the global workspace cannot free memory the graph still writes to."""
+
+    def __init__(self, existing=None):
+        self.set = existing or _ScratchSet()
+
+    def __enter__(self):
+        global _scratch_set
+        self.prev, _scratch_set = _scratch_set, self.set
+        return self.set
+
+    def __exit__(self, *exc):
+        global _scratch_set
+        _scratch_set = self.prev
 
 
 def _workspace(dev, nbytes):
-    buf = _ws.get(dev)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
-        _ws[dev] = buf
-    return buf
-
-
-_scratch = {}
+    return _scratch_set.workspace(dev, nbytes)
 
 
 def _red_scratch(dev):
-    s = _scratch.get(dev)
-    if s is None:
-        s = torch.zeros(_lib().srgan_reduce_scratch_bytes(0) // 4, dtype=torch.float32, device=dev)
-        _scratch[dev] = s
-    return s
+    return _scratch_set.red_scratch(dev)
 
 
 # ----------------------------------------------------------------------------- host RNG
+_dp_forced = None
+
+
 def dp_rank_world():
+    """(rank, world) of the data-parallel job; (0, 1) without torch.distributed or inside `single_process()`."""
+    if _dp_forced is not None:
+        return _dp_forced
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+class single_process(object):
+    """with single_process(): the trainers and operators behave as a single-GPU job (no collectives, the whole batch
+    is local) although torch.distributed is initialised.  bench.py uses it on rank 0 to re-run a data-parallel step
+    as the single-GPU global-batch step it must reproduce."""
+
+    def __enter__(self):
+        global _dp_forced
+        self.prev, _dp_forced = _dp_forced, (0, 1)
+
+    def __exit__(self, *exc):
+        global _dp_forced
+        _dp_forced = self.prev
 
 
 class FeedTape(object):
@@ -279,7 +347,12 @@ def _krsc(w):
     return _raw_to_nhwc(w.detach())
 
 
-def _fprop(d, x, w, bias, act, slope):
+def _conv_weight(w, like):
+    """The filter tensor a convolution on `like`-typed activations reads (fp32 storage: the parameter itself)."""
+    return w
+
+
+def _fprop(d, x, w, bias, act, slope, out_dtype=None):
     y = _empty_nhwc(d.N, d.K, d.P, d.Q, x)
     if y.numel() == 0:
         return y
@@ -359,6 +432,15 @@ def _wgrad(d, x, dy, want_w, want_b, dw_out=None, db_out=None):
     ws = _workspace(x.device, nb) if nb else None
     _call("srgan_conv2d_wgrad", d, _p(x), _p(dy), _p(dw), _p(db), _engine, _p(ws), nb, _stream())
     return dw, db
+
+
+def wgrad_plan(d):
+    """(pixel splits, CTAs) of the tcgen05 wgrad launch for this layer (introspection for tests / tools)."""
+    import ctypes
+    s_, c_ = ctypes.c_int(0), ctypes.c_int(0)
+    check(_lib().srgan_conv2d_wgrad_plan(ctypes.byref(d), ctypes.addressof(s_), ctypes.addressof(c_)),
+          "srgan_conv2d_wgrad_plan")
+    return s_.value, c_.value
 
 
 def _act_bwd(dy, y, act, slope):

@@ -6,11 +6,11 @@ latent-loss / reduction kernels of libsrgan_b200.so; everything above them is bo
 runs on the host exactly like the reference's (label bookkeeping, image conversion, plotting).
 matplotlib and prdc are imported lazily: neither is needed by the training step.
 """
-import glob
-import itertools
-import os
+import glob  # noqa: F401  (re-exported: the notebooks rely on `from util import *`)
+import itertools  # noqa: F401
+import os  # noqa: F401
 import pickle
-import shutil
+import shutil  # noqa: F401
 
 import numpy as np
 import torch
@@ -18,11 +18,6 @@ import torch.nn as nn
 import torch.nn.functional as F  # noqa: F401  (re-exported for notebooks that rely on `from util import *`)
 
 import srgan_ops as ops
-
-
-def _plt():
-    import matplotlib.pyplot as plt
-    return plt
 
 
 def compute_prdc(*args, **kwargs):
@@ -158,72 +153,21 @@ def get_target(label, classes, to_tensor=False, to_cuda=False, whole=False, shuf
     return target
 
 
-def get_random_dataset(dataset, num, random=True, random_seed=0):
-    if not random:
-        np.random.seed(random_seed)
-    index = np.random.choice(np.arange(len(dataset)), num, False)
-    # (the reference draws `index` and then takes the first `num` items; kept)
-    return torch.cat([dataset[i][0].unsqueeze(0) for i in range(len(index))], dim=0)
+# ------------------------------------------------------------------------------- out of scope (evaluation)
+def _out_of_scope(name):
+    def stub(*args, **kwargs):
+        raise NotImplementedError(
+            "%s is an evaluation / plotting helper outside the training step this package replaces (SURVEY.md 2: out "
+            "of scope); import it from the reference's pyfiles/util.py" % name)
+    stub.__name__ = name
+    return stub
 
 
-# ------------------------------------------------------------------------------- plotting (host only)
-def plot_correlation_matrix(cm, save=False, save_dir="", save_name=""):
-    plt = _plt()
-    plt.figure(figsize=(10, 8))
-    plt.imshow(cm, interpolation="nearest", cmap=plt.get_cmap("Blues"))
-    plt.colorbar()
-    half = cm.max() / 2
-    for i, j in itertools.product(range(cm.shape[0]), range(cm.shape[1])):
-        plt.text(j, i, str(round(cm[i, j], 4)), horizontalalignment="center", fontsize=12,
-                 color="white" if cm[i, j] > half else "black")
-    plt.tight_layout()
-    if save:
-        plt.savefig(fname=save_dir + save_name, format="png", bbox_inches="tight")
-    plt.show()
-
-
-def save_gif(data_list, gif_path, title, save_dir="contempolary_images/", fig_size=(8, 8), font_title=24,
-             duration=100):
-    from PIL import Image
-    plt = _plt()
-    shutil.rmtree(save_dir, ignore_errors=True)
-    os.makedirs(save_dir, exist_ok=True)
-    for i, frame in enumerate(data_list):
-        fig = plt.figure(figsize=fig_size)
-        ax = fig.add_subplot(1, 1, 1)
-        ax.imshow(frame)
-        plt.title(title, fontsize=font_title)
-        plt.tick_params(labelbottom=False, labelleft=False, labelright=False, labeltop=False)
-        plt.savefig(save_dir + f"{str(i).zfill(3)}.png", dpi=64, facecolor="lightgray", bbox_inches="tight",
-                    format="png")
-        plt.close()
-    frames = [Image.open(f) for f in sorted(glob.glob(save_dir + "*.png"))]
-    frames[0].save(gif_path, save_all=True, append_images=frames[1:], duration=duration, loop=0)
-    shutil.rmtree(save_dir, ignore_errors=True)
-
-
-def plot_confusion_matrix(cm, target_names, title="Confusion matrix", cmap=None, normalize=True):
-    plt = _plt()
-    accuracy = np.trace(cm) / float(np.sum(cm))
-    plt.figure(figsize=(10, 8))
-    plt.imshow(cm, interpolation="nearest", cmap=cmap if cmap is not None else plt.get_cmap("Blues"))
-    plt.title(title)
-    plt.colorbar()
-    if target_names is not None:
-        ticks = np.arange(len(target_names))
-        plt.xticks(ticks, target_names, rotation=45)
-        plt.yticks(ticks, target_names)
-    if normalize:
-        cm = cm.astype("float") / cm.sum(axis=1)[:, np.newaxis]
-    thresh = cm.max() / 1.5 if normalize else cm.max() / 2
-    fmt = "{:0.4f}" if normalize else "{:,}"
-    for i, j in itertools.product(range(cm.shape[0]), range(cm.shape[1])):
-        plt.text(j, i, fmt.format(cm[i, j]), horizontalalignment="center",
-                 color="white" if cm[i, j] > thresh else "black")
-    plt.tight_layout()
-    plt.ylabel("True label")
-    plt.xlabel("Predicted label\naccuracy={:0.4f}; misclass={:0.4f}".format(accuracy, 1 - accuracy))
-    plt.show()
+# the names stay importable because the notebooks do `from util import *`
+get_random_dataset = _out_of_scope("get_random_dataset")
+plot_correlation_matrix = _out_of_scope("plot_correlation_matrix")
+save_gif = _out_of_scope("save_gif")
+plot_confusion_matrix = _out_of_scope("plot_confusion_matrix")
 
 
 # =============================================================================== Loss

@@ -50,9 +50,7 @@ _SPLIT_BACKWARD = os.environ.get("SRGAN_DBG_SPLIT_BACKWARD", "0") != "0"     # b
 
 
 def _world():
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
+    return ops.dp_rank_world()
 
 
 def _allreduce_mean_(t):
@@ -155,8 +153,22 @@ class _UnrolledTrainer(object):
         self.c_rand = None
         self.enc_info = None
         self.target_cenc = None
+        self.latent_stats = None        # statistics blob of the last restriction-loss evaluation (ops.latent_stats_views)
         if lbd["hist"] > 0:
             self.hi = histogram_imitation(device)
+        # Three step shortcuts (one no-grad generator pass for the k-1 early fakes, D(real) and D(fake) as one pass,
+        # reuse of the source batch's encoder output in phase 1) are exact only while no layer couples the samples
+        # of a batch: with norm_type="batch" (CBBNorm2d / BatchNorm2d) the batch statistics and the running-statistics
+        # updates would differ from the reference's call pattern, so the reference's pattern is executed instead.
+        import model as _model
+        coupled = (_model._CBBNorm, torch.nn.modules.batchnorm._BatchNorm)
+        nets_d = self._nD if isinstance(self._nD, (list, tuple)) else [self._nD]
+        self._coupled = {name: any(isinstance(m, coupled) for n in nets for m in n.modules())
+                         for name, nets in (("G", [self._nG]), ("E", [self._nE]), ("D", nets_d))}
+        if isinstance(self._nD, (list, tuple)) and _world()[1] > 1:
+            raise NotImplementedError(
+                "one discriminator per class (singleD=False) is not data-parallel: the per-class sub-batches differ "
+                "between ranks, so the D[i] replicas would drift apart; run notebook 01 on one GPU or use singleD=True")
 
     @staticmethod
     def _adam(module, lr):
@@ -222,8 +234,9 @@ class _UnrolledTrainer(object):
         if flags & ops.LAT_HIST:
             g = hi.gausshist
             kw = dict(target=hi.target, bins=g.bins, hmin=g.min, hmax=g.max, sigma=g.sigma)
-        losses, _ = ops.latent_losses(mu, logvar if flags & ops.LAT_KL else None, n_cfg=self.n_batch, flags=flags,
-                                      mu_all=mu_all, logvar_all=lv_all, row0=rank * mu.shape[0], **kw)
+        losses, self.latent_stats = ops.latent_losses(mu, logvar if flags & ops.LAT_KL else None, n_cfg=self.n_batch,
+                                                      flags=flags, mu_all=mu_all, logvar_all=lv_all,
+                                                      row0=rank * mu.shape[0], **kw)
         terms = {}
         if flags & ops.LAT_KL:
             terms["KL"] = losses[3] * lbd["KL"]
@@ -242,7 +255,7 @@ class _UnrolledTrainer(object):
         their graphs, pyfiles/util_notebook.py:716-722), so they come from ONE no-grad generator pass over the k-1
         noise draws - drawn in the reference's order: nothing else consumes the CPU generator between two
         `update_D` calls.  Returns a list of (image, noise), or None when there is nothing to batch."""
-        if _NO_BATCH_FAKES or self.k < 2 or isinstance(self._nD, (list, tuple)):
+        if _NO_BATCH_FAKES or self.k < 2 or isinstance(self._nD, (list, tuple)) or self._coupled["G"]:
             return None
         src, lab, n = self.source_image, self.label["target"], self.k - 1
         B = src.shape[0]
@@ -262,7 +275,7 @@ class _UnrolledTrainer(object):
         output is bit-identical to the two separate passes, the weight gradients differ only in summation order, and
         the many small layers of D run at twice the batch (fewer, better filled launches)."""
         src = self.source_image
-        if _SPLIT_D:
+        if _SPLIT_D or self._coupled["D"]:
             output, output_class = self._nD(src)
             out_fake, _ = self._nD(fake)
         else:
@@ -292,7 +305,7 @@ class _UnrolledTrainer(object):
         # The restriction terms do not touch the RNG, so evaluating them in one fused launch here (after the
         # identity pass) is equivalent to the reference's interleaving; they are ADDED in the reference's order.
         if lbd["idt"] > 0:
-            if _REENCODE:
+            if _REENCODE or self._coupled["E"]:
                 identity_image, _ = self.G_transformation(lab["source"], src, True, src)
             else:
                 # The reference encodes the source batch a second time here (pyfiles/util_notebook.py:637-641).  The
@@ -413,7 +426,10 @@ class _UnrolledTrainer(object):
             import gc
             gc.collect()
             torch.cuda.synchronize(dev)
-            with ops.recording(st["tape"]):
+            # the captured kernels keep raw addresses of their scratch: the graph gets its own set, allocated inside
+            # the capture (graph memory pool) and held by `st` for as long as the graph lives
+            st["scratch"] = ops.private_scratch()
+            with ops.recording(st["tape"]), st["scratch"]:
                 # data parallel: NCCL's watchdog thread polls CUDA events while this thread captures; only the
                 # capturing thread may be restricted
                 mode = "thread_local" if _world()[1] > 1 else "global"
@@ -435,11 +451,14 @@ class _UnrolledTrainer(object):
         _, world = _world()
         if world == 1:
             return errs
-        out = []
-        for e in errs:
-            if torch.is_tensor(e):
-                e = _allreduce_mean_(e.detach().clone())
-            out.append(e)
+        idx = [i for i, e in enumerate(errs) if torch.is_tensor(e)]
+        if not idx:
+            return errs
+        # ONE collective for all reported scalars
+        packed = _allreduce_mean_(torch.stack([errs[i].detach().float().reshape(()) for i in idx]))
+        out = list(errs)
+        for j, i in enumerate(idx):
+            out[i] = packed[j]
         return out
 
 

@@ -87,6 +87,15 @@ int srgan_conv2d_dgrad_add_supported(const srgan_conv_desc* d, int engine);
 int srgan_conv2d_dgrad_add(const srgan_conv_desc* d, const float* dy, const float* w, const float* addend,
                            float* dx, int engine, void* workspace, size_t workspace_bytes, void* stream);
 /* introspection (tests, tools): pixel splits and CTAs of the tcgen05 wgrad launch for this layer (host only) */
+/* bf16 storage (experimental, next round): x, w, y, dy, dx, addend are NHWC / KRSC tensors of bfloat16 (passed as
+ * void*), bias is fp32, accumulation fp32 in TMEM (tcgen05 kind::f16).  Plain layers only: reduction channels a
+ * multiple of 64.  addend may be NULL (stride 1 only otherwise). */
+int srgan_conv2d_bf16_supported(const srgan_conv_desc* d, int pass);
+size_t srgan_conv2d_bf16_workspace(const srgan_conv_desc* d, int pass);
+int srgan_conv2d_fprop_bf16(const srgan_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                            int act, float slope, void* stream);
+int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
+                            void* workspace, size_t workspace_bytes, void* stream);
 int srgan_conv2d_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
 /* which engine AUTO resolves to for this shape/pass: SRGAN_CONV_FP32 or SRGAN_CONV_TF32 */
 int srgan_conv2d_engine(const srgan_conv_desc* d, int pass);

@@ -38,6 +38,14 @@ void conv_umma_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
 int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, float*, float*, void*, size_t,
                            cudaStream_t);
 
+// conv_umma.cu, bf16 storage (void*: __nv_bfloat16 tensors)
+bool conv_umma_bf16_supported(const srgan_conv_desc* d, int pass);
+size_t conv_umma_bf16_workspace(const srgan_conv_desc* d, int pass);
+int conv_fprop_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, const float*, void*, int, float,
+                                cudaStream_t);
+int conv_dgrad_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, void*, void*, size_t, cudaStream_t,
+                                const void* addend);
+
 static int check_desc(const srgan_conv_desc* d) {
   if (!d) { set_error("conv: null descriptor"); return SRGAN_E_BADARG; }
   if (d->N < 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->K <= 0 || d->R <= 0 || d->S <= 0 || d->stride <= 0 ||
@@ -133,6 +141,29 @@ extern "C" int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, cons
   if (e == SRGAN_CONV_TF32)
     return conv_wgrad_umma_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
   return conv_wgrad_ffma_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- bf16 storage (experimental): NHWC bf16 activations, KRSC bf16 filters, fp32 bias and accumulation
+extern "C" int srgan_conv2d_bf16_supported(const srgan_conv_desc* d, int pass) {
+  if (check_desc(d)) return 0;
+  return (pass == 1 || dense_x(d)) && conv_umma_bf16_supported(d, pass) ? 1 : 0;
+}
+extern "C" size_t srgan_conv2d_bf16_workspace(const srgan_conv_desc* d, int pass) {
+  if (check_desc(d)) return 0;
+  return conv_umma_bf16_workspace(d, pass);
+}
+extern "C" int srgan_conv2d_fprop_bf16(const srgan_conv_desc* d, const void* x, const void* w, const float* bias,
+                                       void* y, int act, float slope, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(x && w && y, "null pointer");
+  SRGAN_CHECK_ARG(dense_x(d), "bf16 conv: dense NHWC input only");
+  return conv_fprop_umma_bf16_launch(d, x, w, bias, y, act, slope, (cudaStream_t)stream);
+}
+extern "C" int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy, const void* w, const void* addend,
+                                       void* dx, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
+  return conv_dgrad_umma_bf16_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream, addend);
 }
 
 extern "C" int srgan_conv2d_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas) {

@@ -18,9 +18,30 @@
 //   dgrad stride 2 /      4 output-parity classes (blockIdx.z), each a 2x2-tap stride-1 problem on dy,
 //   conv-transpose fwd    written to every second output pixel
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "umma_ptx.cuh"
 
 namespace srgan {
+
+// Storage type of the activations / filters of a launch.  Everything in the kernels is laid out in BYTES (a stage
+// row is one 128-byte swizzle atom, an MMA K-step is 32 bytes), so the storage type only changes how many reduction
+// channels a row holds, the operand format of the instruction descriptor and the MMA kind, and the epilogue's stores.
+template <typename ST> struct UmmaElem;
+template <> struct UmmaElem<float> {
+  static constexpr int kRow = 32;                       // reduction channels per 128-byte row
+  static constexpr uint32_t kFmt = 2;                   // TF32
+  static constexpr CUtensorMapDataType kTma = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
+template <> struct UmmaElem<__nv_bfloat16> {
+  static constexpr int kRow = 64;
+  static constexpr uint32_t kFmt = 1;                   // BF16 (kind::f16)
+  static constexpr CUtensorMapDataType kTma = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+template <typename ST>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (sizeof(ST) == 4) umma_tf32(d, a, b, idesc, acc);
+  else umma_f16(d, a, b, idesc, acc);
+}
 
 constexpr int kUmmaThreads = 192;
 constexpr int kMaxTaps = 64;
@@ -48,7 +69,7 @@ struct UmmaConvP {
 // MT = number of 128-pixel M sub-tiles a CTA accumulates against ONE filter tile per stage: the filter bytes are
 // amortised over MT*128 pixels (TF32 operands are 4 bytes, so a 128x256 tile needs 96 B/clk of shared-memory
 // fill to keep the tensor pipe busy, a 256x256 tile 64 B/clk).
-template <int BN, int MT = 1>
+template <int BN, int MT = 1, typename ST = float>
 struct UmmaCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
@@ -64,8 +85,9 @@ struct UmmaCfg {
   static constexpr int kBoxes = MT + BN / kBRows;
   static constexpr int kProducers = 2 * kBoxes;
   static constexpr int kThreads = 32 * (5 + kProducers);   // warp 0 MMA, warps 1-4 epilogue, then the producers
-  // instruction descriptor: D=f32, A=B=tf32, K-major both, N=BN, M=128
-  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  // instruction descriptor: D=f32, A=B=tf32 or bf16, K-major both, N=BN, M=128
+  static constexpr uint32_t kIdesc = (1u << 4) | (UmmaElem<ST>::kFmt << 7) | (UmmaElem<ST>::kFmt << 10) |
+                                     ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
 };
 
 // Persistent: gridDim.x CTAs (one per SM) walk over the work items (tile group, filter tile, parity class) with a
@@ -119,9 +141,63 @@ __device__ __forceinline__ void epi_row_chunk(const float (&v)[32], float* __res
     }
   }
 }
-template <int N>
-__device__ __forceinline__ void epi_row_chunk_any(const float (&v)[32], float* dst, const float* bias, int act,
-                                                  float slope, int vec, const float* add = nullptr) {
+// ---- bf16 storage: the same row chunk packed two outputs per 32-bit word; VEC == 8: 32-byte stores (16 outputs),
+// VEC == 4: 16-byte stores (8 outputs)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* o) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { o[2 * e] = __uint_as_float(w[e] << 16); o[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+}
+__device__ __forceinline__ void st_global_v8_b32(void* p, const uint32_t* o) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+               "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+template <int ACT, int N, int VEC>
+__device__ __forceinline__ void epi_row_chunk(const float (&v)[32], __nv_bfloat16* __restrict__ dst,
+                                              const float* __restrict__ bias, float slope,
+                                              const __nv_bfloat16* __restrict__ add = nullptr) {
+#pragma unroll
+  for (int j = 0; j < N; j += 16) {
+    float o[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = v[j + e];
+    if (bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + j + 4 * q));
+        o[4 * q] += b.x; o[4 * q + 1] += b.y; o[4 * q + 2] += b.z; o[4 * q + 3] += b.w;
+      }
+    }
+    if (add) {                      // same layout as dst: the other gradient that flows into this tensor
+      float a[16];
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(add + j)), a);
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(add + j + 8)), a + 8);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] += a[e];
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(act_t<ACT>(o[2 * e], slope), act_t<ACT>(o[2 * e + 1], slope));
+    if (VEC == 8) {
+      st_global_v8_b32(dst + j, w);
+    } else {
+      *reinterpret_cast<uint4*>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(dst + j + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+}
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int N, typename ST>
+__device__ __forceinline__ void epi_row_chunk_any(const float (&v)[32], ST* dst, const float* bias, int act,
+                                                  float slope, int vec, const ST* add = nullptr) {
   if (add) {                                     // fused gradient accumulation: no bias, no activation
     if (vec == 8) epi_row_chunk<SRGAN_ACT_NONE, N, 8>(v, dst, nullptr, 0.f, add);
     else epi_row_chunk<SRGAN_ACT_NONE, N, 4>(v, dst, nullptr, 0.f, add);
@@ -164,12 +240,12 @@ __device__ __forceinline__ UmmaItem umma_item(const UmmaConvP& p, int item) {
   return u;
 }
 
-template <int BN, int MT>
-__global__ void __launch_bounds__((UmmaCfg<BN, MT>::kThreads), 1)
+template <int BN, int MT, typename ST>
+__global__ void __launch_bounds__((UmmaCfg<BN, MT, ST>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, float* __restrict__ y,
-                 const float* __restrict__ addend) {
-  using Cfg = UmmaCfg<BN, MT>;
+                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, ST* __restrict__ y,
+                 const ST* __restrict__ addend) {
+  using Cfg = UmmaCfg<BN, MT, ST>;
   constexpr int NBUF = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -219,7 +295,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int stage = gi % Cfg::kStages;
           const uint32_t phase = (uint32_t)(gi / Cfg::kStages) & 1u;
           const int4 tp = p.taps[tap0 + it / p.c_chunks];
-          const int cc = (it % p.c_chunks) * 32;
+          const int cc = (it % p.c_chunks) * UmmaElem<ST>::kRow;
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
           if (box < MT) {
@@ -261,8 +337,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int mt = 0; mt < MT; ++mt) {
             const uint64_t adesc = smem_desc_sw128(sa + mt * kABytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
-              umma_tf32(acc + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            for (int k = 0; k < 4; ++k)   // 4 x (K = 8 tf32 / 16 bf16 = 32 bytes) per 128-byte row; +32 B = +2 in the address field
+              umma_any<ST>(acc + mt * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
           }
           umma_commit(empty + stage);     // stage reusable once these MMAs have read it
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -290,11 +366,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int n = (t / p.tiles_h) * bn + nl, pp = (t % p.tiles_h) * bh + hl, qq = tw * bw + wl;
         const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
-        float* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
-                           (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
+        ST* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
+                        (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MT * BN) + mt * BN;
         const float* brow = bias ? bias + col0 : nullptr;
-        const float* arow = addend ? addend + (yrow - y) + col0 : nullptr;      // addend has the layout of y
+        const ST* arow = addend ? addend + (yrow - y) + col0 : nullptr;         // addend has the layout of y
         if (kChunk == 32) {
           // the TMEM load of chunk c + 1 is in flight while chunk c is converted and stored
           uint32_t ra[32], rb[32];
@@ -317,8 +393,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (col0 + c + j < p.K)
-                    yrow[col0 + c + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f) +
-                                                   (arow ? __ldg(arow + c + j) : 0.f), p.act, p.slope);
+                    st_from_float(yrow + col0 + c + j,
+                                  apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f) +
+                                            (arow ? ld_as_float(arow + c + j) : 0.f), p.act, p.slope));
               }
             }
           }
@@ -332,8 +409,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (col0 + j < p.K)
-                  yrow[col0 + j] = apply_act(v[j] + (bias ? __ldg(bias + col0 + j) : 0.f) +
-                                             (arow ? __ldg(arow + j) : 0.f), p.act, p.slope);
+                  st_from_float(yrow + col0 + j, apply_act(v[j] + (bias ? __ldg(bias + col0 + j) : 0.f) +
+                                                           (arow ? ld_as_float(arow + j) : 0.f), p.act, p.slope));
             }
           }
         }
@@ -533,13 +610,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 }
 
 // w[K][T][C] -> wt[C][T][K]  (filter transpose for the dgrad-shaped problems)
-__global__ void filter_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int T, int C) {
-  __shared__ float tile[32][33];
+template <typename ST>
+__global__ void filter_transpose_kernel(const ST* __restrict__ w, ST* __restrict__ wt, int K, int T, int C) {
+  __shared__ ST tile[32][33 + (sizeof(ST) == 2 ? 1 : 0)];
   const int tp = blockIdx.z;
   const int k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     int k = k0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (k < K && c < C) ? w[((size_t)k * T + tp) * C + c] : 0.f;
+    tile[j][threadIdx.x] = (k < K && c < C) ? w[((size_t)k * T + tp) * C + c] : ST(0.f);
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -569,13 +647,13 @@ static int pick_bn(int K) {
   return 16;
 }
 
-template <int BN, int MT = 1>
-static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, float* y,
-                     dim3 grid, cudaStream_t st, const float* addend) {
-  using Cfg = UmmaCfg<BN, MT>;
+template <int BN, int MT, typename ST>
+static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, ST* y,
+                     dim3 grid, cudaStream_t st, const ST* addend) {
+  using Cfg = UmmaCfg<BN, MT, ST>;
   static unsigned long long attr_done = 0;
   {
-    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT>, (int)Cfg::kSmem, &attr_done);
+    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST>, (int)Cfg::kSmem, &attr_done);
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
   UmmaConvP q = p;
@@ -594,63 +672,71 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
   }
   q.n_items = (int)items;
   const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);     // persistent: one CTA per SM
-  conv_umma_kernel<BN, MT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend);
+  conv_umma_kernel<BN, MT, ST><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend);
   SRGAN_RETURN_LAUNCH();
 }
 
 // Generic launcher.  act_*: the tensor providing the A operand, [aN][aH][aW][aC] NHWC; `a_stride` 1 or 2
 // (2 => parity view).  filt: [fK][T][fC] with fC == aC the reduction channels, fK = output channels.
+// Activation, filter, output and addend share one storage type ST (float: TF32 MMAs; __nv_bfloat16: kind::f16).
 struct Problem {
-  const float* act; int aN, aH, aW, aC; int a_stride;
-  const float* filt; int fK, T;
+  const void* act; int aN, aH, aW, aC; int a_stride;
+  const void* filt; int fK, T;
   int Nn, P, Q;              // pixel grid per class
   int out_H, out_W, os;
   int ncls;
   UmmaConvP p;               // taps / classes prefilled
 };
 
-static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st,
-                       const CUtensorMap* ma_prebuilt = nullptr, const float* addend = nullptr) {
+template <typename ST>
+static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float slope, cudaStream_t st,
+                         const CUtensorMap* ma_prebuilt, const ST* addend) {
+  constexpr uint64_t ES = sizeof(ST);
+  constexpr uint32_t ROW = UmmaElem<ST>::kRow;
+  constexpr CUtensorMapDataType DT = UmmaElem<ST>::kTma;
   if (((uintptr_t)pr.act | (uintptr_t)pr.filt | (uintptr_t)y) % 16) {
     set_error("tcgen05 conv: tensors must be 16-byte aligned");
     return SRGAN_E_BADARG;
   }
   CUtensorMap ma, mb;
   const int C = pr.aC;
+  if (C % (int)ROW) { set_error("tcgen05 conv: reduction channels must be a multiple of %d", (int)ROW); return SRGAN_E_UNSUPPORTED; }
   if (ma_prebuilt) {
     ma = *ma_prebuilt;            // caller picked the box with pick_box(pr.P, pr.Q) and filled pr.p.lw / lh
   } else if (pr.a_stride == 1) {
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)pr.aW, 1, (uint64_t)pr.aH, (uint64_t)pr.aN};
-    uint64_t str[4] = {(uint64_t)C * 4, (uint64_t)pr.aW * C * 4, (uint64_t)pr.aW * C * 4,
-                       (uint64_t)pr.aH * pr.aW * C * 4};
+    uint64_t str[4] = {(uint64_t)C * ES, (uint64_t)pr.aW * C * ES, (uint64_t)pr.aW * C * ES,
+                       (uint64_t)pr.aH * pr.aW * C * ES};
     pick_box(pr.P, pr.Q, &pr.p.lw, &pr.p.lh);
-    uint32_t box[5] = {32, 1u << pr.p.lw, 1, 1u << pr.p.lh, 128u >> (pr.p.lw + pr.p.lh)};
-    if (int e = encode_map(&ma, pr.act, 5, dims, str, box)) return e;
+    uint32_t box[5] = {ROW, 1u << pr.p.lw, 1, 1u << pr.p.lh, 128u >> (pr.p.lw + pr.p.lh)};
+    if (int e = encode_map(&ma, pr.act, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, DT)) return e;
   } else {
     uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)pr.aW / 2, 2, (uint64_t)pr.aH / 2, (uint64_t)pr.aN};
-    uint64_t str[4] = {(uint64_t)2 * C * 4, (uint64_t)pr.aW * C * 4, (uint64_t)2 * pr.aW * C * 4,
-                       (uint64_t)pr.aH * pr.aW * C * 4};
+    uint64_t str[4] = {(uint64_t)2 * C * ES, (uint64_t)pr.aW * C * ES, (uint64_t)2 * pr.aW * C * ES,
+                       (uint64_t)pr.aH * pr.aW * C * ES};
     pick_box(pr.P, pr.Q, &pr.p.lw, &pr.p.lh);
-    uint32_t box[5] = {32, 1u << pr.p.lw, 1, 1u << pr.p.lh, 128u >> (pr.p.lw + pr.p.lh)};
-    if (int e = encode_map(&ma, pr.act, 5, dims, str, box)) return e;
+    uint32_t box[5] = {ROW, 1u << pr.p.lw, 1, 1u << pr.p.lh, 128u >> (pr.p.lw + pr.p.lh)};
+    if (int e = encode_map(&ma, pr.act, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, DT)) return e;
   }
   const int BN = pick_bn(pr.fK);
   {
     uint64_t dims[3] = {(uint64_t)C, (uint64_t)pr.T, (uint64_t)pr.fK};
-    uint64_t str[2] = {(uint64_t)C * 4, (uint64_t)pr.T * C * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)(BN < 128 ? BN : 128)};      // == UmmaCfg::kBRows
-    if (int e = encode_map(&mb, pr.filt, 3, dims, str, box)) return e;
+    uint64_t str[2] = {(uint64_t)C * ES, (uint64_t)pr.T * C * ES};
+    uint32_t box[3] = {ROW, 1, (uint32_t)(BN < 128 ? BN : 128)};      // == UmmaCfg::kBRows
+    if (int e = encode_map(&mb, pr.filt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, DT)) return e;
   }
   UmmaConvP& p = pr.p;
-  p.c_chunks = C / 32;
+  p.c_chunks = C / (int)ROW;
   const int bw = 1 << p.lw, bh = 1 << p.lh, bn = 128 >> (p.lw + p.lh);
   p.tiles_w = ceil_div(pr.Q, bw); p.tiles_h = ceil_div(pr.P, bh); p.tiles_n = ceil_div(pr.Nn, bn);
   p.Nn = pr.Nn; p.P = pr.P; p.Q = pr.Q;
   p.out_H = pr.out_H; p.out_W = pr.out_W; p.out_C = pr.fK; p.os = pr.os; p.K = pr.fK;
   p.act = act; p.slope = slope;
-  p.epi_vec = (pr.fK % 8 == 0 && (uintptr_t)y % 32 == 0) ? 8 : (pr.fK % 4 == 0 ? 4 : 0);
+  // epi_vec 8: a row segment of 32 accumulator columns is written with 32-byte stores, 4: 16-byte stores, 0: scalar
+  constexpr int V8 = 32 / (int)ES, V4 = 16 / (int)ES;      // outputs per 32-byte / 16-byte store
+  p.epi_vec = (pr.fK % V8 == 0 && (uintptr_t)y % 32 == 0) ? 8 : (pr.fK % V4 == 0 ? 4 : 0);
   if (bias && (uintptr_t)bias % 16) p.epi_vec = 0;            // vector bias loads need an aligned bias
-  if (addend && ((uintptr_t)addend % 16 || pr.fK % 4)) { set_error("conv: addend must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  if (addend && ((uintptr_t)addend % 16 || pr.fK % V4)) { set_error("conv: addend must be 16-byte aligned"); return SRGAN_E_BADARG; }
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
   // Two M sub-tiles per CTA (one filter tile feeds 256 pixels) when TMEM can still double-buffer the accumulator
   // (2 x 2 x 128 columns) and every SM keeps work; 256-wide tiles stay at MT = 1: overlapping the epilogue with the
@@ -659,16 +745,22 @@ static int run_problem(Problem& pr, const float* bias, float* y, int act, float 
   static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
   const long ctas = (long)grid.x * grid.y * grid.z;
   const int mt = e_mt ? atoi(e_mt) : ((BN == 128 || BN == 64) && ctas >= 2 * kNumSMs ? 2 : 1);
-  if (mt == 2 && BN == 256) return launch_bn<256, 2>(ma, mb, p, bias, y, grid, st, addend);
-  if (mt == 2 && BN == 128) return launch_bn<128, 2>(ma, mb, p, bias, y, grid, st, addend);
-  if (mt == 2 && BN == 64) return launch_bn<64, 2>(ma, mb, p, bias, y, grid, st, addend);
+  if (mt == 2 && BN == 256) return launch_bn<256, 2, ST>(ma, mb, p, bias, y, grid, st, addend);
+  if (mt == 2 && BN == 128) return launch_bn<128, 2, ST>(ma, mb, p, bias, y, grid, st, addend);
+  if (mt == 2 && BN == 64) return launch_bn<64, 2, ST>(ma, mb, p, bias, y, grid, st, addend);
   switch (BN) {
-    case 256: return launch_bn<256>(ma, mb, p, bias, y, grid, st, addend);
-    case 128: return launch_bn<128>(ma, mb, p, bias, y, grid, st, addend);
-    case 64:  return launch_bn<64>(ma, mb, p, bias, y, grid, st, addend);
-    case 32:  return launch_bn<32>(ma, mb, p, bias, y, grid, st, addend);
-    default:  return launch_bn<16>(ma, mb, p, bias, y, grid, st, addend);
+    case 256: return launch_bn<256, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
+    case 128: return launch_bn<128, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
+    case 64:  return launch_bn<64, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
+    case 32:  return launch_bn<32, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
+    default:  return launch_bn<16, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
   }
+}
+
+// fp32 storage (TF32 MMAs): the entry point of the thin-tensor and plain fp32 paths
+static int run_problem(Problem& pr, const float* bias, float* y, int act, float slope, cudaStream_t st,
+                       const CUtensorMap* ma_prebuilt = nullptr, const float* addend = nullptr) {
+  return run_problem_t<float>(pr, bias, y, act, slope, st, ma_prebuilt, addend);
 }
 
 
@@ -955,11 +1047,8 @@ size_t conv_umma_workspace(const srgan_conv_desc* d, int pass) {
   return 0;
 }
 
-int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                           int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (conv_thinout_supported(d, 0)) return conv_thinout_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st);
-  { ThinPlan t; if (thin_plan(d, 0, &t)) return conv_thin_fwdlike_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st); }
-  Problem pr = {};
+// plain (non-thin) forward problem: taps (r, s) at offsets (r - pad, s - pad); stride 2 through the parity view
+static void fprop_problem(const srgan_conv_desc* d, const void* x, const void* w, Problem& pr) {
   pr.act = x; pr.aN = d->N; pr.aH = d->H; pr.aW = d->W; pr.aC = d->C; pr.a_stride = d->stride;
   pr.filt = w; pr.fK = d->K; pr.T = d->R * d->S;
   pr.Nn = d->N; pr.P = d->P; pr.Q = d->Q; pr.out_H = d->P; pr.out_W = d->Q; pr.os = 1; pr.ncls = 1;
@@ -980,29 +1069,11 @@ int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float
     }
   p.tap_begin[1] = nt;
   p.cls_oph[0] = 0; p.cls_opw[0] = 0;
-  return run_problem(pr, bias, y, act, slope, st);
 }
 
-// addend (optional, layout of dx): dx = dgrad(dy) + addend in the epilogue; only on the generic stride-1 path
-bool conv_dgrad_umma_add_supported(const srgan_conv_desc* d) {
-  ThinPlan t;
-  return d->stride == 1 && d->C % 4 == 0 && !conv_thinout_supported(d, 1) && !thin_plan(d, 1, &t);
-}
-
-int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
-                           size_t ws_bytes, cudaStream_t st, const float* addend) {
-  if (addend && !conv_dgrad_umma_add_supported(d)) { set_error("conv dgrad: fused addend not available for this shape"); return SRGAN_E_UNSUPPORTED; }
-  if (conv_thinout_supported(d, 1)) return conv_thinout_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st);
-  { ThinPlan t; if (thin_plan(d, 1, &t)) return conv_thin_fwdlike_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st); }
+// plain input-gradient problem on dy and the transposed filter wt[C][T][K]
+static void dgrad_problem(const srgan_conv_desc* d, const void* dy, const void* wt, Problem& pr) {
   const int T = d->R * d->S;
-  size_t need = (size_t)d->K * T * d->C * sizeof(float);
-  if (ws_bytes < need || !ws) { set_error("conv dgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
-  float* wt = (float*)ws;       // [C][T][K]
-  {
-    dim3 g(ceil_div(d->C, 32), ceil_div(d->K, 32), T);
-    filter_transpose_kernel<<<g, dim3(32, 8), 0, st>>>(w, wt, d->K, T, d->C);
-  }
-  Problem pr = {};
   pr.act = dy; pr.aN = d->N; pr.aH = d->P; pr.aW = d->Q; pr.aC = d->K; pr.a_stride = 1;
   pr.filt = wt; pr.fK = d->C; pr.T = T;
   UmmaConvP& p = pr.p;
@@ -1032,7 +1103,84 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
     }
     p.tap_begin[4] = nt;
   }
+}
+
+int conv_fprop_umma_launch(const srgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                           int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (conv_thinout_supported(d, 0)) return conv_thinout_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st);
+  { ThinPlan t; if (thin_plan(d, 0, &t)) return conv_thin_fwdlike_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, st); }
+  Problem pr = {};
+  fprop_problem(d, x, w, pr);
+  return run_problem(pr, bias, y, act, slope, st);
+}
+
+// addend (optional, layout of dx): dx = dgrad(dy) + addend in the epilogue; only on the generic stride-1 path
+bool conv_dgrad_umma_add_supported(const srgan_conv_desc* d) {
+  ThinPlan t;
+  return d->stride == 1 && d->C % 4 == 0 && !conv_thinout_supported(d, 1) && !thin_plan(d, 1, &t);
+}
+
+int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
+                           size_t ws_bytes, cudaStream_t st, const float* addend) {
+  if (addend && !conv_dgrad_umma_add_supported(d)) { set_error("conv dgrad: fused addend not available for this shape"); return SRGAN_E_UNSUPPORTED; }
+  if (conv_thinout_supported(d, 1)) return conv_thinout_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st);
+  { ThinPlan t; if (thin_plan(d, 1, &t)) return conv_thin_fwdlike_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, st); }
+  const int T = d->R * d->S;
+  size_t need = (size_t)d->K * T * d->C * sizeof(float);
+  if (ws_bytes < need || !ws) { set_error("conv dgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  float* wt = (float*)ws;       // [C][T][K]
+  {
+    dim3 g(ceil_div(d->C, 32), ceil_div(d->K, 32), T);
+    filter_transpose_kernel<float><<<g, dim3(32, 8), 0, st>>>(w, wt, d->K, T, d->C);
+  }
+  Problem pr = {};
+  dgrad_problem(d, dy, wt, pr);
   return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st, nullptr, addend);
+}
+
+// ------------------------------------------------------------------------------------------ bf16 storage
+// Activations, filters (a bf16 shadow of the fp32 master weights) and outputs in bf16, fp32 accumulation and bias.
+// Plain layers only (reduction channels a multiple of 64); thin RGB layers stay on the fp32 kernels.
+bool conv_umma_bf16_supported(const srgan_conv_desc* d, int pass) {
+  if (d->N < 1 || d->R * d->S > kMaxTaps) return false;
+  const bool even = d->H % 2 == 0 && d->W % 2 == 0;
+  if (pass == 0) return d->C % 64 == 0 && d->K % 8 == 0 && (d->stride == 1 || (d->stride == 2 && even));
+  if (pass == 1) {
+    if (d->K % 64 || d->C % 8) return false;
+    if (d->stride == 1) return d->pad < d->R && d->pad < d->S;
+    return d->stride == 2 && even && d->R >= 2 && d->S >= 2;
+  }
+  return false;
+}
+
+size_t conv_umma_bf16_workspace(const srgan_conv_desc* d, int pass) {
+  return pass == 1 ? (size_t)d->K * d->R * d->S * d->C * sizeof(__nv_bfloat16) : 0;     // transposed filter
+}
+
+int conv_fprop_umma_bf16_launch(const srgan_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                                int act, float slope, cudaStream_t st) {
+  if (!conv_umma_bf16_supported(d, 0)) { set_error("bf16 conv fprop: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  Problem pr = {};
+  fprop_problem(d, x, w, pr);
+  return run_problem_t<__nv_bfloat16>(pr, bias, (__nv_bfloat16*)y, act, slope, st, nullptr, nullptr);
+}
+
+int conv_dgrad_umma_bf16_launch(const srgan_conv_desc* d, const void* dy, const void* w, void* dx, void* ws,
+                                size_t ws_bytes, cudaStream_t st, const void* addend) {
+  if (!conv_umma_bf16_supported(d, 1)) { set_error("bf16 conv dgrad: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  if (addend && d->stride != 1) { set_error("bf16 conv dgrad: fused addend only for stride 1"); return SRGAN_E_UNSUPPORTED; }
+  const int T = d->R * d->S;
+  const size_t need = conv_umma_bf16_workspace(d, 1);
+  if (ws_bytes < need || !ws) { set_error("bf16 conv dgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  __nv_bfloat16* wt = (__nv_bfloat16*)ws;       // [C][T][K]
+  {
+    dim3 g(ceil_div(d->C, 32), ceil_div(d->K, 32), T);
+    filter_transpose_kernel<__nv_bfloat16><<<g, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)w, wt, d->K, T, d->C);
+  }
+  Problem pr = {};
+  dgrad_problem(d, dy, wt, pr);
+  return run_problem_t<__nv_bfloat16>(pr, nullptr, (__nv_bfloat16*)dx, SRGAN_ACT_NONE, 0.f, st, nullptr,
+                                      (const __nv_bfloat16*)addend);
 }
 
 void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st);

@@ -31,6 +31,10 @@ SIGNATURES = {
     "srgan_conv2d_fprop": (c_int, [DP, P, P, P, P, c_int, c_float, c_int, P, c_size_t, P]),
     "srgan_conv2d_dgrad": (c_int, [DP, P, P, P, c_int, P, c_size_t, P]),
     "srgan_conv2d_wgrad_plan": (c_int, [DP, P, P]),
+    "srgan_conv2d_bf16_supported": (c_int, [DP, c_int]),
+    "srgan_conv2d_bf16_workspace": (c_size_t, [DP, c_int]),
+    "srgan_conv2d_fprop_bf16": (c_int, [DP, P, P, P, P, c_int, c_float, P]),
+    "srgan_conv2d_dgrad_bf16": (c_int, [DP, P, P, P, P, P, c_size_t, P]),
     "srgan_conv2d_dgrad_add_supported": (c_int, [DP, c_int]),
     "srgan_conv2d_dgrad_add": (c_int, [DP, P, P, P, P, c_int, P, c_size_t, P]),
     "srgan_conv2d_wgrad": (c_int, [DP, P, P, P, P, c_int, P, c_size_t, P]),

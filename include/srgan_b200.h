@@ -86,16 +86,25 @@ int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, const float* dy
 int srgan_conv2d_dgrad_add_supported(const srgan_conv_desc* d, int engine);
 int srgan_conv2d_dgrad_add(const srgan_conv_desc* d, const float* dy, const float* w, const float* addend,
                            float* dx, int engine, void* workspace, size_t workspace_bytes, void* stream);
-/* introspection (tests, tools): pixel splits and CTAs of the tcgen05 wgrad launch for this layer (host only) */
-/* bf16 storage (experimental, next round): x, w, y, dy, dx, addend are NHWC / KRSC tensors of bfloat16 (passed as
- * void*), bias is fp32, accumulation fp32 in TMEM (tcgen05 kind::f16).  Plain layers only: reduction channels a
- * multiple of 64.  addend may be NULL (stride 1 only otherwise). */
+/* ---- bf16-storage engine (the generator's trunk; ref layers pyfiles/model.py:188-249).  x, w, y, dy, dx, addend are
+ * NHWC / KRSC tensors of bfloat16 (passed as void*), bias / dw are fp32, accumulation is fp32 in TMEM (tcgen05
+ * kind::f16).  Plain layers only: fprop needs C % 64 == 0, dgrad K % 64 == 0, wgrad both (pass: 0 fprop, 1 dgrad,
+ * 2 wgrad).  w is the bf16 shadow of the fp32 master filter (srgan_cast_f32_bf16).  addend may be NULL (stride 1 only
+ * otherwise).  wgrad writes dw[K][R][S][C] in fp32 (split partials in the workspace, fixed-order reduction). */
+#define SRGAN_DT_F32  0
+#define SRGAN_DT_BF16 1
 int srgan_conv2d_bf16_supported(const srgan_conv_desc* d, int pass);
 size_t srgan_conv2d_bf16_workspace(const srgan_conv_desc* d, int pass);
 int srgan_conv2d_fprop_bf16(const srgan_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                             int act, float slope, void* stream);
 int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                             void* workspace, size_t workspace_bytes, void* stream);
+int srgan_conv2d_wgrad_bf16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int srgan_conv2d_wgrad_bf16_plan(const srgan_conv_desc* d, int* splits, int* ctas);
+/* dst[i] = bf16(src[i]) (round to nearest even), n elements; both 16-byte aligned */
+int srgan_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
+/* introspection (tests, tools): pixel splits and CTAs of the tcgen05 wgrad launch for this layer (host only) */
 int srgan_conv2d_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
 /* which engine AUTO resolves to for this shape/pass: SRGAN_CONV_FP32 or SRGAN_CONV_TF32 */
 int srgan_conv2d_engine(const srgan_conv_desc* d, int pass);
@@ -134,6 +143,18 @@ int srgan_inorm_bwd(const float* dy, const float* x, const float* mean, const fl
                     void* workspace, size_t workspace_bytes, void* stream);
 int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma, const float* cbias,
                             float* dgamma, float* dbeta, float* dcbias, int N, int C, void* stream);
+/* Mixed storage: x / dx have dtype x_dtype, y / dy / residual have dtype y_dtype (SRGAN_DT_F32 or SRGAN_DT_BF16,
+ * independently); statistics, parameters and arithmetic stay fp32 (partials fp64).  Otherwise as srgan_inorm_fwd /
+ * srgan_inorm_bwd.  The generator uses f32 -> bf16 behind its RGB stem, bf16 -> bf16 in the trunk and bf16 -> f32 in
+ * front of the RGB head. */
+int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, float* mean, float* rstd,
+                          const float* gamma, const float* beta, const float* cbias, const void* residual,
+                          int N, int HW, int C, float eps, int act, float slope,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean,
+                          const float* rstd, const float* gamma, const float* beta, const float* cbias,
+                          void* dx, float* s1, float* s2, int N, int HW, int C, int act, float slope,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- batch-statistics norms
  * ref: CBBNorm2d / _CBBNorm.forward pyfiles/model.py:75-171 and nn.BatchNorm2d(affine=True) chosen by

@@ -45,6 +45,10 @@ int conv_fprop_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*
                                 cudaStream_t);
 int conv_dgrad_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, void*, void*, size_t, cudaStream_t,
                                 const void* addend);
+bool conv_umma_bf16_wgrad_supported(const srgan_conv_desc* d);
+size_t conv_umma_bf16_wgrad_workspace(const srgan_conv_desc* d);
+void conv_umma_bf16_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
+int conv_wgrad_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, float*, void*, size_t, cudaStream_t);
 
 static int check_desc(const srgan_conv_desc* d) {
   if (!d) { set_error("conv: null descriptor"); return SRGAN_E_BADARG; }
@@ -146,11 +150,27 @@ extern "C" int srgan_conv2d_wgrad(const srgan_conv_desc* d, const float* x, cons
 // ---- bf16 storage (experimental): NHWC bf16 activations, KRSC bf16 filters, fp32 bias and accumulation
 extern "C" int srgan_conv2d_bf16_supported(const srgan_conv_desc* d, int pass) {
   if (check_desc(d)) return 0;
+  if (pass == 2) return dense_x(d) && conv_umma_bf16_wgrad_supported(d) ? 1 : 0;
   return (pass == 1 || dense_x(d)) && conv_umma_bf16_supported(d, pass) ? 1 : 0;
 }
 extern "C" size_t srgan_conv2d_bf16_workspace(const srgan_conv_desc* d, int pass) {
   if (check_desc(d)) return 0;
+  if (pass == 2) return conv_umma_bf16_wgrad_supported(d) ? conv_umma_bf16_wgrad_workspace(d) : 0;
   return conv_umma_bf16_workspace(d, pass);
+}
+extern "C" int srgan_conv2d_wgrad_bf16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(x && dy && dw, "null pointer");
+  SRGAN_CHECK_ARG(dense_x(d), "bf16 conv: dense NHWC input only");
+  return conv_wgrad_umma_bf16_launch(d, x, dy, dw, ws, ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int srgan_conv2d_wgrad_bf16_plan(const srgan_conv_desc* d, int* splits, int* ctas) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(splits && ctas, "null pointer");
+  SRGAN_CHECK_ARG(conv_umma_bf16_wgrad_supported(d), "shape does not qualify for the bf16 wgrad");
+  conv_umma_bf16_wgrad_plan(d, splits, ctas);
+  return SRGAN_OK;
 }
 extern "C" int srgan_conv2d_fprop_bf16(const srgan_conv_desc* d, const void* x, const void* w, const float* bias,
                                        void* y, int act, float slope, void* stream) {

@@ -475,11 +475,32 @@ struct WgradCfg {
   static constexpr int kThreads = 32 * (5 + kProducers);      // warp 0 MMA, warps 1-4 epilogue, then producers
 };
 
-template <int BN, int KT, int PW>
+// Storage-type constants of the MN-major operand boxes.  A box is {kCh channels (one 128-byte row), kPix pixels}:
+//   fp32 / TF32 : 32 ch x 32 pixels = 4 KB, "128B swizzle with 32-byte atoms" (the only MN-major TF32 layout),
+//                 canonical K block = 4 pixel rows (SBO 512), one MMA = 8 pixels = 1024 B further;
+//   bf16        : 64 ch x 64 pixels = 8 KB, plain 128B swizzle (16-byte atoms), canonical K block = 8 pixel rows
+//                 (SBO 1024), one MMA (K = 16) = 16 pixels = 2048 B further.
+// Either way a 128-row operand tile of one pixel chunk is 16 KB (kABytes), a stage runs 4 MMAs per 128-row tile, and
+// a 32-column accumulator chunk is 32 output channels.
+template <typename ST> struct WgradElem;
+template <> struct WgradElem<float> {
+  static constexpr int kCh = 32, kPix = 32, kBoxBytes = 4096, kKStep = 64 /* 1024 B >> 4 */;
+  static constexpr uint32_t kFmt = 2, kLbo = 4096, kSbo = 512, kLayout = 1;
+  static constexpr CUtensorMapSwizzle kSwz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+};
+template <> struct WgradElem<__nv_bfloat16> {
+  static constexpr int kCh = 64, kPix = 64, kBoxBytes = 8192, kKStep = 128 /* 2048 B >> 4 */;
+  static constexpr uint32_t kFmt = 1, kLbo = 8192, kSbo = 1024, kLayout = 2;
+  static constexpr CUtensorMapSwizzle kSwz = CU_TENSOR_MAP_SWIZZLE_128B;
+};
+
+template <int BN, int KT, int PW, typename ST>
 __global__ void __launch_bounds__((WgradCfg<BN, KT, PW>::kThreads), 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ UmmaWgradP p, float* __restrict__ out) {
   using Cfg = WgradCfg<BN, KT, PW>;
+  using El = WgradElem<ST>;
+  constexpr int kDyBoxes = 128 / El::kCh;             // dY boxes per 128-filter sub-tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
@@ -491,13 +512,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int kt = blockIdx.x / p.tiles_c, ct = blockIdx.x % p.tiles_c;
   const int tap0 = blockIdx.y * p.gt;
   const int ntaps = min(p.gt, p.T - tap0);
-  const int nblk = ntaps * p.cpb;                     // 32-column N blocks of this CTA
+  const int nblk = ntaps * p.cpb;                     // kCh-column N blocks (one TMA box each) of this CTA
   const int k0 = kt * 128 * KT, c0 = ct * BN;
   const int ch_beg = blockIdx.z * p.chunks_per_split;
   const int ch_end = min(p.chunks, ch_beg + p.chunks_per_split);
   const int iters = ch_end - ch_beg;
   const int bw = 1 << p.lw, bh = 1 << p.lh;
-  const int bn = 32 >> (p.lw + p.lh);
+  const int bn = El::kPix >> (p.lw + p.lh);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kProducers); mbar_init(empty + s, 1); }
@@ -515,7 +536,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   if (warp >= 5) {
     if (lane == 0) {
       const int pw = warp - 5;
-      const int nboxes = KT * 4 + nblk;
+      const int nboxes = KT * kDyBoxes + nblk;
       int mine = 0;
       for (int b = pw; b < nboxes; b += Cfg::kProducers) ++mine;
       int stage = 0;
@@ -528,15 +549,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int q0 = tw * bw, p0 = th * bh, n0 = tn * bn;
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
-        mbar_expect_tx(full + stage, mine * 4096);
+        mbar_expect_tx(full + stage, mine * El::kBoxBytes);
         for (int b = pw; b < nboxes; b += Cfg::kProducers) {
-          if (b < KT * 4) {
-            tma_load_5d(&map_dy, full + stage, sa + b * 4096, k0 + 32 * b, q0, 0, p0, n0);
+          if (b < KT * kDyBoxes) {
+            tma_load_5d(&map_dy, full + stage, sa + b * El::kBoxBytes, k0 + El::kCh * b, q0, 0, p0, n0);
           } else {
-            const int j = b - KT * 4;
+            const int j = b - KT * kDyBoxes;
             const int4 tj = p.taps[tap0 + j / p.cpb];
-            tma_load_5d(&map_x, full + stage, sa + KT * kABytes + j * 4096, c0 + 32 * (j % p.cpb) + tj.x, q0 + tj.y, tj.z,
-                        p0 + tj.w, n0);
+            tma_load_5d(&map_x, full + stage, sa + KT * kABytes + j * El::kBoxBytes, c0 + El::kCh * (j % p.cpb) + tj.x,
+                        q0 + tj.y, tj.z, p0 + tj.w, n0);
           }
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -544,9 +565,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     }
   } else if (warp == 0) {
     if (lane == 0) {
-      // D = f32, A = B = tf32, both MN-major, N = 32 * nblk, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)((nblk * 32) >> 3) << 17) | ((128u >> 4) << 24);
+      // D = f32, A = B = tf32 or bf16, both MN-major, N = kCh * nblk, M = 128
+      const uint32_t idesc = (1u << 4) | (El::kFmt << 7) | (El::kFmt << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)((nblk * El::kCh) >> 3) << 17) | ((128u >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -558,8 +579,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         for (int t = 0; t < KT; ++t) {
           const uint64_t adesc = p.desc_hi | (uint64_t)(((sa + t * kABytes) >> 4) & 0x3FFF);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)     // 4 x 8 pixels; 8 pixel rows = 1024 B further (+64 in the address field)
-            umma_tf32(tmem_base + t * BN, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it | k) != 0);
+          for (int k = 0; k < 4; ++k)     // 4 x (8 tf32 | 16 bf16) pixels, each 1024 | 2048 B further
+            umma_any<ST>(tmem_base + t * BN, adesc + (uint64_t)(El::kKStep * k), bdesc + (uint64_t)(El::kKStep * k), idesc,
+                         (it | k) != 0);
         }
         umma_commit(empty + stage);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -577,9 +599,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       float* orow = out + (size_t)blockIdx.z * p.split_stride + ((size_t)k * p.T + tap0) * p.C + c0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * BN;
       // two 32-column chunks per trip: the TMEM load of the next chunk is in flight while this one is stored
-      const int ncols = nblk * 32;
+      const int ncols = nblk * El::kCh;
       auto put = [&](const uint32_t (&r)[32], int c) {
-        if (!(valid && c0 + (c % (p.cpb * 32)) < p.C)) return;
+        if (!(valid && c0 + (c % (p.cpb * El::kCh)) < p.C)) return;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -969,28 +991,29 @@ struct WgradPlan { int BN, KT, gt, cpb, ngroups, lw, lh, tiles_w, tiles_h, tiles
 
 static int pow2_at_least(int v, int lo) { int b = lo; while (b < v) b *= 2; return b; }
 
-static WgradPlan plan_wgrad(const srgan_conv_desc* d) {
+// ch / pix: channels and pixels of one operand box (WgradElem: 32 x 32 for fp32 storage, 64 x 64 for bf16)
+static WgradPlan plan_wgrad(const srgan_conv_desc* d, int ch = 32, int pix = 32) {
   WgradPlan w;
   const int T = d->R * d->S;
   if (d->C >= 256) {
-    w.BN = 256; w.cpb = 8; w.gt = 1; w.ngroups = T; w.tiles_c = ceil_div(d->C, 256);
+    w.BN = 256; w.cpb = 256 / ch; w.gt = 1; w.ngroups = T; w.tiles_c = ceil_div(d->C, 256);
   } else {
-    w.cpb = d->C / 32;
+    w.cpb = d->C / ch;
     int gt_max = 256 / d->C;
     if (gt_max < 1) gt_max = 1;
     w.ngroups = ceil_div(T, gt_max);
     w.gt = ceil_div(T, w.ngroups);
     w.tiles_c = 1;
-    w.BN = pow2_at_least(w.gt * d->C, 32);
+    w.BN = pow2_at_least(w.gt * d->C, ch);
   }
   w.KT = d->K > 128 ? 2 : 1;
   w.tiles_k = ceil_div(d->K, 128 * w.KT);
   int bw = 1 << ilog2(d->Q);
-  if (bw > 32) bw = 32;
+  if (bw > pix) bw = pix;
   int bh = 1 << ilog2(d->P);
-  if (bh > 32 / bw) bh = 32 / bw;
+  if (bh > pix / bw) bh = pix / bw;
   w.lw = ilog2(bw); w.lh = ilog2(bh);
-  int bn = 32 / (bw * bh);
+  int bn = pix / (bw * bh);
   w.tiles_w = ceil_div(d->Q, bw); w.tiles_h = ceil_div(d->P, bh); w.tiles_n = ceil_div(d->N, bn);
   w.chunks = w.tiles_w * w.tiles_h * w.tiles_n;
   // Pixel splits (split-K): one CTA per SM is resident, so the launch runs in ceil(CTAs / 148) rounds of
@@ -1187,29 +1210,32 @@ void splitk_reduce_launch(const float* part, float* out, long long n, int splits
 int colsum_launch(const float* x, float* out, long long rows, int C, float* scratch, int scratch_blocks,
                   cudaStream_t st);
 
-template <int BN, int KT, int PW>
+template <int BN, int KT, int PW, typename ST>
 static int launch_wgrad_pw(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
                            cudaStream_t st) {
   using Cfg = WgradCfg<BN, KT, PW>;
   static unsigned long long attr_done = 0;
   {
-    cudaError_t e = ensure_dyn_smem(wgrad_umma_kernel<BN, KT, PW>, (int)Cfg::kSmem, &attr_done);
+    cudaError_t e = ensure_dyn_smem(wgrad_umma_kernel<BN, KT, PW, ST>, (int)Cfg::kSmem, &attr_done);
     if (e != cudaSuccess) { set_error("wgrad_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  wgrad_umma_kernel<BN, KT, PW><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
+  wgrad_umma_kernel<BN, KT, PW, ST><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(mdy, mx, p, out);
   SRGAN_RETURN_LAUNCH();
 }
 
 // Producer warps: a stage of the widest tiles is 16 boxes of 4 KB; boxes issued by one warp complete one after the
 // other, so the wide tiles deal them to 8 warps.  Bring-up override: SRGAN_DBG_WGRAD_PW=4|8.
-template <int BN, int KT>
+template <int BN, int KT, typename ST>
 static int launch_wgrad_cfg(const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p, float* out, dim3 grid,
                             cudaStream_t st) {
   static const char* e_pw = getenv("SRGAN_DBG_WGRAD_PW");
-  const int pw = e_pw ? atoi(e_pw) : (KT * 4 + BN / 32 >= 12 ? 8 : 4);
-  if (pw == 16) return launch_wgrad_pw<BN, KT, 16>(mdy, mx, p, out, grid, st);
-  if (pw == 8) return launch_wgrad_pw<BN, KT, 8>(mdy, mx, p, out, grid, st);
-  return launch_wgrad_pw<BN, KT, 4>(mdy, mx, p, out, grid, st);
+  constexpr int boxes = (KT * 128 + BN) / WgradElem<ST>::kCh;      // TMA boxes of one full stage
+  const int pw = e_pw ? atoi(e_pw) : (boxes * WgradElem<ST>::kBoxBytes >= 12 * 4096 ? 8 : 4);
+  if constexpr (sizeof(ST) == 4) {
+    if (pw == 16) return launch_wgrad_pw<BN, KT, 16, ST>(mdy, mx, p, out, grid, st);
+  }
+  if (pw == 8) return launch_wgrad_pw<BN, KT, 8, ST>(mdy, mx, p, out, grid, st);
+  return launch_wgrad_pw<BN, KT, 4, ST>(mdy, mx, p, out, grid, st);
 }
 
 static int launch_wgrad(int BN, int KT, const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p_in,
@@ -1218,17 +1244,37 @@ static int launch_wgrad(int BN, int KT, const CUtensorMap& mdy, const CUtensorMa
   p.vec8 = (uintptr_t)out % 32 == 0 && p.C % 8 == 0 && p.split_stride % 8 == 0;
   if (KT == 2) {
     switch (BN) {
-      case 256: return launch_wgrad_cfg<256, 2>(mdy, mx, p, out, grid, st);
-      case 128: return launch_wgrad_cfg<128, 2>(mdy, mx, p, out, grid, st);
-      case 64:  return launch_wgrad_cfg<64, 2>(mdy, mx, p, out, grid, st);
-      default:  return launch_wgrad_cfg<32, 2>(mdy, mx, p, out, grid, st);
+      case 256: return launch_wgrad_cfg<256, 2, float>(mdy, mx, p, out, grid, st);
+      case 128: return launch_wgrad_cfg<128, 2, float>(mdy, mx, p, out, grid, st);
+      case 64:  return launch_wgrad_cfg<64, 2, float>(mdy, mx, p, out, grid, st);
+      default:  return launch_wgrad_cfg<32, 2, float>(mdy, mx, p, out, grid, st);
     }
   }
   switch (BN) {
-    case 256: return launch_wgrad_cfg<256, 1>(mdy, mx, p, out, grid, st);
-    case 128: return launch_wgrad_cfg<128, 1>(mdy, mx, p, out, grid, st);
-    case 64:  return launch_wgrad_cfg<64, 1>(mdy, mx, p, out, grid, st);
-    default:  return launch_wgrad_cfg<32, 1>(mdy, mx, p, out, grid, st);
+    case 256: return launch_wgrad_cfg<256, 1, float>(mdy, mx, p, out, grid, st);
+    case 128: return launch_wgrad_cfg<128, 1, float>(mdy, mx, p, out, grid, st);
+    case 64:  return launch_wgrad_cfg<64, 1, float>(mdy, mx, p, out, grid, st);
+    default:  return launch_wgrad_cfg<32, 1, float>(mdy, mx, p, out, grid, st);
+  }
+}
+
+// bf16 operands: N blocks are 64 channels wide, so the narrowest tile is 64 columns
+static int launch_wgrad_bf16(int BN, int KT, const CUtensorMap& mdy, const CUtensorMap& mx, const UmmaWgradP& p_in,
+                             float* out, dim3 grid, cudaStream_t st) {
+  using B = __nv_bfloat16;
+  UmmaWgradP p = p_in;
+  p.vec8 = (uintptr_t)out % 32 == 0 && p.C % 8 == 0 && p.split_stride % 8 == 0;
+  if (KT == 2) {
+    switch (BN) {
+      case 256: return launch_wgrad_cfg<256, 2, B>(mdy, mx, p, out, grid, st);
+      case 128: return launch_wgrad_cfg<128, 2, B>(mdy, mx, p, out, grid, st);
+      default:  return launch_wgrad_cfg<64, 2, B>(mdy, mx, p, out, grid, st);
+    }
+  }
+  switch (BN) {
+    case 256: return launch_wgrad_cfg<256, 1, B>(mdy, mx, p, out, grid, st);
+    case 128: return launch_wgrad_cfg<128, 1, B>(mdy, mx, p, out, grid, st);
+    default:  return launch_wgrad_cfg<64, 1, B>(mdy, mx, p, out, grid, st);
   }
 }
 
@@ -1370,6 +1416,79 @@ int conv_wgrad_umma_launch(const srgan_conv_desc* d, const float* x, const float
   dim3 grid(w.tiles_k * w.tiles_c, w.ngroups, w.splits);
   if (int e = launch_wgrad(w.BN, w.KT, mdy, mx, p, out, grid, st)) return e;
   if (w.splits > 1) splitk_reduce_launch(part, dw, (long long)d->K * T * C, w.splits, st);
+  SRGAN_RETURN_LAUNCH();
+}
+
+// ---- bf16 storage: x and dy are bf16 NHWC, dW (and the split partials) fp32 KRSC, dbias fp32
+bool conv_umma_bf16_wgrad_supported(const srgan_conv_desc* d) {
+  if (d->N < 1 || d->R * d->S > kMaxTaps) return false;
+  if (d->C % 64 || d->K % 64) return false;
+  if (d->C < 256 && 256 % d->C) return false;                 // tap groups: N = gt * C must tile 64-column blocks
+  return d->stride == 1 || (d->stride == 2 && d->H % 2 == 0 && d->W % 2 == 0);
+}
+
+size_t conv_umma_bf16_wgrad_workspace(const srgan_conv_desc* d) {
+  const WgradPlan w = plan_wgrad(d, 64, 64);
+  return w.splits > 1 ? (size_t)w.splits * d->K * d->R * d->S * d->C * sizeof(float) : 0;
+}
+
+void conv_umma_bf16_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas) {
+  const WgradPlan w = plan_wgrad(d, 64, 64);
+  *splits = w.splits;
+  *ctas = w.tiles_k * w.tiles_c * w.ngroups * w.splits;
+}
+
+int conv_wgrad_umma_bf16_launch(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* ws,
+                                size_t ws_bytes, cudaStream_t st) {
+  using El = WgradElem<__nv_bfloat16>;
+  if (!conv_umma_bf16_wgrad_supported(d)) { set_error("bf16 conv wgrad: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  const WgradPlan w = plan_wgrad(d, El::kCh, El::kPix);
+  const int T = d->R * d->S;
+  const size_t need = conv_umma_bf16_wgrad_workspace(d);
+  if (need > ws_bytes || (need && !ws)) { set_error("bf16 conv wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw | (uintptr_t)ws) % 16) {
+    set_error("tcgen05 wgrad: tensors must be 16-byte aligned");
+    return SRGAN_E_BADARG;
+  }
+  float* part = (float*)ws;
+  CUtensorMap mdy, mx;
+  const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = (uint32_t)El::kPix / (bw * bh);
+  const CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const uint64_t K = d->K, C = d->C;
+  {
+    uint64_t dims[5] = {K, (uint64_t)d->Q, 1, (uint64_t)d->P, (uint64_t)d->N};
+    uint64_t str[4] = {K * 2, (uint64_t)d->Q * K * 2, (uint64_t)d->Q * K * 2, (uint64_t)d->P * d->Q * K * 2};
+    uint32_t box[5] = {(uint32_t)El::kCh, bw, 1, bh, bn};
+    if (int e = encode_map(&mdy, dy, 5, dims, str, box, El::kSwz, DT)) return e;
+  }
+  if (d->stride == 1) {
+    uint64_t dims[5] = {C, (uint64_t)d->W, 1, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[4] = {C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2};
+    uint32_t box[5] = {(uint32_t)El::kCh, bw, 1, bh, bn};
+    if (int e = encode_map(&mx, x, 5, dims, str, box, El::kSwz, DT)) return e;
+  } else {
+    uint64_t dims[5] = {2 * C, (uint64_t)d->W / 2, 2, (uint64_t)d->H / 2, (uint64_t)d->N};
+    uint64_t str[4] = {2 * C * 2, (uint64_t)d->W * C * 2, (uint64_t)2 * d->W * C * 2, (uint64_t)d->H * d->W * C * 2};
+    uint32_t box[5] = {(uint32_t)El::kCh, bw, 1, bh, bn};
+    if (int e = encode_map(&mx, x, 5, dims, str, box, El::kSwz, DT)) return e;
+  }
+  UmmaWgradP p = {};
+  p.tiles_c = w.tiles_c; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
+  p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
+  p.K = d->K; p.C = d->C; p.T = T;
+  p.gt = w.gt; p.cpb = w.cpb;
+  p.split_stride = (long long)d->K * T * d->C;
+  p.desc_hi = mn_desc_hi(El::kLbo, El::kSbo, El::kLayout);
+  for (int r = 0; r < d->R; ++r)
+    for (int s2 = 0; s2 < d->S; ++s2) {
+      int a = r - d->pad, b = s2 - d->pad;
+      if (d->stride == 1) p.taps[r * d->S + s2] = make_int4(0, b, 0, a);
+      else p.taps[r * d->S + s2] = make_int4((((b % 2) + 2) % 2) * d->C, floordiv2(b), ((a % 2) + 2) % 2, floordiv2(a));
+    }
+  float* out = w.splits > 1 ? part : dw;
+  dim3 grid(w.tiles_k * w.tiles_c, w.ngroups, w.splits);
+  if (int e = launch_wgrad_bf16(w.BN, w.KT, mdy, mx, p, out, grid, st)) return e;
+  if (w.splits > 1) splitk_reduce_launch(part, dw, (long long)d->K * T * d->C, w.splits, st);
   SRGAN_RETURN_LAUNCH();
 }
 

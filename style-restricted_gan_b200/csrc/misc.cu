@@ -1,6 +1,7 @@
 // Memory-bound glue kernels: layout changes, reflect padding, pooling, activations,
 // conditional bias, softmax, reparametrisation.  NHWC fp32; vectorised (float4) where the
 // channel count allows, grid-stride loops sized to a multiple of the SM count.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace srgan {
@@ -237,6 +238,21 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dx[i] = dy[i] * act_grad_out(y[i], act, slope);
 }
+// dst = bf16(src), 8 elements (32 B in, 16 B out) per thread and trip
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  const size_t n8 = n / 8;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  GRID_STRIDE(i, n8) {
+    const float4 a = __ldg(s4 + 2 * i), b = __ldg(s4 + 2 * i + 1);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    d4[i] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                       *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+  }
+  for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
                            size_t n) {
   size_t n4 = n / 4;
@@ -447,6 +463,13 @@ extern "C" int srgan_act_bwd(const float* dy, const float* y, float* dx, size_t 
   SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) % 16 == 0, "pointers must be 16-byte aligned");
   if (n == 0) return SRGAN_OK;
   act_bwd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(dy, y, dx, n, act, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream) {
+  SRGAN_CHECK_ARG(src && dst, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)src | (uintptr_t)dst) % 16 == 0, "pointers must be 16-byte aligned");
+  if (n == 0) return SRGAN_OK;
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, ST>>>(src, (__nv_bfloat16*)dst, n);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_add(const float* a, const float* b, float* y, size_t n, void* stream) {

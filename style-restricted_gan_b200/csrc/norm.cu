@@ -14,6 +14,7 @@
 //             (2) apply       - dx = rstd*gamma * (dv - mean(dv) - xh * mean(dv*xh)).
 // Algorithmic traffic: forward 2 reads + 1 write of the plane (the second read is an L2 hit for planes that
 // fit the 126 MB L2), backward 4 reads + 1 write.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -94,39 +95,71 @@ __device__ __forceinline__ void fold_parts(const NormP& p, const V* __restrict__
   s1 = to_f4(t1); s2 = to_f4(t2);
 }
 
+// Storage-type views of an activation tensor as groups of 4 channels (16 B of fp32, 8 B of bf16): the kernels index
+// pixels / channel groups, the view does the load / store and the conversion.  Arithmetic is fp32 either way.
+template <typename T> struct In4;
+template <> struct In4<float> {
+  const float* p;
+  __device__ __forceinline__ In4 operator+(size_t i) const { return In4{p + 4 * i}; }
+  __device__ __forceinline__ float4 ld() const { return __ldg(reinterpret_cast<const float4*>(p)); }
+};
+template <> struct In4<__nv_bfloat16> {
+  const __nv_bfloat16* p;
+  __device__ __forceinline__ In4 operator+(size_t i) const { return In4{p + 4 * i}; }
+  __device__ __forceinline__ float4 ld() const {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xffff0000u));
+  }
+};
+template <typename T> struct Out4;
+template <> struct Out4<float> {
+  float* p;
+  __device__ __forceinline__ Out4 operator+(size_t i) const { return Out4{p + 4 * i}; }
+  __device__ __forceinline__ void st(const float4& v) const { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Out4<__nv_bfloat16> {
+  __nv_bfloat16* p;
+  __device__ __forceinline__ Out4 operator+(size_t i) const { return Out4{p + 4 * i}; }
+  __device__ __forceinline__ void st(const float4& v) const {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+
 // partial layout: part[(n * SL + slice) * q4 + c4], two planes (first, second moment) of N*SL*q4 V each
-template <typename V>
-__global__ void __launch_bounds__(kNormThreads, 4) inorm_stats_kernel(NormP p, const float* __restrict__ x,
+template <typename V, typename T = float>
+__global__ void __launch_bounds__(kNormThreads, 4) inorm_stats_kernel(NormP p, const T* __restrict__ x,
                                                                    V* __restrict__ part) {
   __shared__ V sa[kNormThreads], sb[kNormThreads];
   const NormIdx i = norm_idx(p);
   const int n = blockIdx.y;
-  const float4* xg = reinterpret_cast<const float4*>(x) + (size_t)n * p.HW * p.q4 + i.c4;
+  const In4<T> xg = In4<T>{x} + ((size_t)n * p.HW * p.q4 + i.c4);
   V s1 = vzero<V>(), s2 = vzero<V>();
   if (i.active) {
-    const float4 pv = __ldg(xg);                       // pivot: first pixel of the plane
+    const float4 pv = xg.ld();                       // pivot: first pixel of the plane
     const int step = p.RPP;
     int r = i.px0 + i.row;
 #define SRGAN_ACC(v, t1, t2) { float a = v.x - pv.x, b = v.y - pv.y, c = v.z - pv.z, d = v.w - pv.w; \
                        t1.x += a; t1.y += b; t1.z += c; t1.w += d; t2.x += a * a; t2.y += b * b; t2.z += c * c; t2.w += d * d; }
     if constexpr (sizeof(V) == sizeof(float4)) {
       for (; r + 3 * step < i.px1; r += 4 * step) {
-        float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
-        float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+        float4 v0 = (xg + (size_t)r * p.q4).ld(), v1 = (xg + (size_t)(r + step) * p.q4).ld();
+        float4 v2 = (xg + (size_t)(r + 2 * step) * p.q4).ld(), v3 = (xg + (size_t)(r + 3 * step) * p.q4).ld();
         SRGAN_ACC(v0, s1, s2) SRGAN_ACC(v1, s1, s2) SRGAN_ACC(v2, s1, s2) SRGAN_ACC(v3, s1, s2)
       }
-      for (; r < i.px1; r += step) { float4 v0 = __ldg(xg + (size_t)r * p.q4); SRGAN_ACC(v0, s1, s2) }
+      for (; r < i.px1; r += step) { float4 v0 = (xg + (size_t)r * p.q4).ld(); SRGAN_ACC(v0, s1, s2) }
     } else {
       for (; r + 3 * step < i.px1; r += 4 * step) {      // one atom per iteration
-        float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
-        float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+        float4 v0 = (xg + (size_t)r * p.q4).ld(), v1 = (xg + (size_t)(r + step) * p.q4).ld();
+        float4 v2 = (xg + (size_t)(r + 2 * step) * p.q4).ld(), v3 = (xg + (size_t)(r + 3 * step) * p.q4).ld();
         float4 a1 = f4(0.f), a2 = f4(0.f);
         SRGAN_ACC(v0, a1, a2) SRGAN_ACC(v1, a1, a2) SRGAN_ACC(v2, a1, a2) SRGAN_ACC(v3, a1, a2)
         acc4(s1, a1); acc4(s2, a2);
       }
       if (r < i.px1) {                                   // the image's last, incomplete atom
         float4 a1 = f4(0.f), a2 = f4(0.f);
-        for (; r < i.px1; r += step) { float4 v0 = __ldg(xg + (size_t)r * p.q4); SRGAN_ACC(v0, a1, a2) }
+        for (; r < i.px1; r += step) { float4 v0 = (xg + (size_t)r * p.q4).ld(); SRGAN_ACC(v0, a1, a2) }
         acc4(s1, a1); acc4(s2, a2);
       }
     }
@@ -140,16 +173,17 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_stats_kernel(NormP p, c
   }
 }
 
-template <typename V>
+// T: storage type of x (the producing convolution's output), TY: storage type of y and of the residual
+template <typename V, typename T = float, typename TY = T>
 __global__ void __launch_bounds__(kNormThreads, 4) inorm_apply_kernel(
-    NormP p, const float* __restrict__ x, const V* __restrict__ part, float* __restrict__ y,
+    NormP p, const T* __restrict__ x, const V* __restrict__ part, TY* __restrict__ y,
     float* mean_out, float* rstd_out, const float* __restrict__ gamma,
-    const float* __restrict__ beta, const float* __restrict__ cbias, const float* __restrict__ residual) {
+    const float* __restrict__ beta, const float* __restrict__ cbias, const TY* __restrict__ residual) {
   const NormIdx i = norm_idx(p);
   if (!i.active) return;
   const int n = blockIdx.y;
   const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
-  const float4* xg = reinterpret_cast<const float4*>(x) + plane;
+  const In4<T> xg = In4<T>{x} + plane;
   const int c = i.c4 * 4;
   float4 mu, rs;
   if (p.given) {
@@ -158,7 +192,7 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_apply_kernel(
   } else {
     float4 s1, s2;
     fold_parts(p, part, n, i.c4, s1, s2);
-    const float4 pv = __ldg(xg);
+    const float4 pv = xg.ld();
     const float inv = 1.f / (float)p.HW;
 #define SRGAN_STAT(f) { float m = s1.f * inv; float var = fmaxf(s2.f * inv - m * m, 0.f); mu.f = pv.f + m; rs.f = rsqrtf(var + p.eps); }
     SRGAN_STAT(x) SRGAN_STAT(y) SRGAN_STAT(z) SRGAN_STAT(w)
@@ -175,25 +209,26 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_apply_kernel(
   const float4 k = make_float4(rs.x * g.x, rs.y * g.y, rs.z * g.z, rs.w * g.w);
   const float4 o = make_float4((tb.x - mu.x * rs.x) * g.x + b.x, (tb.y - mu.y * rs.y) * g.y + b.y,
                                (tb.z - mu.z * rs.z) * g.z + b.z, (tb.w - mu.w * rs.w) * g.w + b.w);
-  float4* yg = reinterpret_cast<float4*>(y) + plane;
-  const float4* rg = residual ? reinterpret_cast<const float4*>(residual) + plane : nullptr;
+  const Out4<TY> yg = Out4<TY>{y} + plane;
+  const bool has_res = residual != nullptr;
+  const In4<TY> rg = In4<TY>{residual} + (has_res ? plane : 0);
   auto one = [&](float4 v, int r) {
     float4 t;
     t.x = apply_act(fmaf(v.x, k.x, o.x), p.act, p.slope);
     t.y = apply_act(fmaf(v.y, k.y, o.y), p.act, p.slope);
     t.z = apply_act(fmaf(v.z, k.z, o.z), p.act, p.slope);
     t.w = apply_act(fmaf(v.w, k.w, o.w), p.act, p.slope);
-    if (rg) acc4(t, __ldg(rg + (size_t)r * p.q4));
-    yg[(size_t)r * p.q4] = t;
+    if (has_res) acc4(t, (rg + (size_t)r * p.q4).ld());
+    (yg + (size_t)r * p.q4).st(t);
   };
   const int step = p.RPP;
   int r = i.px0 + i.row;
   for (; r + 3 * step < i.px1; r += 4 * step) {
-    float4 v0 = __ldg(xg + (size_t)r * p.q4), v1 = __ldg(xg + (size_t)(r + step) * p.q4);
-    float4 v2 = __ldg(xg + (size_t)(r + 2 * step) * p.q4), v3 = __ldg(xg + (size_t)(r + 3 * step) * p.q4);
+    float4 v0 = (xg + (size_t)r * p.q4).ld(), v1 = (xg + (size_t)(r + step) * p.q4).ld();
+    float4 v2 = (xg + (size_t)(r + 2 * step) * p.q4).ld(), v3 = (xg + (size_t)(r + 3 * step) * p.q4).ld();
     one(v0, r); one(v1, r + step); one(v2, r + 2 * step); one(v3, r + 3 * step);
   }
-  for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), r);
+  for (; r < i.px1; r += step) one((xg + (size_t)r * p.q4).ld(), r);
 }
 
 struct NormBwdConsts { float4 mu, rs, g, b, tb; };
@@ -220,9 +255,10 @@ __device__ __forceinline__ void norm_dv_xh(const NormP& p, const NormBwdConsts& 
   dv.w = dy.w * act_grad_pre((xh.w + k.tb.w) * k.g.w + k.b.w, p.act, p.slope);
 }
 
-template <typename V>
+// T: storage type of x and dx, TY: storage type of dy (= the forward output's)
+template <typename V, typename T = float, typename TY = T>
 __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_reduce_kernel(
-    NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    NormP p, const TY* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ cbias, V* __restrict__ part) {
   __shared__ V sa[kNormThreads], sb[kNormThreads];
@@ -231,8 +267,8 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_reduce_kernel(
   V a1 = vzero<V>(), a2 = vzero<V>();
   if (i.active) {
     const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
-    const float4* xg = reinterpret_cast<const float4*>(x) + plane;
-    const float4* dg = reinterpret_cast<const float4*>(dy) + plane;
+    const In4<T> xg = In4<T>{x} + plane;
+    const In4<TY> dg = In4<TY>{dy} + plane;
     const NormBwdConsts k = norm_bwd_consts(p, n, i.c4 * 4, mean, rstd, gamma, beta, cbias);
     auto one = [&](float4 xv, float4 dv_in, auto& t1, auto& t2) {
       float4 xh, dv;
@@ -244,22 +280,22 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_reduce_kernel(
     int r = i.px0 + i.row;
     if constexpr (sizeof(V) == sizeof(float4)) {
       for (; r + step < i.px1; r += 2 * step) {
-        float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
-        float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+        float4 x0 = (xg + (size_t)r * p.q4).ld(), d0 = (dg + (size_t)r * p.q4).ld();
+        float4 x1 = (xg + (size_t)(r + step) * p.q4).ld(), d1 = (dg + (size_t)(r + step) * p.q4).ld();
         one(x0, d0, a1, a2); one(x1, d1, a1, a2);
       }
-      for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4), a1, a2);
+      for (; r < i.px1; r += step) one((xg + (size_t)r * p.q4).ld(), (dg + (size_t)r * p.q4).ld(), a1, a2);
     } else {
       for (; r + step < i.px1; r += 2 * step) {          // one atom (2 rows of this thread) per iteration
-        float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
-        float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+        float4 x0 = (xg + (size_t)r * p.q4).ld(), d0 = (dg + (size_t)r * p.q4).ld();
+        float4 x1 = (xg + (size_t)(r + step) * p.q4).ld(), d1 = (dg + (size_t)(r + step) * p.q4).ld();
         float4 b1 = f4(0.f), b2 = f4(0.f);
         one(x0, d0, b1, b2); one(x1, d1, b1, b2);
         acc4(a1, b1); acc4(a2, b2);
       }
       if (r < i.px1) {
         float4 b1 = f4(0.f), b2 = f4(0.f);
-        one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4), b1, b2);
+        one((xg + (size_t)r * p.q4).ld(), (dg + (size_t)r * p.q4).ld(), b1, b2);
         acc4(a1, b1); acc4(a2, b2);
       }
     }
@@ -272,11 +308,11 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_reduce_kernel(
   }
 }
 
-template <typename V>
+template <typename V, typename T = float, typename TY = T>
 __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_apply_kernel(
-    NormP p, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    NormP p, const TY* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ cbias, const V* __restrict__ part, float* __restrict__ dx,
+    const float* __restrict__ cbias, const V* __restrict__ part, T* __restrict__ dx,
     float* s1_out, float* s2_out) {
   const NormIdx i = norm_idx(p);
   if (!i.active) return;
@@ -300,9 +336,9 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_apply_kernel(
     m2 = make_float4(S2.x * inv, S2.y * inv, S2.z * inv, S2.w * inv);
   }
   const size_t plane = (size_t)n * p.HW * p.q4 + i.c4;
-  const float4* xg = reinterpret_cast<const float4*>(x) + plane;
-  const float4* dg = reinterpret_cast<const float4*>(dy) + plane;
-  float4* og = reinterpret_cast<float4*>(dx) + plane;
+  const In4<T> xg = In4<T>{x} + plane;
+  const In4<TY> dg = In4<TY>{dy} + plane;
+  const Out4<T> og = Out4<T>{dx} + plane;
   auto one = [&](float4 xv, float4 dv_in, int r) {
     float4 xh, dv, o;
     norm_dv_xh(p, k, xv, dv_in, xh, dv);
@@ -310,16 +346,16 @@ __global__ void __launch_bounds__(kNormThreads, 4) inorm_bwd_apply_kernel(
     o.y = kk.y * (dv.y - m1.y - xh.y * m2.y);
     o.z = kk.z * (dv.z - m1.z - xh.z * m2.z);
     o.w = kk.w * (dv.w - m1.w - xh.w * m2.w);
-    og[(size_t)r * p.q4] = o;
+    (og + (size_t)r * p.q4).st(o);
   };
   const int step = p.RPP;
   int r = i.px0 + i.row;
   for (; r + step < i.px1; r += 2 * step) {
-    float4 x0 = __ldg(xg + (size_t)r * p.q4), d0 = __ldg(dg + (size_t)r * p.q4);
-    float4 x1 = __ldg(xg + (size_t)(r + step) * p.q4), d1 = __ldg(dg + (size_t)(r + step) * p.q4);
+    float4 x0 = (xg + (size_t)r * p.q4).ld(), d0 = (dg + (size_t)r * p.q4).ld();
+    float4 x1 = (xg + (size_t)(r + step) * p.q4).ld(), d1 = (dg + (size_t)(r + step) * p.q4).ld();
     one(x0, d0, r); one(x1, d1, r + step);
   }
-  for (; r < i.px1; r += step) one(__ldg(xg + (size_t)r * p.q4), __ldg(dg + (size_t)r * p.q4), r);
+  for (; r < i.px1; r += step) one((xg + (size_t)r * p.q4).ld(), (dg + (size_t)r * p.q4).ld(), r);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -930,6 +966,85 @@ extern "C" int srgan_inorm_bwd(const float* dy, const float* x, const float* mea
                                                                           (const float4*)ws, dx, s1, s2);
   }
   SRGAN_RETURN_LAUNCH();
+}
+
+// ---- mixed storage: x / dx and y / dy / residual are NHWC tensors of fp32 or bfloat16, independently (dtype codes
+// SRGAN_DT_F32 / SRGAN_DT_BF16); statistics, parameters and all arithmetic are fp32, the partial sums fp64.  The
+// generator's bf16 trunk uses (f32 -> bf16) behind the RGB stem, (bf16 -> bf16) inside and (bf16 -> f32) in front of
+// the RGB head, so the thin first / last layers keep their fp32 kernels without a conversion pass.
+template <typename TX, typename TY>
+static int inorm_fwd_typed(const NormP& p, const void* x, void* y, float* mean, float* rstd, const float* gamma,
+                           const float* beta, const float* cbias, const void* residual, void* ws, cudaStream_t st) {
+  inorm_stats_kernel<D4, TX><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TX*)x, (D4*)ws);
+  inorm_apply_kernel<D4, TX, TY><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TX*)x, (const D4*)ws, (TY*)y, mean, rstd,
+                                                                        gamma, beta, cbias, (const TY*)residual);
+  SRGAN_RETURN_LAUNCH();
+}
+
+template <typename TX, typename TY>
+static int inorm_bwd_typed(const NormP& p, const void* dy, const void* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, const float* cbias, void* dx, float* s1, float* s2,
+                           void* ws, cudaStream_t st) {
+  inorm_bwd_reduce_kernel<D4, TX, TY><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TY*)dy, (const TX*)x, mean, rstd,
+                                                                             gamma, beta, cbias, (D4*)ws);
+  inorm_bwd_apply_kernel<D4, TX, TY><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TY*)dy, (const TX*)x, mean, rstd,
+                                                                            gamma, beta, cbias, (const D4*)ws, (TX*)dx,
+                                                                            s1, s2);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, float* mean, float* rstd,
+                                     const float* gamma, const float* beta, const float* cbias, const void* residual,
+                                     int N, int HW, int C, float eps, int act, float slope, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  SRGAN_CHECK_ARG(x && y && mean && rstd, "null pointer");
+  SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
+  SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)residual | (uintptr_t)ws) % 16 == 0,
+                  "pointers must be 16-byte aligned");
+  SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
+  SRGAN_CHECK_ARG((x_dtype == SRGAN_DT_F32 || x_dtype == SRGAN_DT_BF16) &&
+                  (y_dtype == SRGAN_DT_F32 || y_dtype == SRGAN_DT_BF16), "unknown dtype code");
+  if (N == 0) return SRGAN_OK;
+  NormP p;
+  SRGAN_CHECK_ARG(plan_norm(N, HW, C, &p), "channel count cannot be mapped");
+  SRGAN_CHECK_ARG(norm_f64(), "mixed-storage norms need the fp64 partial sums");
+  p.eps = eps; p.slope = slope; p.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_fwd_mixed: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
+  using B = __nv_bfloat16;
+  const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
+  if (xb && yb) return inorm_fwd_typed<B, B>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
+  if (xb) return inorm_fwd_typed<B, float>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
+  if (yb) return inorm_fwd_typed<float, B>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
+  return inorm_fwd_typed<float, float>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
+}
+
+extern "C" int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean,
+                                     const float* rstd, const float* gamma, const float* beta, const float* cbias,
+                                     void* dx, float* s1, float* s2, int N, int HW, int C, int act, float slope,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  SRGAN_CHECK_ARG(dy && x && mean && rstd && dx && s1 && s2, "null pointer");
+  SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
+  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
+                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)dx | (uintptr_t)s1 | (uintptr_t)s2 |
+                   (uintptr_t)ws) % 16 == 0, "pointers must be 16-byte aligned");
+  SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
+  SRGAN_CHECK_ARG((x_dtype == SRGAN_DT_F32 || x_dtype == SRGAN_DT_BF16) &&
+                  (y_dtype == SRGAN_DT_F32 || y_dtype == SRGAN_DT_BF16), "unknown dtype code");
+  if (N == 0) return SRGAN_OK;
+  NormP p;
+  SRGAN_CHECK_ARG(plan_norm(N, HW, C, &p), "channel count cannot be mapped");
+  SRGAN_CHECK_ARG(norm_f64(), "mixed-storage norms need the fp64 partial sums");
+  p.eps = 0.f; p.slope = slope; p.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_bwd_mixed: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
+  using B = __nv_bfloat16;
+  const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
+  if (xb && yb) return inorm_bwd_typed<B, B>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
+  if (xb) return inorm_bwd_typed<B, float>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
+  if (yb) return inorm_bwd_typed<float, B>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
+  return inorm_bwd_typed<float, float>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
 }
 
 extern "C" int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma,

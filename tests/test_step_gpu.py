@@ -5,7 +5,7 @@ Tolerances (fp32 FFMA engine vs the fp32 CPU oracle; stated per quantity):
   losses 1e-4 relative; mu/logvar 1e-4; D gradients 1e-3; E phase-1 5e-3; G phase-1 1e-2 (L1-sign noise
   floor); phase 2 is compared with TEACHER FORCING (the oracle's post-step weights are injected
   into the product after phase 1) at 2e-2.
-With the tcgen05 TF32 engine: losses 5e-3, gradients 1e-1 (norm-level)."""
+With the tcgen05 TF32 engine: 3 x the measured values, see TF32_TOL below."""
 import numpy as np
 import pytest
 import torch
@@ -94,11 +94,13 @@ def _compare(name, engine, t):
         assert abs(got - ref) <= t["loss"] * max(1.0, abs(ref)), (errs, errs_o)
     k = cases.CASES[name]["k"]
     if cases.CASES[name]["kind"] == "single_multi":
-        for i in range(cases.N_CLASS):
-            assert _rel_all(rec["Dc%d_%d.grad" % (i, k - 1)], rec_o["Dc%d_%d.grad" % (i, k - 1)]) < t["D"]
+        dmax = max(_rel_all(rec["Dc%d_%d.grad" % (i, k - 1)], rec_o["Dc%d_%d.grad" % (i, k - 1)])
+                   for i in range(cases.N_CLASS))
     else:
-        for it in range(k):
-            assert _rel_all(rec["D%d.grad" % it], rec_o["D%d.grad" % it]) < t["D"], it
+        dmax = max(_rel_all(rec["D%d.grad" % it], rec_o["D%d.grad" % it]) for it in range(k))
+    lmax = max(abs(got - ref) / max(1.0, abs(ref)) for got, ref in zip(errs, errs_o))
+    print("%s[%s] loss rel %.2e | D %.2e" % (name, engine, lmax, dmax))
+    assert dmax < t["D"], dmax
     e0, g0 = _rel_all(rec["E0.grad"], rec_o["E0.grad"]), _rel_all(rec["G0.grad"], rec_o["G0.grad"])
     g1, e1 = _rel_all(rec["G1.grad"], rec_o["G1.grad"]), _rel_all(rec["E_final.grad"], rec_o["E_final.grad"])
     print("%s[%s] losses %s vs %s | E0 %.2e G0 %.2e | G1 %.2e E_final %.2e" % (name, engine, errs, errs_o, e0, g0, g1, e1))
@@ -107,7 +109,11 @@ def _compare(name, engine, t):
 
 
 FP32_TOL = dict(loss=1e-4, D=1e-3, E0=5e-3, G0=1e-2, P2=2e-2)
-TF32_TOL = dict(loss=5e-3, D=5e-2, E0=2e-1, G0=3e-1, P2=5e-1)
+# TF32 engine, full-width nets at batch 2, k = 1.  Measured on B200 (round 2, printed by the test): losses 7.8e-5,
+# E0 4.8e-2, G0 1.1e-1, phase 2 1.3e-1 / 6.5e-2.  The gradient figures are NORM-level distances of whole-network
+# gradients whose loss contains L1 terms and ReLU masks: a pre-activation within TF32 rounding of zero flips a mask and
+# the reference itself moves by 8.5e-2 between thread counts.  Bounds = 3 x measured.
+TF32_TOL = dict(loss=3e-4, D=3e-2, E0=1.5e-1, G0=3.2e-1, P2=4e-1)
 
 
 @pytest.mark.parametrize("name", ["srgan_small", "single_solo_small", "single_multi_small", "srgan_frozen_small"])

@@ -149,7 +149,10 @@ def time_dominant_kernel(batch, dev):
     """CUDA-event time of the dominant kernel alone: the residual-block convolution forward
     (3x3, 256->256 channels, 32x32, batch `batch`) through the C ABI, L2 flushed between launches."""
     import srgan_ops as ops
+    bf16 = ops.get_conv_engine() == "bf16"
     x = torch.randn(batch, 256, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
+    if bf16:
+        x = x.to(torch.bfloat16)          # the trunk's storage type (channels-last is preserved)
     w = (torch.randn(256, 256, 3, 3, device=dev) * 0.02).contiguous(memory_format=torch.channels_last)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(3):
@@ -168,13 +171,15 @@ def time_dominant_kernel(batch, dev):
     flops = 2.0 * batch * 1024 * 256 * 2304
     d = ops._desc(batch, 32, 32, 256, 256, 3, 3, 1, 1)
     engine = ops._lib().srgan_conv2d_engine(d, 0)
-    return ms, flops, ("tcgen05_tf32" if engine == 2 else "ffma_fp32")
+    return ms, flops, ("tcgen05_bf16" if bf16 else ("tcgen05_tf32" if engine == 2 else "ffma_fp32"))
 
 
 def time_norm_kernel(batch, dev):
     """CUDA-event time of the fused instance-norm forward on [batch, 256, 32, 32], L2 flushed between launches."""
     import srgan_ops as ops
     x = torch.randn(batch, 256, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
+    if ops.get_conv_engine() == "bf16":
+        x = x.to(torch.bfloat16)
     g, b = torch.ones(256, device=dev), torch.zeros(256, device=dev)
     cb = torch.randn(batch, 256, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -462,7 +467,7 @@ def run_ours(args):
         # secondary roofline: the fused instance-norm (+ conditional bias + affine + ReLU) forward of the residual
         # blocks, HBM bound; algorithmic bytes = read x + write y
         nms = time_norm_kernel(batch, dev)
-        nbytes = 2.0 * 4 * batch * 256 * 1024
+        nbytes = 2.0 * (4 if is_tf32 or kname == "ffma_fp32" else 2) * batch * 256 * 1024
         glue = {"bound": "hbm", "kernel": "instance norm + cond. bias + affine + ReLU forward, 256 ch @32x32",
                 "achieved": nbytes / (nms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": nbytes / (nms * 1e-3) / 1e9 / pk["hbm"], "kernel_ms": nms,

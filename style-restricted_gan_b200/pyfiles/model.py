@@ -66,8 +66,8 @@ class _KernelInstanceNorm2d(nn.Module):
             raise NotImplementedError("plain InstanceNorm2d is only used with affine=False here")
         self.num_features, self.eps = num_features, eps
 
-    def forward(self, x, act=ops.ACT_NONE, slope=0.0):
-        return ops.instance_norm_act(x, eps=self.eps, act=act, slope=slope)
+    def forward(self, x, act=ops.ACT_NONE, slope=0.0, out_dtype=None):
+        return ops.instance_norm_act(x, eps=self.eps, act=act, slope=slope, out_dtype=out_dtype)
 
 
 def _activation_of(module):
@@ -123,11 +123,11 @@ class _CBINorm(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                                       error_msgs)
 
-    def forward(self, input, ConInfor, act=ops.ACT_NONE, slope=0.0, residual=None):
+    def forward(self, input, ConInfor, act=ops.ACT_NONE, slope=0.0, residual=None, out_dtype=None):
         self._check_input_dim(input)
         lin = self.ConBias[0]
         t = ops.cond_bias(ConInfor, lin.weight, lin.bias)
-        return ops.instance_norm_act(input, self.weight, self.bias, t, residual, self.eps, act, slope)
+        return ops.instance_norm_act(input, self.weight, self.bias, t, residual, self.eps, act, slope, out_dtype)
 
     def extra_repr(self):
         return "{num_features}, eps={eps}, affine={affine}".format(**self.__dict__)
@@ -309,12 +309,28 @@ class SingleGenerator(nn.Module):
         self.up_convs = nn.ModuleList(ups)
         self.up_norms = nn.ModuleList(norms)
 
+    def _bf16_trunk(self):
+        """Engine 'bf16': everything between the RGB stem and the RGB head keeps bf16 activations - the first
+        conditional norm converts on its way out (fp32 in, bf16 out), the last up-path norm on its way back (bf16 in,
+        fp32 out), so both thin RGB layers keep their fp32 kernels and no conversion pass exists.  Needs instance
+        norms (no batch-coupled statistics in bf16) and trunk widths that are multiples of 64."""
+        if not ops.bf16_trunk_enabled() or self.num_cls < 1:
+            return False
+        if self.down_convs[0].out_channels % 64:
+            return False
+        norms = list(self.down_cnorms) + list(self.up_norms)
+        return all(isinstance(m, (_CBINorm, _KernelInstanceNorm2d)) for m in norms) and \
+            all(isinstance(b.cn1, _CBINorm) and isinstance(b.cn2, _CBINorm) for b in self.resBlocks)
+
     def forward(self, x, c):
+        lo = torch.bfloat16 if self._bf16_trunk() else None
         for conv, cnorm in zip(self.down_convs, self.down_cnorms):
-            x = cnorm(conv(x), c, act=ops.ACT_RELU)
+            x = cnorm(conv(x), c, act=ops.ACT_RELU, out_dtype=lo)
         x = self.resBlocks([x, c])[0]
         for i in range(self.num_cls):
-            x = self.up_norms[i](self.up_convs[i](x), act=ops.ACT_RELU)
+            last = i == self.num_cls - 1
+            x = self.up_norms[i](self.up_convs[i](x), act=ops.ACT_RELU,
+                                 out_dtype=torch.float32 if (last and lo is not None) else None)
         return self.up_convs[-1](x, act=ops.ACT_TANH)
 
 

@@ -24,20 +24,33 @@ from _srgan_lib import ConvDesc, SrganKernelError, check
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TF32 = 0, 1, 2
 _ENGINE_NAMES = {"auto": ENGINE_AUTO, "fp32": ENGINE_FP32, "tf32": ENGINE_TF32}
-_engine = _ENGINE_NAMES[os.environ.get("SRGAN_CONV_ENGINE", "auto").lower()]
+DT_F32, DT_BF16 = 0, 1
+BF16 = torch.bfloat16
 
 CL = torch.channels_last
 abi_calls = 0          # number of C-ABI kernel entry points invoked (bench: gpu_launches)
 
 
 def set_conv_engine(name):
-    """'auto' (tcgen05 where the shape qualifies), 'fp32' (exact FFMA) or 'tf32' (force tcgen05)."""
-    global _engine
-    _engine = _ENGINE_NAMES[name]
+    """'auto' (tcgen05 TF32 on fp32 storage where the shape qualifies), 'fp32' (exact FFMA), 'tf32' (force tcgen05)
+    or 'bf16': like 'auto', and the generator keeps the activations of its trunk (everything between the RGB stem and
+    the RGB head) in bfloat16 and runs those convolutions on tcgen05 kind::f16 with bf16 shadows of the fp32 master
+    weights (fp32 accumulation, fp32 statistics, fp32 gradients and optimizer state)."""
+    global _engine, _bf16
+    _bf16 = name == "bf16"
+    _engine = ENGINE_AUTO if _bf16 else _ENGINE_NAMES[name]
 
 
 def get_conv_engine():
-    return {v: k for k, v in _ENGINE_NAMES.items()}[_engine]
+    return "bf16" if _bf16 else {v: k for k, v in _ENGINE_NAMES.items()}[_engine]
+
+
+def bf16_trunk_enabled():
+    return _bf16
+
+
+_engine, _bf16 = ENGINE_AUTO, False
+set_conv_engine(os.environ.get("SRGAN_CONV_ENGINE", "auto").lower())
 
 
 def _lib():
@@ -59,10 +72,10 @@ def _req(*ts):
     for t in ts:
         if t is None:
             continue
-        if not t.is_cuda or t.dtype != torch.float32:
+        if not t.is_cuda or (t.dtype != torch.float32 and t.dtype != BF16):
             raise SrganKernelError(
-                "srgan_b200 operators need CUDA float32 tensors (got %s on %s); there is no CPU fallback"
-                % (t.dtype, t.device))
+                "srgan_b200 operators need CUDA float32 tensors (bfloat16 inside the bf16 trunk; got %s on %s); there "
+                "is no CPU fallback" % (t.dtype, t.device))
         if cur is None:
             cur = torch._C._cuda_getDevice()
         if t.device.index != cur:
@@ -284,6 +297,9 @@ def _raw_to_nhwc(x):
     """No-autograd conversion of a 4-D tensor to channels-last storage with our kernel."""
     if _dense_nhwc(x):
         return x
+    if x.dtype != torch.float32:
+        raise SrganKernelError("bf16 activations only exist in channels-last storage (produced by these kernels); "
+                               "got strides %s" % (tuple(x.stride()),))
     if not x.is_contiguous():
         x = x.contiguous()
     N, C, H, W = x.shape
@@ -325,8 +341,13 @@ def to_nhwc(x):
     return _ToNHWC.apply(x)
 
 
-def _empty_nhwc(N, C, H, W, like):
-    return torch.empty((N, C, H, W), dtype=torch.float32, device=like.device, memory_format=CL)
+def _empty_nhwc(N, C, H, W, like, dtype=None):
+    return torch.empty((N, C, H, W), dtype=like.dtype if dtype is None else dtype, device=like.device,
+                       memory_format=CL)
+
+
+def _dt(t):
+    return DT_BF16 if t.dtype == BF16 else DT_F32
 
 
 # ----------------------------------------------------------------------------- convolution
@@ -347,12 +368,60 @@ def _krsc(w):
     return _raw_to_nhwc(w.detach())
 
 
+def cast_bf16(src, dst):
+    """dst (bf16, same storage order and size as src) = round-to-nearest-even(src fp32)."""
+    _call("srgan_cast_f32_bf16", _p(src), _p(dst), src.numel(), _stream())
+
+
+def _shadow16(w):
+    """bf16 shadow of an fp32 filter parameter, in the parameter's own storage order (KRSC for 4-D filters).
+    Parameters owned by a FusedAdam share one flat bf16 buffer that the optimizer refreshes after every step (the
+    backward passes read weights LIVE, see the module docstring, and so do they read the live shadow); any other
+    in-place change of the parameter (load_state_dict, copy_) bumps its version counter and refreshes the shadow on
+    next use."""
+    sh = getattr(w, "_srgan_bf16", None)
+    ver, ptr = w._version, w.data_ptr()
+    if sh is not None and sh[1] == ver and sh[2] == ptr:
+        return sh[0]
+    owner = getattr(w, "_srgan_owner", None)
+    with torch.no_grad():
+        if owner is not None and owner[0]["p"].data_ptr() <= ptr < owner[0]["p"].data_ptr() + owner[0]["p"].numel() * 4:
+            st, view, o, k = owner
+            if st.get("p16") is None:
+                st["p16"] = torch.empty(st["p"].numel(), dtype=BF16, device=st["p"].device)
+                cast_bf16(st["p"], st["p16"])
+            else:
+                cast_bf16(st["p"][o:o + k], st["p16"][o:o + k])
+            t = view(st["p16"])
+        else:
+            src = _krsc(w) if w.dim() == 4 else w.detach().contiguous()
+            t = sh[0] if sh is not None and sh[0].shape == w.shape else torch.empty_like(src, dtype=BF16)
+            cast_bf16(src, t)
+    w._srgan_bf16 = (t, ver, ptr)
+    return t
+
+
 def _conv_weight(w, like):
-    """The filter tensor a convolution on `like`-typed activations reads (fp32 storage: the parameter itself)."""
-    return w
+    """The filter tensor a convolution on `like`-typed activations reads: the KRSC fp32 parameter, or its bf16 shadow."""
+    return _shadow16(w) if like.dtype == BF16 else _krsc(w)
+
+
+def _need16(d, p):
+    if not _lib().srgan_conv2d_bf16_supported(d, p):
+        raise SrganKernelError(
+            "bf16 convolution (%s) not available for N=%d C=%d K=%d %dx%d stride %d: the bf16 trunk needs channel "
+            "counts that are multiples of 64" % (("fprop", "dgrad", "wgrad")[p], d.N, d.C, d.K, d.R, d.S, d.stride))
 
 
 def _fprop(d, x, w, bias, act, slope, out_dtype=None):
+    """w: the filter in the storage `x` asks for (see _conv_weight)."""
+    if x.dtype == BF16:
+        y = _empty_nhwc(d.N, d.K, d.P, d.Q, x)
+        if y.numel() == 0:
+            return y
+        _need16(d, 0)
+        _call("srgan_conv2d_fprop_bf16", d, _p(x), _p(w), _p(bias), _p(y), act, slope, _stream())
+        return y
     y = _empty_nhwc(d.N, d.K, d.P, d.Q, x)
     if y.numel() == 0:
         return y
@@ -365,10 +434,23 @@ def _fprop(d, x, w, bias, act, slope, out_dtype=None):
 
 def _dgrad(d, dy, w, like, addend=None):
     """dx = dgrad(dy) (+ addend, fused into the epilogue where the engine supports it)."""
-    dx = _empty_nhwc(d.N, d.C, d.H, d.W, like)
+    dx = _empty_nhwc(d.N, d.C, d.H, d.W, like, dtype=dy.dtype)
     if dx.numel() == 0:
         return dx
     lib = _lib()
+    if dy.dtype == BF16:
+        _need16(d, 1)
+        nb = lib.srgan_conv2d_bf16_workspace(d, 1)
+        ws = _workspace(dy.device, nb) if nb else None
+        fused = addend is not None and d.stride == 1
+        if addend is not None:
+            addend = _raw_to_nhwc(addend)
+            if addend.dtype != BF16:
+                raise SrganKernelError("dgrad: the skip gradient must have the storage type of dy")
+        _call("srgan_conv2d_dgrad_bf16", d, _p(dy), _p(w), _p(addend) if fused else None, _p(dx), _p(ws), nb, _stream())
+        if addend is not None and not fused:
+            dx.add_(addend)
+        return dx
     nb = lib.srgan_conv2d_workspace(d, 1, _engine)
     ws = _workspace(dy.device, nb) if nb else None
     if addend is not None:
@@ -428,6 +510,15 @@ def _wgrad(d, x, dy, want_w, want_b, dw_out=None, db_out=None):
             db.zero_()
         return dw, db
     lib = _lib()
+    if x.dtype == BF16 or dy.dtype == BF16:
+        if x.dtype != dy.dtype or want_b or db is not None:
+            raise SrganKernelError("bf16 wgrad: x and dy must both be bf16 and the layer bias-free")
+        _need16(d, 2)
+        nb = lib.srgan_conv2d_bf16_workspace(d, 2)
+        ws = _workspace(x.device, nb) if nb else None
+        if dw is not None:
+            _call("srgan_conv2d_wgrad_bf16", d, _p(x), _p(dy), _p(dw), _p(ws), nb, _stream())
+        return dw, None
     nb = lib.srgan_conv2d_workspace(d, 2, _engine)
     ws = _workspace(x.device, nb) if nb else None
     _call("srgan_conv2d_wgrad", d, _p(x), _p(dy), _p(dw), _p(db), _engine, _p(ws), nb, _stream())
@@ -446,6 +537,8 @@ def wgrad_plan(d):
 def _act_bwd(dy, y, act, slope):
     if act == ACT_NONE:
         return dy
+    if dy.dtype != torch.float32:
+        raise SrganKernelError("fused conv activations are fp32-only (the bf16 trunk activates in its norm kernels)")
     dz = torch.empty_like(y)
     _call("srgan_act_bwd", _p(dy), _p(y), _p(dz), y.numel(), act, slope, _stream())
     return dz
@@ -462,7 +555,7 @@ class _Conv2dFn(torch.autograd.Function):
         if C2 != C:
             raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
         d = _desc(N, H, W, C, K, R, S, stride, pad)
-        y = _fprop(d, x, _krsc(weight), bias, act, slope)
+        y = _fprop(d, x, _conv_weight(weight, x), bias, act, slope)
         ctx.d, ctx.act, ctx.slope = d, act, slope
         ctx.weight, ctx.bias, ctx.has_bias = weight, bias, bias is not None
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
@@ -474,7 +567,7 @@ class _Conv2dFn(torch.autograd.Function):
         dz = _act_bwd(_raw_to_nhwc(dy), y, ctx.act, ctx.slope)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _dgrad(ctx.d, dz, _krsc(ctx.weight), x)       # live weight (see module docstring)
+            dx = _dgrad(ctx.d, dz, _conv_weight(ctx.weight, dz), x)       # live weight (see module docstring)
         want_w = ctx.needs_input_grad[1]
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_w or want_b:
@@ -498,7 +591,7 @@ class _Conv2dSkipFn(torch.autograd.Function):
         if C2 != C:
             raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
         d = _desc(N, H, W, C, K, R, S, stride, pad)
-        y = _fprop(d, x, _krsc(weight), None, ACT_NONE, 0.0)
+        y = _fprop(d, x, _conv_weight(weight, x), None, ACT_NONE, 0.0)
         ctx.d, ctx.weight = d, weight
         ctx.save_for_backward(x)
         return y, x.view_as(x)
@@ -509,7 +602,7 @@ class _Conv2dSkipFn(torch.autograd.Function):
         dz = _raw_to_nhwc(dy)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _dgrad(ctx.d, dz, _krsc(ctx.weight), x, addend=dskip)      # live weight (see module docstring)
+            dx = _dgrad(ctx.d, dz, _conv_weight(ctx.weight, dz), x, addend=dskip)      # live weight (see module docstring)
         if ctx.needs_input_grad[1]:
             sink = _grad_sink(ctx.weight, True, True)
             dw, _ = _wgrad(ctx.d, x, dz, True, False, sink)
@@ -532,7 +625,7 @@ class _ConvTranspose2dFn(torch.autograd.Function):
         Wo = (W - 1) * stride - 2 * pad + S
         d = _desc(N, Ho, Wo, Cout, Cin, R, S, stride, pad)     # mirrored conv: (Ho,Wo,Cout) -> (H,W,Cin)
         assert d.P == H and d.Q == W
-        y = _dgrad(d, x, _krsc(weight), x)
+        y = _dgrad(d, x, _conv_weight(weight, x), x)
         ctx.d, ctx.weight = d, weight
         ctx.save_for_backward(x)
         return y
@@ -543,7 +636,7 @@ class _ConvTranspose2dFn(torch.autograd.Function):
         dy = _raw_to_nhwc(dy)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _fprop(ctx.d, dy, _krsc(ctx.weight), None, ACT_NONE, 0.0)
+            dx = _fprop(ctx.d, dy, _conv_weight(ctx.weight, dy), None, ACT_NONE, 0.0)
         if ctx.needs_input_grad[1]:
             sink = _grad_sink(ctx.weight, True, True)
             dw, _ = _wgrad(ctx.d, dy, x, True, False, sink)
@@ -674,27 +767,38 @@ def cond_bias(con, weight, bias):
 
 class _InstanceNormFn(torch.autograd.Function):
     """y = act(((x-mean)*rstd + cbias) * gamma + beta) (+ residual).
-    ref: CBINorm2d.forward pyfiles/model.py:54-67, nn.InstanceNorm2d(affine=False) :178, ReLU/LeakyReLU/add."""
+    ref: CBINorm2d.forward pyfiles/model.py:54-67, nn.InstanceNorm2d(affine=False) :178, ReLU/LeakyReLU/add.
+    `out_dtype`: storage type of y (and of the residual): fp32 or bf16 independently of x's (srgan_inorm_*_mixed);
+    dx comes back in x's storage type, dy arrives in y's."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, cbias, residual, eps, act, slope):
+    def forward(ctx, x, gamma, beta, cbias, residual, eps, act, slope, out_dtype):
         x = _raw_to_nhwc(x)
         N, C, H, W = x.shape
+        out_dtype = x.dtype if out_dtype is None else out_dtype
         if residual is not None:
             residual = _raw_to_nhwc(residual)
+            if residual.dtype != out_dtype:
+                raise SrganKernelError("instance_norm_act: the residual must have the output's storage type")
         if cbias is not None:
             cbias = cbias.contiguous()
-        y = torch.empty_like(x)
+        y = torch.empty_like(x, dtype=out_dtype)
         mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
         rstd = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        mixed = x.dtype != torch.float32 or out_dtype != torch.float32
         if x.numel():
             nb = _lib().srgan_inorm_workspace(N, H * W, C)
             ws = _workspace(x.device, nb)
-            _call("srgan_inorm_fwd", _p(x), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias),
-                  _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb, _stream())
+            if mixed:
+                _call("srgan_inorm_fwd_mixed", _p(x), _dt(x), _p(y), _dt(y), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                      _p(cbias), _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb, _stream())
+            else:
+                _call("srgan_inorm_fwd", _p(x), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias),
+                      _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb, _stream())
         ctx.gamma, ctx.beta = gamma, beta
         ctx.act, ctx.slope = act, slope
         ctx.has_res = residual is not None
+        ctx.out_dtype, ctx.mixed = out_dtype, mixed
         ctx.save_for_backward(x, mean, rstd, cbias)
         return y
 
@@ -704,14 +808,21 @@ class _InstanceNormFn(torch.autograd.Function):
         gamma, beta = ctx.gamma, ctx.beta
         N, C, H, W = x.shape
         dy = _raw_to_nhwc(dy)
+        if dy.dtype != ctx.out_dtype:
+            raise SrganKernelError("instance_norm_act backward: dy is %s, the forward output was %s"
+                                   % (dy.dtype, ctx.out_dtype))
         dx = torch.empty_like(x)
         s1 = torch.empty((N, C), dtype=torch.float32, device=x.device)
         s2 = torch.empty((N, C), dtype=torch.float32, device=x.device)
         if x.numel():
             nb = _lib().srgan_inorm_workspace(N, H * W, C)
             ws = _workspace(x.device, nb)
-            _call("srgan_inorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(dx),
-                  _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
+            if ctx.mixed:
+                _call("srgan_inorm_bwd_mixed", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                      _p(cbias), _p(dx), _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
+            else:
+                _call("srgan_inorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(dx),
+                      _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
         dgamma = dbeta = dcb = None
         need_g = gamma is not None and ctx.needs_input_grad[1]
         need_b = beta is not None and ctx.needs_input_grad[2]
@@ -726,10 +837,11 @@ class _InstanceNormFn(torch.autograd.Function):
             dgamma = None if sink_g is not None else dgamma
             dbeta = None if sink_b is not None else dbeta
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
-        return (dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, dcb, dres, None, None, None
+        return (dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, dcb, dres, None, None, None, None
 
 
-def instance_norm_act(x, gamma=None, beta=None, cbias=None, residual=None, eps=1e-5, act=ACT_NONE, slope=0.0):
+def instance_norm_act(x, gamma=None, beta=None, cbias=None, residual=None, eps=1e-5, act=ACT_NONE, slope=0.0,
+                      out_dtype=None):
     _req(x, gamma, beta, cbias, residual)
     if x.dim() != 4:
         raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
@@ -737,7 +849,9 @@ def instance_norm_act(x, gamma=None, beta=None, cbias=None, residual=None, eps=1
         raise SrganKernelError("instance_norm_act: channel count must be a multiple of 8 (got %d)" % x.shape[1])
     if residual is not None and act != ACT_NONE:
         raise ValueError("residual add is only fused with act=none")
-    return _InstanceNormFn.apply(x, gamma, beta, cbias, residual, float(eps), int(act), float(slope))
+    if out_dtype not in (None, torch.float32, BF16):
+        raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+    return _InstanceNormFn.apply(x, gamma, beta, cbias, residual, float(eps), int(act), float(slope), out_dtype)
 
 
 def _gather_rows(t):
@@ -1281,9 +1395,21 @@ class FusedAdam(torch.optim.Optimizer):
             p.grad = view(fg)
             views.append((p, view))
             o += -(-k // 64) * 64
-        st = dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), step=0, views=views, params=ps)
+        st = dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), step=0, views=views, params=ps,
+                  p16=None)
+        o = 0
+        for p, view in views:
+            p._srgan_owner = (st, view, o, p.numel())          # see _shadow16
+            o += -(-p.numel() // 64) * 64
         self._flat[gi] = st
         return st
+
+    @staticmethod
+    def _refresh_shadow(st):
+        """Keep the bf16 shadow of the flat parameter buffer (created on first use by a bf16 convolution) in step
+        with the weights the Adam kernel just wrote."""
+        if st["p16"] is not None:
+            cast_bf16(st["p"], st["p16"])
 
     def flat_grads(self):
         """Flat gradient buffers (one per group) -- what a data-parallel caller all-reduces."""
@@ -1366,8 +1492,10 @@ class FusedAdam(torch.optim.Optimizer):
                 hyper = _tape.add(_tape.staging(8), _tape.device_buffer(8), fill)
                 _call("srgan_adam_step_dev", _p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
                       _p(hyper), _stream())
+                self._refresh_shadow(st)
                 continue
             st["step"] += 1
             b1, b2 = group["betas"]
             _call("srgan_adam_step", _p(st["p"]), _p(st["g"]), _p(st["m"]), _p(st["v"]), st["p"].numel(),
                   group["lr"], b1, b2, group["eps"], st["step"], _stream())
+            self._refresh_shadow(st)

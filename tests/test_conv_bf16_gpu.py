@@ -96,3 +96,174 @@ def test_bf16_res_conv_rate():
     fl = 2.0 * N * H * W * K * C * 9
     print("res conv fprop: bf16 %.1f us (%.0f TF/s)   tf32 %.1f us (%.0f TF/s)" %
           (t16 * 1e3, fl / t16 / 1e9, t32 * 1e3, fl / t32 / 1e9))
+
+
+WGRAD_GEOMS = [  # N, C, H, W, K, R, stride, pad
+    (4, 256, 32, 32, 256, 3, 1, 1),     # residual block: KT = 2, 256-wide channel tile, 9 tap groups
+    (3, 64, 64, 64, 128, 4, 2, 1),      # down1: 4 taps x 64 channels per MMA, stride-2 parity view of x
+    (2, 128, 32, 32, 256, 4, 2, 1),     # down2: 2 taps x 128 channels
+    (2, 64, 40, 24, 128, 4, 2, 1),      # ragged plane (pixel chunks cross image rows), mirrored up1
+    (5, 128, 9, 13, 64, 3, 1, 1),       # odd plane, 64 filters (half an accumulator tile)
+    (64, 256, 32, 32, 256, 3, 1, 1),    # production batch: cost-model pixel split + fixed-order reduction
+]
+
+
+@pytest.mark.parametrize("g", WGRAD_GEOMS)
+def test_wgrad_bf16(g):
+    """dW from bf16 x / dy (MN-major operands, plain 128B swizzle, 64-pixel chunks) against torch on the same
+    bf16-rounded operands: products exact in fp32, so only the accumulation order differs (rel-L2 <= 1e-4)."""
+    N, C, H, W, K, R, stride, pad = g
+    torch.manual_seed(3)
+    d = ops._desc(N, H, W, C, K, R, R, stride, pad)
+    x = _nhwc_bf16(torch.randn(N, C, H, W))
+    dy = _nhwc_bf16(torch.randn(N, K, d.P, d.Q))
+    assert ops._lib().srgan_conv2d_bf16_supported(d, 2) == 1
+    dw, _ = ops._wgrad(d, x, dy, True, False)
+    assert dw.dtype == torch.float32 and dw.is_contiguous(memory_format=CL)
+    ref = torch.nn.grad.conv2d_weight(x.float(), (K, C, R, R), dy.float(), stride, pad)
+    assert _rel(dw, ref) < 1e-4, (g, _rel(dw, ref))
+
+
+@pytest.mark.parametrize("xd,yd", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                   (torch.bfloat16, torch.float32)])
+def test_instance_norm_mixed_storage(xd, yd):
+    """srgan_inorm_{fwd,bwd}_mixed: x / dx and y / dy / residual in fp32 or bf16 independently; arithmetic fp32.
+    Reference: fp64 on the SAME (rounded) inputs; the only error left is the rounding of the bf16 outputs (2^-9)."""
+    N, C, H = 5, 128, 24
+    torch.manual_seed(4)
+    x = (torch.randn(N, C, H, H, device=DEV) * 1.3 + 0.2).to(xd).contiguous(memory_format=CL).requires_grad_(True)
+    g = torch.randn(C, device=DEV).requires_grad_(True)
+    b = torch.randn(C, device=DEV).requires_grad_(True)
+    cb = torch.randn(N, C, device=DEV).requires_grad_(True)
+    res = torch.randn(N, C, H, H, device=DEV).to(yd).contiguous(memory_format=CL).requires_grad_(True)
+    for act, residual in ((ops.ACT_RELU, None), (ops.ACT_NONE, res)):
+        y = ops.instance_norm_act(x, g, b, cb, residual, 1e-5, act, 0.0, out_dtype=yd)
+        assert y.dtype == yd and y.is_contiguous(memory_format=CL)
+        gy = torch.randn(N, C, H, H, device=DEV).to(yd).contiguous(memory_format=CL)
+        ins = [x, g, b, cb] + ([res] if residual is not None else [])
+        got = torch.autograd.grad(y, ins, gy)
+        assert got[0].dtype == xd
+        xr, gr, br, cr = (t.detach().double().requires_grad_(True) for t in (x, g, b, cb))
+        rr = res.detach().double().requires_grad_(True)
+        v = (F.instance_norm(xr, eps=1e-5) + cr[:, :, None, None]) * gr[None, :, None, None] + br[None, :, None, None]
+        yr = torch.relu(v) if act == ops.ACT_RELU else v + rr
+        ref = torch.autograd.grad(yr, [xr, gr, br, cr] + ([rr] if residual is not None else []), gy.double())
+        tol_y = 4e-3 if yd == torch.bfloat16 else 1e-5
+        tol_x = 4e-3 if xd == torch.bfloat16 else 1e-5
+        assert _rel(y, yr) < tol_y
+        assert _rel(got[0], ref[0]) < tol_x
+        for a_, r_ in zip(got[1:4], ref[1:4]):
+            assert _rel(a_, r_) < 1e-4                      # parameter gradients: fp32 sums of exact products
+        if residual is not None:
+            assert torch.equal(got[4], gy)
+
+
+def _generator_pair(batch=3):
+    """Full-width generator and a forward/backward on it, once per engine, same weights and inputs."""
+    import cases
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(0)
+    G = model.SingleGenerator(3, 64, 2, 2, 6, "instance", num_con=12).to(DEV)
+    x = (torch.rand(batch, 3, 128, 128, device=DEV) * 2 - 1).requires_grad_(True)
+    c = torch.randn(batch, 12, device=DEV)
+    gy = torch.randn(batch, 3, 128, 128, device=DEV)
+    out = {}
+    for eng in ("fp32", "auto", "bf16"):
+        ops.set_conv_engine(eng)
+        try:
+            for p in G.parameters():
+                p.grad = None
+            y = G(x, c)
+            dx, = torch.autograd.grad(y, x, gy, retain_graph=True)
+            y.backward(gy)
+            out[eng] = (y.detach().clone(), dx.clone(), {n: p.grad.detach().clone() for n, p in G.named_parameters()})
+        finally:
+            ops.set_conv_engine("auto")
+    return out
+
+
+def _rel_dict(a, b):
+    num = sum(float((a[k].double() - b[k].double()).pow(2).sum()) for k in b)
+    den = sum(float(b[k].double().pow(2).sum()) for k in b)
+    return (num / den) ** 0.5
+
+
+def test_generator_bf16_trunk_against_fp32_engine():
+    """SingleGenerator forward / backward with the bf16 trunk against the exact-fp32 engine on the same weights
+    (ref pyfiles/model.py:236-249).  Stated bf16 tolerance: output 1e-2, input gradient and parameter gradients 5e-2
+    relative L2 (bf16 keeps 8 significant bits per stored activation; 17 convolutions and 17 norms deep).  The TF32
+    engine's distance to fp32 is printed next to it."""
+    out = _generator_pair()
+    y0, dx0, g0 = out["fp32"]
+    for eng in ("auto", "bf16"):
+        y, dx, g = out[eng]
+        e = (_rel(y, y0), _rel(dx, dx0), _rel_dict(g, g0))
+        print("generator %s vs fp32 engine: y %.2e  dx %.2e  param grads %.2e" % ((eng,) + e))
+        if eng == "bf16":
+            assert e[0] < 1e-2 and e[1] < 5e-2 and e[2] < 5e-2, e
+    assert out["bf16"][0].dtype == torch.float32
+
+
+def test_bf16_step_matches_oracle_within_bf16_tolerance():
+    """One full-width SRGAN step (nb03 recipe, batch 2, k = 1) with the bf16 trunk against the CPU oracle.
+    Stated bf16 tolerance: losses 1e-2 relative; discriminator gradients (fp32 D on bf16-generated fakes) 5e-2."""
+    import numpy as np
+    import cases
+    import srgan_oracle as so
+    name = "srgan_full"
+    c = cases.CASES[name]
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(c["seed"])
+    np.random.seed(c["seed"])
+    nets = cases.build_nets(model, name, DEV)
+    sds = cases.state_dicts(nets)
+    torch.manual_seed(c["seed"] + 500)
+    oracle = cases.build_oracle(name, sds, so)
+    torch.manual_seed(c["seed"] + 500)
+    sg = cases.build_trainer(nb, name, tuple(n.to(DEV) for n in nets), DEV)
+    x, label = cases.synthetic_batch(c["batch"], util.get_target)
+    torch.manual_seed(c["seed"] + 1000)
+    ref = [float(e) for e in oracle.train(x, label)]
+    ops.set_conv_engine("bf16")
+    try:
+        torch.manual_seed(c["seed"] + 1000)
+        got = [float(e) for e in sg.train(x.to(DEV), {"source": label["source"].to(DEV), "target": label["target"]})]
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_engine("auto")
+    err = [abs(a - b) / max(1.0, abs(b)) for a, b in zip(got, ref)]
+    print("bf16 step losses %s vs oracle %s: rel %s" % (got, ref, ["%.2e" % e for e in err]))
+    assert max(err) < 1e-2, (got, ref)
+
+
+def test_bf16_cuda_graph_replay_is_bit_identical_to_eager():
+    """The bf16 trunk under CUDA-graph replay (shadow refresh after each Adam step is part of the captured step)."""
+    import numpy as np
+    import cases
+    c = dict(cases.CASES["srgan_full"], batch=2, k=2, res_num=2)
+    model, util, nb = cases.use_product_modules()
+
+    def run(graph):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        nets = tuple(n.to(DEV) for n in cases.build_nets(model, c, DEV))
+        torch.manual_seed(1)
+        sg = cases.build_trainer(nb, c, nets, DEV)
+        if graph:
+            sg.enable_cuda_graph(warmup=1)
+        losses = []
+        torch.manual_seed(2)
+        for step in range(4):
+            x, label = cases.synthetic_batch(c["batch"], util.get_target, seed=100 + step)
+            errs = sg.train(x.to(DEV), {"source": label["source"].to(DEV), "target": label["target"]})
+            losses.append([float(e) for e in errs])
+        torch.cuda.synchronize()
+        return losses, torch.cat([p.detach().reshape(-1) for n in nets for p in n.parameters()]).cpu()
+    ops.set_conv_engine("bf16")
+    try:
+        le, pe = run(False)
+        lg, pg = run(True)
+    finally:
+        ops.set_conv_engine("auto")
+    assert le == lg, (le, lg)
+    assert torch.equal(pe, pg)

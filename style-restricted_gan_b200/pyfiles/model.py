@@ -204,7 +204,9 @@ class _CBBNorm(nn.Module):
             return self.momentum
         return 0.0
 
-    def forward(self, input, ConInfor, act=ops.ACT_NONE, slope=0.0, residual=None):
+    def forward(self, input, ConInfor, act=ops.ACT_NONE, slope=0.0, residual=None, out_dtype=None):
+        if out_dtype not in (None, torch.float32):
+            raise NotImplementedError("batch-statistics norms keep fp32 storage")
         self._check_input_dim(input)
         factor = self._factor()
         lin = self.ConBias[0]
@@ -227,7 +229,9 @@ class _KernelBatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d(affine=True) for norm_type="batch" (ref get_norm_layer pyfiles/model.py:175): same parameters,
     buffers and state_dict keys; forward through the fused kernels (optional activation)."""
 
-    def forward(self, x, act=ops.ACT_NONE, slope=0.0):
+    def forward(self, x, act=ops.ACT_NONE, slope=0.0, out_dtype=None):
+        if out_dtype not in (None, torch.float32):
+            raise NotImplementedError("batch-statistics norms keep fp32 storage")
         self._check_input_dim(x)
         factor = 0.0
         if self.training and self.track_running_stats:

@@ -110,10 +110,10 @@ def _compare(name, engine, t):
 
 FP32_TOL = dict(loss=1e-4, D=1e-3, E0=5e-3, G0=1e-2, P2=2e-2)
 # TF32 engine, full-width nets at batch 2, k = 1.  Measured on B200 (round 2, printed by the test): losses 7.8e-5,
-# E0 4.8e-2, G0 1.1e-1, phase 2 1.3e-1 / 6.5e-2.  The gradient figures are NORM-level distances of whole-network
+# D 2.9e-3, E0 4.8e-2, G0 1.1e-1, phase 2 1.3e-1 / 6.5e-2.  The gradient figures are NORM-level distances of whole-network
 # gradients whose loss contains L1 terms and ReLU masks: a pre-activation within TF32 rounding of zero flips a mask and
 # the reference itself moves by 8.5e-2 between thread counts.  Bounds = 3 x measured.
-TF32_TOL = dict(loss=3e-4, D=3e-2, E0=1.5e-1, G0=3.2e-1, P2=4e-1)
+TF32_TOL = dict(loss=3e-4, D=1e-2, E0=1.5e-1, G0=3.2e-1, P2=4e-1)
 
 
 @pytest.mark.parametrize("name", ["srgan_small", "single_solo_small", "single_multi_small", "srgan_frozen_small"])

@@ -291,6 +291,18 @@ int srgan_adam_step(float* p, const float* g, float* m, float* v, size_t n,
  * (the caller uploads them before each step), so the launch can be part of a replayed CUDA graph. */
 int srgan_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* hyper, void* stream);
 
+/* ---------------------------------------------------------------- input pipeline
+ * ref: notebook/01-train_Conventional_SingleGAN.ipynb cell 9 (transform["train"]: CenterCrop(178) -> Resize(128) ->
+ *      RandomHorizontalFlip -> ToTensor -> MinMax(True)), pyfiles/dataset.py:127-141, pyfiles/util.py:108-116,148-153.
+ * img: B decoded RGB images [B][H][W][3] uint8 (device); y: [B][out][out][3] fp32 NHWC (device) = the channels-last
+ * storage of the logical [B,3,out,out] batch.  coef_* / bounds_*: Pillow's fixed-point (22 fractional bits)
+ * triangle-filter tables for crop -> out along each axis ([out][ksize] int32 and [out][2] = first tap, tap count), as
+ * computed by dataset.resample_coeffs; flip: B bytes (non-zero = mirror) or NULL.  Bit-exact with the CPU pipeline. */
+size_t srgan_face_transform_smem(int crop, int out, int ksize_h, int ksize_v);
+int srgan_face_transform(const uint8_t* img, int B, int H, int W, int crop, int out, const int* coef_h,
+                         const int* bounds_h, int ksize_h, const int* coef_v, const int* bounds_v, int ksize_v,
+                         const uint8_t* flip, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,8 @@ SIGNATURES = {
     "srgan_corrcoef_bwd": (c_int, [P, c_int, c_int, P, P, P, P]),
     "srgan_softhist_fwd": (c_int, [P, c_int, c_int, c_float, c_float, c_float, P, P]),
     "srgan_softhist_bwd": (c_int, [P, P, c_int, c_int, c_float, c_float, c_float, P, P]),
+    "srgan_face_transform_smem": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "srgan_face_transform": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, c_int, P, P, P]),
     "srgan_adam_step": (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_int, P]),
     "srgan_adam_step_dev": (c_int, [P, P, P, P, c_size_t, P, P]),
 }

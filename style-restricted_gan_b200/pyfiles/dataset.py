@@ -73,3 +73,95 @@ class FaceDataset(torch.utils.data.Dataset):
 
     def __len__(self):
         return len(self.images)
+
+
+# ------------------------------------------------------------------------------------------- GPU-side transform
+def resample_coeffs(in_size, out_size):
+    """Pillow's fixed-point tables for an 8-bit BILINEAR (triangle filter, support scaled by the down-sampling factor)
+    resize of one axis from `in_size` to `out_size` samples: (ksize, bounds[out,2] int32 = (first tap, tap count),
+    coeffs[out,ksize] int32 with 22 fractional bits).  Same arithmetic, in the same order, as Pillow's
+    precompute_coeffs / normalize_coeffs_8bpc (src/libImaging/Resample.c), which is what
+    `transforms.Resize((128, 128))` runs on the PIL image (ref notebook 01 cell 9)."""
+    import math
+    scale = float(np.float32(in_size)) / out_size
+    filterscale = max(scale, 1.0)
+    support = filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    coeffs = np.zeros((out_size, ksize), dtype=np.int32)
+    inv = 1.0 / filterscale
+    one = float(1 << 22)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        first = max(int(center - support + 0.5), 0)
+        count = min(int(center + support + 0.5), in_size) - first
+        w = [max(0.0, 1.0 - abs((x + first - center + 0.5) * inv)) for x in range(count)]
+        total = 0.0
+        for v in w:
+            total += v
+        if total != 0.0:
+            w = [v / total for v in w]
+        bounds[xx] = (first, count)
+        coeffs[xx, :count] = [int(-0.5 + v * one) if v < 0 else int(0.5 + v * one) for v in w]
+    return ksize, bounds, coeffs
+
+
+class GpuFaceTransform(object):
+    """The notebooks' `transform["train"]` / `transform["test"]` (ref notebook 01 cell 9: CenterCrop((178, 178)) ->
+    Resize((128, 128)) -> RandomHorizontalFlip(p=0.5) -> ToTensor() -> MinMax(True)) for a whole batch of decoded
+    images in ONE kernel launch on the GPU, bit-identical to the torchvision / Pillow CPU path.
+
+        tf = GpuFaceTransform(train=True)
+        x = tf(batch_u8)        # uint8 [B, H, W, 3] (host or device) -> float32 [B, 3, 128, 128], channels-last, cuda
+
+    Flip decisions are drawn on the host exactly like torchvision does for consecutive samples (one `torch.rand(1)`
+    per image from the default CPU generator), so a seeded run sees the same augmentation as the reference pipeline.
+    There is no CPU fallback."""
+
+    def __init__(self, crop=178, size=128, p_flip=0.5, train=True, device="cuda"):
+        self.crop, self.size, self.p_flip, self.train, self.device = int(crop), int(size), float(p_flip), train, device
+        self._tables = None
+
+    def _device_tables(self, dev):
+        if self._tables is None or self._tables[0] != dev:
+            k, b, c = resample_coeffs(self.crop, self.size)
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            self._tables = (dev, k, to(b), to(c))
+        return self._tables[1:]
+
+    def draw_flips(self, n):
+        """RandomHorizontalFlip.forward: `if torch.rand(1) < self.p`, once per image, in batch order."""
+        if not self.train or self.p_flip <= 0:
+            return None
+        return torch.tensor([1 if float(torch.rand(1)) < self.p_flip else 0 for _ in range(n)], dtype=torch.uint8)
+
+    def __call__(self, batch_u8, flips=None):
+        import srgan_ops as ops
+        x = torch.as_tensor(batch_u8)
+        if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError("expected a uint8 batch of decoded RGB images [B, H, W, 3]")
+        B, H, W, _ = x.shape
+        if flips is None:
+            flips = self.draw_flips(B)
+        dev = torch.device(self.device if x.device.type != "cuda" else x.device)
+        if dev.type != "cuda":
+            raise ops.SrganKernelError("GpuFaceTransform needs a CUDA device; there is no CPU fallback")
+        if x.device.type != "cuda":
+            x = (x if x.is_pinned() else x.contiguous().pin_memory()).to(dev, non_blocking=True)
+        x = x.contiguous()
+        k, bounds, coeffs = self._device_tables(x.device)
+        f = None if flips is None else torch.as_tensor(flips, dtype=torch.uint8).to(x.device, non_blocking=True)
+        y = torch.empty((B, 3, self.size, self.size), dtype=torch.float32, device=x.device,
+                        memory_format=torch.channels_last)
+        with torch.cuda.device(x.device):
+            ops._call("srgan_face_transform", ops._p(x), B, H, W, self.crop, self.size, ops._p(coeffs), ops._p(bounds),
+                      k, ops._p(coeffs), ops._p(bounds), k, ops._p(f), ops._p(y), ops._stream())
+        return y
+
+
+def raw_uint8_collate(items):
+    """collate_fn for a DataLoader over FaceDataset(transform=None): stacks the decoded PIL images of one batch into
+    one pinned uint8 tensor [B, H, W, 3] (what GpuFaceTransform consumes) and the labels into a LongTensor."""
+    imgs = torch.from_numpy(np.stack([np.asarray(im.convert("RGB")) for im, _ in items]))
+    labels = torch.as_tensor([int(lab) for _, lab in items], dtype=torch.long)
+    return (imgs.pin_memory() if torch.cuda.is_available() else imgs), labels

@@ -178,6 +178,54 @@ class _UnrolledTrainer(object):
     def _sched(optimizer):
         return torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=0.95)
 
+    # ---- collectives overlapped with compute (data parallel only) --------------------------------------
+    # The gradient all-reduce of a network is followed by that network's Adam step and then by the next forward that
+    # needs the new weights; whatever the step can compute in between without those weights hides the collective:
+    #   * D's all-reduce + Adam of update i      ||  the generator pass that makes the fake batch of update i + 1
+    #                                                (after the last update: encoder + generator pass of phase 1);
+    #   * the all-gather of mu (batch statistics) ||  the reconstruction pass of G and the D pass of phase 1;
+    #   * the all-reduce of the reported losses   ||  the backward pass of phase 2.
+    # Collective + dependent optimizer step run on a side stream; `_comm_join` makes the compute stream wait for it
+    # right before the first kernel that touches the network again (its next forward or the zeroing of its gradient
+    # buffer).  Under CUDA-graph capture the fork / join become graph edges.  Results are unchanged: the same kernels
+    # run on the same data, only their order relative to independent work differs.
+    _OVERLAP = os.environ.get("SRGAN_DBG_NO_COMM_OVERLAP", "0") == "0"
+
+    def _comm_fork(self):
+        """Side stream that has waited for everything issued so far on the compute stream, or None (single process /
+        CPU tensors / overlap disabled): the caller then runs the collective inline."""
+        if not self._OVERLAP or _world()[1] == 1 or not torch.cuda.is_available():
+            return None
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            return None
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(dev)
+        self._comm_stream.wait_stream(torch.cuda.current_stream(dev))
+        self._comm_pending = True
+        return self._comm_stream
+
+    def _comm_join(self):
+        if getattr(self, "_comm_pending", False):
+            torch.cuda.current_stream(torch.device(self.device)).wait_stream(self._comm_stream)
+            self._comm_pending = False
+
+    def _reduce_and_step(self, pairs):
+        """All-reduce the gradients of every (module, optimizer) in `pairs` and step the optimizers - on the side
+        stream when one is available (see above), else inline."""
+        side = self._comm_fork()
+        if side is None:
+            for module, opt in pairs:
+                _sync_grads(module, opt)
+            for _, opt in pairs:
+                opt.step()
+            return
+        with torch.cuda.stream(side):
+            for module, opt in pairs:
+                _sync_grads(module, opt)
+            for _, opt in pairs:
+                opt.step()
+
     # ---- small helpers --------------------------------------------------------------------------------
     def _onehot(self, label):
         return class_encode(label, self.device, self.ref_label)
@@ -223,12 +271,13 @@ class _UnrolledTrainer(object):
         rank, world = _world()
         mu_all = lv_all = None
         if world > 1:
-            # the statistics are those of the global batch: gather mu (B_global x ndim floats)
-            mu_all = torch.empty((mu.shape[0] * world, mu.shape[1]), dtype=mu.dtype, device=mu.device)
-            dist.all_gather_into_tensor(mu_all, mu.detach().contiguous())
-            if flags & ops.LAT_KL:
-                lv_all = torch.empty_like(mu_all)
-                dist.all_gather_into_tensor(lv_all, logvar.detach().contiguous())
+            pre = getattr(self, "_gathered", None)
+            if pre is not None and pre[0] is info:
+                self._comm_join()                       # issued right after the encoder pass (_prefetch_latent_stats)
+                mu_all, lv_all = pre[1], pre[2]
+                self._gathered = None
+            else:
+                mu_all, lv_all = self._gather_latent(mu, logvar, flags)
         hi = getattr(self, "hi", None)
         kw = {}
         if flags & ops.LAT_HIST:
@@ -247,6 +296,49 @@ class _UnrolledTrainer(object):
         if flags & ops.LAT_HIST:
             terms["hist"] = losses[2] * lbd["hist"]
         return terms
+
+    def _restriction_flags(self):
+        lbd, flags = self.lbd, 0
+        if lbd["KL"] > 0:
+            flags |= ops.LAT_KL
+        if lbd["batch_KL"] > 0:
+            flags |= ops.LAT_BKL
+        return flags
+
+    @staticmethod
+    def _gather_latent(mu, logvar, flags, side=None):
+        """The statistics are those of the GLOBAL batch: all-gather mu (B_global x ndim floats; logvar too for the
+        conventional KL term).  Buffers are allocated on the calling (compute) stream, which also consumes them; only
+        the collectives run on `side`."""
+        world = _world()[1]
+        kl = bool(flags & ops.LAT_KL)
+        mu_loc = mu.detach().contiguous()
+        lv_loc = logvar.detach().contiguous() if kl else None
+        mu_all = torch.empty((mu.shape[0] * world, mu.shape[1]), dtype=mu.dtype, device=mu.device)
+        lv_all = torch.empty_like(mu_all) if kl else None
+
+        def run():
+            dist.all_gather_into_tensor(mu_all, mu_loc)
+            if kl:
+                dist.all_gather_into_tensor(lv_all, lv_loc)
+        if side is None:
+            run()
+        else:
+            with torch.cuda.stream(side):
+                run()
+        return mu_all, lv_all
+
+    def _prefetch_latent_stats(self, info):
+        """Start the all-gather of the encoder output as soon as it exists; `_latent_restriction` picks it up."""
+        flags = self._restriction_flags()
+        if not flags or _world()[1] == 1:
+            return
+        mu_loc = info[1].detach().contiguous()          # materialised on the compute stream before the fork
+        side = self._comm_fork()
+        if side is None:
+            return
+        mu_all, lv_all = self._gather_latent(mu_loc, info[2], flags, side)
+        self._gathered = (info, mu_all, lv_all)
 
     # ---- the step --------------------------------------------------------------------------------------
     def _early_fakes(self):
@@ -296,7 +388,13 @@ class _UnrolledTrainer(object):
         _zero_grads(self._nG, self.optG)
         _zero_grads(self._nE, self.optE)
 
-        recon_image, enc_info = self.G_transformation(lab["source"], self.target_image, True, src)
+        # == G_transformation(lab["source"], self.target_image, True, src), with the all-gather of the encoder output
+        # started between the encoder and the generator pass.  Nothing here reads D: the all-reduce + Adam step of the
+        # last discriminator update may still be running on the side stream ...
+        enc_info = self._encode(src, lab["source"])
+        self._prefetch_latent_stats(enc_info)
+        recon_image = self._generate(lab["source"], self.target_image, self._style_of(enc_info))
+        self._comm_join()                               # ... and is waited for here, before D's next forward
         errG = self._fool_D(self.target_image, lab["target"])
         cyc = ops.l1_mean(src, recon_image)
         errG = errG + cyc * lbd["cycle"]
@@ -346,10 +444,8 @@ class _UnrolledTrainer(object):
             total = errG + restrict_bp if torch.is_tensor(restrict_bp) else errG
             with ops.direct_param_grads():
                 total.backward(retain_graph=True)
-        _sync_grads(self._nG, self.optG)
-        _sync_grads(self._nE, self.optE)
-        self.optG.step()
-        self.optE.step()
+        self._reduce_and_step([(self._nG, self.optG), (self._nE, self.optE)])
+        self._comm_join()
         hook = getattr(self, "_after_phase1", None)     # test hook (teacher forcing of the post-step weights)
         if hook is not None:
             hook(self)
@@ -361,11 +457,13 @@ class _UnrolledTrainer(object):
         errG_ex = ops.l1_mean(self.c_rand, target_mu) * lbd["reg"]
         if lbd["idt_reg"] * lbd["idt"] > 0:
             errG_ex = errG_ex + self._identity_regression() * lbd["idt_reg"] * (lbd["idt"] / lbd["cycle"])
+        out = [errG + errG_ex, errE_output]
+        self._report_async(out)                         # the reported scalars are final: reduce them behind the backward
         with ops.direct_param_grads():
             errG_ex.backward()
-        _sync_grads(self._nG, self.optG)
-        self.optG.step()
-        return [errG + errG_ex, errE_output]
+        self._reduce_and_step([(self._nG, self.optG)])
+        self._comm_join()
+        return out
 
     def train(self, source_image, label):
         if getattr(self, "_graph", None) is not None and torch.is_tensor(source_image) and source_image.is_cuda:
@@ -446,16 +544,41 @@ class _UnrolledTrainer(object):
         st["graph"].replay()
         return [e.clone() if torch.is_tensor(e) else e for e in st["out"]]
 
+    def _report_async(self, g_and_e):
+        """Called by update_GandE once errG / errE are final (before the phase-2 backward): average [errG, errD, errE]
+        over ranks on the side stream.  `_report` returns the result."""
+        self._reported = None
+        errD = getattr(self, "_errD_first", None)
+        if errD is None or _world()[1] == 1:
+            return
+        errs = [g_and_e[0], errD, g_and_e[1]]
+        if not (self._OVERLAP and torch.cuda.is_available() and torch.device(self.device).type == "cuda"):
+            return
+        self._reported = (self._report_now(errs, overlap=True), errs)
+
     def _report(self, errs):
         """Average the reported scalars over ranks so they equal the global-batch values."""
+        pre, self._reported = getattr(self, "_reported", None), None
+        if pre is not None and all(a is b for a, b in zip(pre[1], errs)):
+            self._comm_join()
+            return pre[0]
+        return self._report_now(errs)
+
+    def _report_now(self, errs, overlap=False):
         _, world = _world()
         if world == 1:
             return errs
         idx = [i for i, e in enumerate(errs) if torch.is_tensor(e)]
         if not idx:
             return errs
-        # ONE collective for all reported scalars
-        packed = _allreduce_mean_(torch.stack([errs[i].detach().float().reshape(()) for i in idx]))
+        # ONE collective for all reported scalars (packed on the compute stream; the collective may run on the side)
+        packed = torch.stack([errs[i].detach().float().reshape(()) for i in idx])
+        side = self._comm_fork() if overlap else None
+        if side is None:
+            _allreduce_mean_(packed)
+        else:
+            with torch.cuda.stream(side):
+                _allreduce_mean_(packed)
         out = list(errs)
         for j, i in enumerate(idx):
             out[i] = packed[j]
@@ -517,12 +640,12 @@ class SingleGAN_training(_UnrolledTrainer):
                 self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
         fake = self.target_image.detach()
         if self.singleD:
+            self._comm_join()                  # the previous update's all-reduce + Adam step (overlapped the G pass above)
             _zero_grads(self._nD, self.optD)
             errD = self._solo_D_loss(fake)
             with ops.direct_param_grads():
                 errD.backward()
-            _sync_grads(self._nD, self.optD)
-            self.optD.step()
+            self._reduce_and_step([(self._nD, self.optD)])
             return errD
         # one discriminator per class; like the reference, the LAST class's loss is what gets returned
         for i in self.classes:
@@ -553,7 +676,9 @@ class SingleGAN_training(_UnrolledTrainer):
                 errorD = errD
                 # (the reference snapshots D.state_dict() here and reloads it below; the snapshot aliases the
                 #  live parameters, so nothing is rolled back -- reproduced by doing nothing)
+        self._errD_first = errorD
         errorG, errorE = self.update_GandE()
+        self._comm_join()
         return self._report([errorG, errorD, errorE])
 
 
@@ -589,17 +714,17 @@ class SRGAN_training(_UnrolledTrainer):
             get_domainloss_D(output_class, self._onehot(fake_label), self.criterion_class) * self.lbd["class"]
 
     def update_D(self, keep_graph=True, fake=None):
-        _zero_grads(self._nD, self.optD)
         if fake is not None:
             self.target_image, self.c_rand = fake          # pre-generated without a graph (_early_fakes)
         else:
             with torch.set_grad_enabled(keep_graph):
                 self.target_image, self.c_rand = self.G_transformation(self.label["target"], self.source_image, False)
+        self._comm_join()                      # the previous update's all-reduce + Adam step (overlapped the G pass above)
+        _zero_grads(self._nD, self.optD)
         errD = self._solo_D_loss(self.target_image.detach())
         with ops.direct_param_grads():
             errD.backward()
-        _sync_grads(self._nD, self.optD)
-        self.optD.step()
+        self._reduce_and_step([(self._nD, self.optD)])
         return errD
 
     def _identity_regression(self):
@@ -613,7 +738,9 @@ class SRGAN_training(_UnrolledTrainer):
             errD = self.update_D(keep_graph=(i == self.k - 1), fake=early[i] if early and i < self.k - 1 else None)
             if i == 0:
                 errorD = errD       # (state_dict snapshot / reload of the reference is an aliasing no-op)
+        self._errD_first = errorD
         errorG, errorE = self.update_GandE()
+        self._comm_join()
         return self._report([errorG, errorD, errorE])
 
 

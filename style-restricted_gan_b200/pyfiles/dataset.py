@@ -153,6 +153,8 @@ class GpuFaceTransform(object):
         f = None if flips is None else torch.as_tensor(flips, dtype=torch.uint8).to(x.device, non_blocking=True)
         y = torch.empty((B, 3, self.size, self.size), dtype=torch.float32, device=x.device,
                         memory_format=torch.channels_last)
+        if B == 0:
+            return y
         with torch.cuda.device(x.device):
             ops._call("srgan_face_transform", ops._p(x), B, H, W, self.crop, self.size, ops._p(coeffs), ops._p(bounds),
                       k, ops._p(coeffs), ops._p(bounds), k, ops._p(f), ops._p(y), ops._stream())

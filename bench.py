@@ -294,7 +294,7 @@ def parity_check(workload, dev, tol):
     return out
 
 
-def dp_invariance_check(workload, dev, rank, world, tol=1e-5):
+def dp_invariance_check(workload, dev, rank, world, tol=None):
     """N > 1: one eager data-parallel step at 8 images per GPU.  (1) the reported losses and the latent statistics
     blob (mean / variance / correlation / histogram bins of the GLOBAL batch) are bit-identical on every rank;
     (2) rank 0 repeats the step as a single-GPU job on the same global batch of 8 N images (same seeds, same host
@@ -303,6 +303,12 @@ def dp_invariance_check(workload, dev, rank, world, tol=1e-5):
     import cases
     import srgan_ops as ops
     B = 8
+    if tol is None:
+        # the N-rank and the single-GPU run differ in the summation order of the weight gradients (pixel splits of
+        # wgrad follow the per-rank batch) and of the mean over ranks; TF32 / fp32 storage keeps the losses of the
+        # step within 5e-6 (measured 3e-7), bf16 storage turns the same differences into 2^-9 steps of stored
+        # activations (measured 1.2e-5)
+        tol = 2e-4 if ops.get_conv_engine() == "bf16" else 5e-6
     case, _, sg, util = _fresh_trainer(workload, B * world, dev, ops, cases)
     xg, lab = cases.synthetic_batch(B * world, util.get_target)
     sl = slice(rank * B, (rank + 1) * B)

@@ -520,6 +520,7 @@ class _UnrolledTrainer(object):
                       tgt=ops.to_device_async(label["target"], dev, torch.long).clone())
             # nothing may keep the previous step's autograd graph (and its accumulation nodes) alive
             self.target_image = self.c_rand = self.source_image = self.label = None
+            self._errD_first = self._reported = self._gathered = None
             cfg["state"] = None
             import gc
             gc.collect()
@@ -559,7 +560,7 @@ class _UnrolledTrainer(object):
     def _report(self, errs):
         """Average the reported scalars over ranks so they equal the global-batch values."""
         pre, self._reported = getattr(self, "_reported", None), None
-        if pre is not None and all(a is b for a, b in zip(pre[1], errs)):
+        if pre is not None and pre[1][0] is errs[0] and pre[1][2] is errs[2]:
             self._comm_join()
             return pre[0]
         return self._report_now(errs)
@@ -676,7 +677,7 @@ class SingleGAN_training(_UnrolledTrainer):
                 errorD = errD
                 # (the reference snapshots D.state_dict() here and reloads it below; the snapshot aliases the
                 #  live parameters, so nothing is rolled back -- reproduced by doing nothing)
-        self._errD_first = errorD
+        self._errD_first = errorD.detach() if torch.is_tensor(errorD) else errorD    # value only: no graph is kept
         errorG, errorE = self.update_GandE()
         self._comm_join()
         return self._report([errorG, errorD, errorE])
@@ -738,7 +739,7 @@ class SRGAN_training(_UnrolledTrainer):
             errD = self.update_D(keep_graph=(i == self.k - 1), fake=early[i] if early and i < self.k - 1 else None)
             if i == 0:
                 errorD = errD       # (state_dict snapshot / reload of the reference is an aliasing no-op)
-        self._errD_first = errorD
+        self._errD_first = errorD.detach() if torch.is_tensor(errorD) else errorD    # value only: no graph is kept
         errorG, errorE = self.update_GandE()
         self._comm_join()
         return self._report([errorG, errorD, errorE])

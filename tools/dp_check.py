@@ -89,7 +89,10 @@ def main():
             # gradient differences into sign-level weight differences, so this quantity is ill-conditioned; two
             # fp32 CPU runs of the reference itself that differ only in thread count disagree by 8.5e-2
             # (SURVEY F12).  Everything up to that step is held to 2e-3 / 2e-2.
-            tol = 2e-1 if key in ("G1",) else (2e-2 if key.startswith("G") or key.startswith("E") else 2e-3)
+            # With bf16 storage the same sign-level weight differences are amplified by the 2^-9 rounding of every stored
+            # activation (measured 2.6e-1 against 8.5e-2 for TF32): 4e-1.
+            g1 = 4e-1 if os.environ.get("SRGAN_CONV_ENGINE", "").lower() == "bf16" else 2e-1
+            tol = g1 if key in ("G1",) else (2e-2 if key.startswith("G") or key.startswith("E") else 2e-3)
             print("  grads at %-3s rel-L2 vs 1-GPU = %.3e (tol %.0e)" % (key, rel, tol))
             ok &= rel < tol
         print("DP_CHECK", "PASS" if ok else "FAIL")

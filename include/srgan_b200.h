@@ -143,18 +143,24 @@ int srgan_inorm_bwd(const float* dy, const float* x, const float* mean, const fl
                     void* workspace, size_t workspace_bytes, void* stream);
 int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma, const float* cbias,
                             float* dgamma, float* dbeta, float* dcbias, int N, int C, void* stream);
-/* Mixed storage: x / dx have dtype x_dtype, y / dy / residual have dtype y_dtype (SRGAN_DT_F32 or SRGAN_DT_BF16,
- * independently); statistics, parameters and arithmetic stay fp32 (partials fp64).  Otherwise as srgan_inorm_fwd /
- * srgan_inorm_bwd.  The generator uses f32 -> bf16 behind its RGB stem, bf16 -> bf16 in the trunk and bf16 -> f32 in
- * front of the RGB head. */
+/* Mixed storage (norm8.cu): x / dx have dtype x_dtype, y / dy / residual have dtype y_dtype (SRGAN_DT_F32 or
+ * SRGAN_DT_BF16, independently); statistics, parameters and arithmetic stay fp32 (partials fp64 over fixed atoms, as
+ * above).  Otherwise as srgan_inorm_fwd / srgan_inorm_bwd.  The generator uses f32 -> bf16 behind its RGB stem,
+ * bf16 -> bf16 in the trunk and bf16 -> f32 in front of the RGB head.
+ * workspace: srgan_inorm_mixed_workspace(N, HW, C) bytes of scratch (slice partials).
+ * counters: srgan_inorm_mixed_counters(N, C) bytes of int32 ticket counters that are ZERO on entry; the kernels leave
+ * them zero (the CTA that completes an image folds its partials and resets the counter), so one zero-initialised
+ * buffer serves every launch issued on the same stream. */
+size_t srgan_inorm_mixed_workspace(int N, int HW, int C);
+size_t srgan_inorm_mixed_counters(int N, int C);
 int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, float* mean, float* rstd,
                           const float* gamma, const float* beta, const float* cbias, const void* residual,
                           int N, int HW, int C, float eps, int act, float slope,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          void* workspace, size_t workspace_bytes, int* counters, void* stream);
 int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean,
                           const float* rstd, const float* gamma, const float* beta, const float* cbias,
                           void* dx, float* s1, float* s2, int N, int HW, int C, int act, float slope,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          void* workspace, size_t workspace_bytes, int* counters, void* stream);
 
 /* ---------------------------------------------------------------- batch-statistics norms
  * ref: CBBNorm2d / _CBBNorm.forward pyfiles/model.py:75-171 and nn.BatchNorm2d(affine=True) chosen by

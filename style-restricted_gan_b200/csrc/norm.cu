@@ -968,85 +968,6 @@ extern "C" int srgan_inorm_bwd(const float* dy, const float* x, const float* mea
   SRGAN_RETURN_LAUNCH();
 }
 
-// ---- mixed storage: x / dx and y / dy / residual are NHWC tensors of fp32 or bfloat16, independently (dtype codes
-// SRGAN_DT_F32 / SRGAN_DT_BF16); statistics, parameters and all arithmetic are fp32, the partial sums fp64.  The
-// generator's bf16 trunk uses (f32 -> bf16) behind the RGB stem, (bf16 -> bf16) inside and (bf16 -> f32) in front of
-// the RGB head, so the thin first / last layers keep their fp32 kernels without a conversion pass.
-template <typename TX, typename TY>
-static int inorm_fwd_typed(const NormP& p, const void* x, void* y, float* mean, float* rstd, const float* gamma,
-                           const float* beta, const float* cbias, const void* residual, void* ws, cudaStream_t st) {
-  inorm_stats_kernel<D4, TX><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TX*)x, (D4*)ws);
-  inorm_apply_kernel<D4, TX, TY><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TX*)x, (const D4*)ws, (TY*)y, mean, rstd,
-                                                                        gamma, beta, cbias, (const TY*)residual);
-  SRGAN_RETURN_LAUNCH();
-}
-
-template <typename TX, typename TY>
-static int inorm_bwd_typed(const NormP& p, const void* dy, const void* x, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, const float* cbias, void* dx, float* s1, float* s2,
-                           void* ws, cudaStream_t st) {
-  inorm_bwd_reduce_kernel<D4, TX, TY><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TY*)dy, (const TX*)x, mean, rstd,
-                                                                             gamma, beta, cbias, (D4*)ws);
-  inorm_bwd_apply_kernel<D4, TX, TY><<<norm_grid(p), kNormThreads, 0, st>>>(p, (const TY*)dy, (const TX*)x, mean, rstd,
-                                                                            gamma, beta, cbias, (const D4*)ws, (TX*)dx,
-                                                                            s1, s2);
-  SRGAN_RETURN_LAUNCH();
-}
-
-extern "C" int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, float* mean, float* rstd,
-                                     const float* gamma, const float* beta, const float* cbias, const void* residual,
-                                     int N, int HW, int C, float eps, int act, float slope, void* ws, size_t ws_bytes,
-                                     void* stream) {
-  SRGAN_CHECK_ARG(x && y && mean && rstd, "null pointer");
-  SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
-  SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
-                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)residual | (uintptr_t)ws) % 16 == 0,
-                  "pointers must be 16-byte aligned");
-  SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
-  SRGAN_CHECK_ARG((x_dtype == SRGAN_DT_F32 || x_dtype == SRGAN_DT_BF16) &&
-                  (y_dtype == SRGAN_DT_F32 || y_dtype == SRGAN_DT_BF16), "unknown dtype code");
-  if (N == 0) return SRGAN_OK;
-  NormP p;
-  SRGAN_CHECK_ARG(plan_norm(N, HW, C, &p), "channel count cannot be mapped");
-  SRGAN_CHECK_ARG(norm_f64(), "mixed-storage norms need the fp64 partial sums");
-  p.eps = eps; p.slope = slope; p.act = act;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_fwd_mixed: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
-  using B = __nv_bfloat16;
-  const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
-  if (xb && yb) return inorm_fwd_typed<B, B>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
-  if (xb) return inorm_fwd_typed<B, float>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
-  if (yb) return inorm_fwd_typed<float, B>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
-  return inorm_fwd_typed<float, float>(p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, st);
-}
-
-extern "C" int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean,
-                                     const float* rstd, const float* gamma, const float* beta, const float* cbias,
-                                     void* dx, float* s1, float* s2, int N, int HW, int C, int act, float slope,
-                                     void* ws, size_t ws_bytes, void* stream) {
-  SRGAN_CHECK_ARG(dy && x && mean && rstd && dx && s1 && s2, "null pointer");
-  SRGAN_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && C % 8 == 0, "need C % 8 == 0, HW > 0");
-  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
-                   (uintptr_t)beta | (uintptr_t)cbias | (uintptr_t)dx | (uintptr_t)s1 | (uintptr_t)s2 |
-                   (uintptr_t)ws) % 16 == 0, "pointers must be 16-byte aligned");
-  SRGAN_CHECK_ARG(N <= 65535, "N too large for grid.y");
-  SRGAN_CHECK_ARG((x_dtype == SRGAN_DT_F32 || x_dtype == SRGAN_DT_BF16) &&
-                  (y_dtype == SRGAN_DT_F32 || y_dtype == SRGAN_DT_BF16), "unknown dtype code");
-  if (N == 0) return SRGAN_OK;
-  NormP p;
-  SRGAN_CHECK_ARG(plan_norm(N, HW, C, &p), "channel count cannot be mapped");
-  SRGAN_CHECK_ARG(norm_f64(), "mixed-storage norms need the fp64 partial sums");
-  p.eps = 0.f; p.slope = slope; p.act = act;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!ws || ws_bytes < norm_ws_bytes(p)) { set_error("inorm_bwd_mixed: workspace %zu < %zu", ws_bytes, norm_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
-  using B = __nv_bfloat16;
-  const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
-  if (xb && yb) return inorm_bwd_typed<B, B>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
-  if (xb) return inorm_bwd_typed<B, float>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
-  if (yb) return inorm_bwd_typed<float, B>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
-  return inorm_bwd_typed<float, float>(p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, st);
-}
-
 extern "C" int srgan_inorm_param_grads(const float* s1, const float* s2, const float* gamma,
                                        const float* cbias, float* dgamma, float* dbeta, float* dcbias, int N,
                                        int C, void* stream) {

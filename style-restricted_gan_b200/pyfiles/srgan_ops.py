@@ -103,7 +103,18 @@ class _ScratchSet(object):
     memory pool), see `private_scratch`."""
 
     def __init__(self):
-        self.ws, self.red, self.keep = {}, {}, []
+        self.ws, self.red, self.ctr, self.keep = {}, {}, {}, []
+
+    def counters(self, dev, nbytes):
+        """Zero-initialised int32 ticket counters of the norm kernels (they leave them zero, see
+        srgan_inorm_fwd_mixed)."""
+        c = self.ctr.get(dev)
+        if c is None or c.numel() * 4 < nbytes:
+            c = torch.zeros(max(nbytes // 4 + 1, 1 << 16), dtype=torch.int32, device=dev)
+            self.ctr[dev] = c
+            if self is not _global_scratch:
+                self.keep.append(c)
+        return c
 
     def workspace(self, dev, nbytes):
         buf = self.ws.get(dev)
@@ -151,6 +162,10 @@ def _workspace(dev, nbytes):
 
 def _red_scratch(dev):
     return _scratch_set.red_scratch(dev)
+
+
+def _norm_counters(dev, N, C):
+    return _scratch_set.counters(dev, _lib().srgan_inorm_mixed_counters(N, C))
 
 
 # ----------------------------------------------------------------------------- host RNG
@@ -787,12 +802,15 @@ class _InstanceNormFn(torch.autograd.Function):
         rstd = torch.empty((N, C), dtype=torch.float32, device=x.device)
         mixed = x.dtype != torch.float32 or out_dtype != torch.float32
         if x.numel():
-            nb = _lib().srgan_inorm_workspace(N, H * W, C)
-            ws = _workspace(x.device, nb)
             if mixed:
+                nb = _lib().srgan_inorm_mixed_workspace(N, H * W, C)
+                ws = _workspace(x.device, nb)
                 _call("srgan_inorm_fwd_mixed", _p(x), _dt(x), _p(y), _dt(y), _p(mean), _p(rstd), _p(gamma), _p(beta),
-                      _p(cbias), _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb, _stream())
+                      _p(cbias), _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb,
+                      _p(_norm_counters(x.device, N, C)), _stream())
             else:
+                nb = _lib().srgan_inorm_workspace(N, H * W, C)
+                ws = _workspace(x.device, nb)
                 _call("srgan_inorm_fwd", _p(x), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias),
                       _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb, _stream())
         ctx.gamma, ctx.beta = gamma, beta
@@ -815,12 +833,15 @@ class _InstanceNormFn(torch.autograd.Function):
         s1 = torch.empty((N, C), dtype=torch.float32, device=x.device)
         s2 = torch.empty((N, C), dtype=torch.float32, device=x.device)
         if x.numel():
-            nb = _lib().srgan_inorm_workspace(N, H * W, C)
-            ws = _workspace(x.device, nb)
             if ctx.mixed:
+                nb = _lib().srgan_inorm_mixed_workspace(N, H * W, C)
+                ws = _workspace(x.device, nb)
                 _call("srgan_inorm_bwd_mixed", _p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(beta),
-                      _p(cbias), _p(dx), _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
+                      _p(cbias), _p(dx), _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb,
+                      _p(_norm_counters(x.device, N, C)), _stream())
             else:
+                nb = _lib().srgan_inorm_workspace(N, H * W, C)
+                ws = _workspace(x.device, nb)
                 _call("srgan_inorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(cbias), _p(dx),
                       _p(s1), _p(s2), N, H * W, C, ctx.act, ctx.slope, _p(ws), nb, _stream())
         dgamma = dbeta = dcb = None

@@ -96,9 +96,19 @@ int srgan_conv2d_dgrad_add(const srgan_conv_desc* d, const float* dy, const floa
 int srgan_conv2d_bf16_supported(const srgan_conv_desc* d, int pass);
 size_t srgan_conv2d_bf16_workspace(const srgan_conv_desc* d, int pass);
 int srgan_conv2d_fprop_bf16(const srgan_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                            int act, float slope, void* stream);
+                            int act, float slope, float* tile_stats, void* stream);
 int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
-                            void* workspace, size_t workspace_bytes, void* stream);
+                            float* tile_stats, void* workspace, size_t workspace_bytes, void* stream);
+/* tile_stats (optional, forward use of fprop / of dgrad as the transposed convolution): the epilogue also writes the
+ * per-tile statistics the instance norm behind the convolution needs (ref CBINorm2d pyfiles/model.py:54-67 follows
+ * every generator convolution :236-249), sparing that norm its own statistics pass:
+ *   tile_stats[((n * rows + r) * K_out + k) * 2 + {0,1}] = sum, sum of squares over the 128 pixels of tile r of image
+ *   n of the values AS STORED (after rounding to bf16), rows = srgan_conv2d_bf16_stat_rows(d, pass) (0: shape cannot
+ *   provide them: tiles must lie inside one image; needs bias == NULL, act none, no addend).
+ * srgan_inorm_stats_from_tiles folds the rows of every image in row order in fp64 (independent of the batch). */
+int srgan_conv2d_bf16_stat_rows(const srgan_conv_desc* d, int pass);
+int srgan_inorm_stats_from_tiles(const float* tile_stats, int rows, int N, int HW, int C, float eps, float* mean,
+                                 float* rstd, void* stream);
 int srgan_conv2d_wgrad_bf16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
                             size_t workspace_bytes, void* stream);
 int srgan_conv2d_wgrad_bf16_plan(const srgan_conv_desc* d, int* splits, int* ctas);
@@ -155,8 +165,9 @@ size_t srgan_inorm_mixed_workspace(int N, int HW, int C);
 size_t srgan_inorm_mixed_counters(int N, int C);
 int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, float* mean, float* rstd,
                           const float* gamma, const float* beta, const float* cbias, const void* residual,
-                          int N, int HW, int C, float eps, int act, float slope,
+                          int N, int HW, int C, float eps, int act, float slope, int stats_given,
                           void* workspace, size_t workspace_bytes, int* counters, void* stream);
+/* stats_given != 0: mean / rstd are inputs (srgan_inorm_stats_from_tiles); only the apply kernel runs. */
 int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean,
                           const float* rstd, const float* gamma, const float* beta, const float* cbias,
                           void* dx, float* s1, float* s2, int N, int HW, int C, int act, float slope,

@@ -41,10 +41,11 @@ int conv_wgrad_umma_launch(const srgan_conv_desc*, const float*, const float*, f
 // conv_umma.cu, bf16 storage (void*: __nv_bfloat16 tensors)
 bool conv_umma_bf16_supported(const srgan_conv_desc* d, int pass);
 size_t conv_umma_bf16_workspace(const srgan_conv_desc* d, int pass);
+int conv_umma_bf16_stat_rows(const srgan_conv_desc* d, int pass);
 int conv_fprop_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, const float*, void*, int, float,
-                                cudaStream_t);
+                                cudaStream_t, float* stats);
 int conv_dgrad_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, void*, void*, size_t, cudaStream_t,
-                                const void* addend);
+                                const void* addend, float* stats);
 bool conv_umma_bf16_wgrad_supported(const srgan_conv_desc* d);
 size_t conv_umma_bf16_wgrad_workspace(const srgan_conv_desc* d);
 void conv_umma_bf16_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
@@ -173,17 +174,21 @@ extern "C" int srgan_conv2d_wgrad_bf16_plan(const srgan_conv_desc* d, int* split
   return SRGAN_OK;
 }
 extern "C" int srgan_conv2d_fprop_bf16(const srgan_conv_desc* d, const void* x, const void* w, const float* bias,
-                                       void* y, int act, float slope, void* stream) {
+                                       void* y, int act, float slope, float* tile_stats, void* stream) {
   if (int e = check_desc(d)) return e;
   SRGAN_CHECK_ARG(x && w && y, "null pointer");
   SRGAN_CHECK_ARG(dense_x(d), "bf16 conv: dense NHWC input only");
-  return conv_fprop_umma_bf16_launch(d, x, w, bias, y, act, slope, (cudaStream_t)stream);
+  return conv_fprop_umma_bf16_launch(d, x, w, bias, y, act, slope, (cudaStream_t)stream, tile_stats);
 }
 extern "C" int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy, const void* w, const void* addend,
-                                       void* dx, void* ws, size_t ws_bytes, void* stream) {
+                                       void* dx, float* tile_stats, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_desc(d)) return e;
   SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
-  return conv_dgrad_umma_bf16_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream, addend);
+  return conv_dgrad_umma_bf16_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream, addend, tile_stats);
+}
+extern "C" int srgan_conv2d_bf16_stat_rows(const srgan_conv_desc* d, int pass) {
+  if (check_desc(d)) return 0;
+  return conv_umma_bf16_stat_rows(d, pass);
 }
 
 extern "C" int srgan_conv2d_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas) {

@@ -76,7 +76,8 @@ struct UmmaCfg {
   static constexpr int kStages = (212 * 1024) / kStageBytes < 8 ? (212 * 1024) / kStageBytes : 8;
   static constexpr int kAccBufs = 2 * MT * BN <= 512 ? 2 : 1;   // accumulator double buffering when TMEM allows
   static constexpr int kTmemCols = kAccBufs * MT * BN < 32 ? 32 : kAccBufs * MT * BN;
-  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kStatBytes = 4 * BN * 2 * sizeof(float);   // per-quadrant column sums of one tile (STATS)
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
   // TMA issue: measured with tools/tma_probe.cu, the bulk-tensor loads of ONE warp execute back to back (~750-1100
   // clk each, whatever their size) while loads of different warps overlap.  A stage is therefore cut into kBoxes
   // boxes of <= 16 KB (MT activation sub-tiles + filter rows in blocks of <= 128), and 2*kBoxes producer warps each
@@ -230,6 +231,22 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Column sums over the 32 rows (lanes) of a warp: every lane passes 32 values s[0..31] (one per column); on return
+// s[0] of lane L is the sum over all lanes of column L.  Butterfly transpose-reduce: 31 shuffles, fixed order.
+__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = up ? s[j] : s[j + off];       // the half this lane does not keep
+      const float keep = up ? s[j + off] : s[j];
+      s[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // 4 epilogue warps
+
 // work item -> linear tile index, first column and width of the column range it covers
 struct UmmaItem { int lin, n_off, width; };
 template <int BN>
@@ -240,11 +257,16 @@ __device__ __forceinline__ UmmaItem umma_item(const UmmaConvP& p, int item) {
   return u;
 }
 
-template <int BN, int MT, typename ST>
+// STATS: the epilogue also writes, per 128-pixel tile and output channel, the sum and the sum of squares of the values
+// it stores (as stored, i.e. after rounding to ST): stats[(tile_row * K + k) * 2 + {0, 1}], tile_row =
+// ((n * classes + cls) * tiles_h + th) * tiles_w + tw - what the instance norm that follows the convolution needs,
+// without its own pass over the tensor (srgan_inorm_stats_from_tiles folds the rows of an image in fp64).  Needs tiles
+// that lie inside one image (box of 128 pixels of one image), no bias / activation / addend.
+template <int BN, int MT, typename ST, bool STATS = false>
 __global__ void __launch_bounds__((UmmaCfg<BN, MT, ST>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, ST* __restrict__ y,
-                 const ST* __restrict__ addend) {
+                 const ST* __restrict__ addend, float* __restrict__ stats) {
   using Cfg = UmmaCfg<BN, MT, ST>;
   constexpr int NBUF = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -254,6 +276,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tfull = empty + Cfg::kStages;          // [NBUF] accumulator complete
   uint64_t* tempty = tfull + 2;                    // [NBUF] accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sstat = reinterpret_cast<float*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes + 256);   // [4][BN][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bw = 1 << p.lw, bh = 1 << p.lh;
@@ -385,6 +408,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
+            if (STATS) {
+              // column sums of the values as they are stored (rounded to ST), rows outside the image count as zero
+              float t[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = valid ? v[j] : 0.f;
+                if (sizeof(ST) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
+                t[j] = a;
+              }
+              warp_colsum32(t, lane);
+              const float sum1 = t[0];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = valid ? v[j] : 0.f;
+                if (sizeof(ST) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
+                t[j] = a * a;
+              }
+              warp_colsum32(t, lane);
+              *reinterpret_cast<float2*>(sstat + ((quad * BN) + c + lane) * 2) = make_float2(sum1, t[0]);
+            }
             if (valid) {
               if (col0 + c + 32 <= p.K && p.epi_vec) {
                 epi_row_chunk_any<32>(v, yrow + col0 + c, brow ? brow + c : nullptr, p.act, p.slope, p.epi_vec,
@@ -413,6 +456,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                                            (arow ? ld_as_float(arow + j) : 0.f), p.act, p.slope));
             }
           }
+        }
+        if (STATS && kChunk == 32) {
+          // the four quadrants (32 pixel rows each) of this tile, added in quadrant order; bn == 1: the tile lies in
+          // image t / (tiles_w * tiles_h)
+          epi_bar_sync();
+          int tt = bx * MT + mt;
+          const int tw2 = tt % p.tiles_w; tt /= p.tiles_w;
+          const int th2 = tt % p.tiles_h, img = tt / p.tiles_h;
+          const size_t prow = (((size_t)img * p.gz + cls) * p.tiles_h + th2) * p.tiles_w + tw2;
+          if (img < p.Nn) {
+            for (int col = quad * 32 + lane; col < u.width; col += 128) {
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { a += sstat[(q * BN + col) * 2]; b += sstat[(q * BN + col) * 2 + 1]; }
+              if (col0 + col < p.K)
+                *reinterpret_cast<float2*>(stats + (prow * p.K + col0 + col) * 2) = make_float2(a, b);
+            }
+          }
+          epi_bar_sync();
         }
       }
       tc_fence_before();
@@ -671,13 +733,17 @@ static int pick_bn(int K) {
 
 template <int BN, int MT, typename ST>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, ST* y,
-                     dim3 grid, cudaStream_t st, const ST* addend) {
+                     dim3 grid, cudaStream_t st, const ST* addend, float* stats = nullptr) {
   using Cfg = UmmaCfg<BN, MT, ST>;
-  static unsigned long long attr_done = 0;
+  constexpr bool kCanStat = sizeof(ST) == 2 && BN >= 32;       // tile statistics: bf16 trunk only
+  static unsigned long long attr_done = 0, attr_done_s = 0;
   {
-    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST>, (int)Cfg::kSmem, &attr_done);
+    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST, false>, (int)Cfg::kSmem, &attr_done);
+    if (e == cudaSuccess && kCanStat && stats)
+      e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST, kCanStat>, (int)Cfg::kSmem, &attr_done_s);
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
+  if (stats && !kCanStat) { set_error("conv_umma: tile statistics need bf16 storage and >= 32 output channels"); return SRGAN_E_UNSUPPORTED; }
   UmmaConvP q = p;
   q.gx = (grid.x + MT - 1) / MT; q.gy = grid.y; q.gz = grid.z;
   long items = (long)q.gx * q.gy * q.gz;
@@ -694,7 +760,10 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
   }
   q.n_items = (int)items;
   const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);     // persistent: one CTA per SM
-  conv_umma_kernel<BN, MT, ST><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend);
+  if (kCanStat && stats)
+    conv_umma_kernel<BN, MT, ST, kCanStat><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend, stats);
+  else
+    conv_umma_kernel<BN, MT, ST, false><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend, nullptr);
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -712,7 +781,7 @@ struct Problem {
 
 template <typename ST>
 static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float slope, cudaStream_t st,
-                         const CUtensorMap* ma_prebuilt, const ST* addend) {
+                         const CUtensorMap* ma_prebuilt, const ST* addend, float* stats = nullptr) {
   constexpr uint64_t ES = sizeof(ST);
   constexpr uint32_t ROW = UmmaElem<ST>::kRow;
   constexpr CUtensorMapDataType DT = UmmaElem<ST>::kTma;
@@ -759,6 +828,10 @@ static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float s
   p.epi_vec = (pr.fK % V8 == 0 && (uintptr_t)y % 32 == 0) ? 8 : (pr.fK % V4 == 0 ? 4 : 0);
   if (bias && (uintptr_t)bias % 16) p.epi_vec = 0;            // vector bias loads need an aligned bias
   if (addend && ((uintptr_t)addend % 16 || pr.fK % V4)) { set_error("conv: addend must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  if (stats && (bn != 1 || bias || addend || act != SRGAN_ACT_NONE)) {
+    set_error("conv: tile statistics need 128-pixel tiles inside one image and a plain epilogue");
+    return SRGAN_E_UNSUPPORTED;
+  }
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, ceil_div(pr.fK, BN), pr.ncls);
   // Two M sub-tiles per CTA (one filter tile feeds 256 pixels) when TMEM can still double-buffer the accumulator
   // (2 x 2 x 128 columns) and every SM keeps work; 256-wide tiles stay at MT = 1: overlapping the epilogue with the
@@ -767,15 +840,15 @@ static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float s
   static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
   const long ctas = (long)grid.x * grid.y * grid.z;
   const int mt = e_mt ? atoi(e_mt) : ((BN == 128 || BN == 64) && ctas >= 2 * kNumSMs ? 2 : 1);
-  if (mt == 2 && BN == 256) return launch_bn<256, 2, ST>(ma, mb, p, bias, y, grid, st, addend);
-  if (mt == 2 && BN == 128) return launch_bn<128, 2, ST>(ma, mb, p, bias, y, grid, st, addend);
-  if (mt == 2 && BN == 64) return launch_bn<64, 2, ST>(ma, mb, p, bias, y, grid, st, addend);
+  if (mt == 2 && BN == 256) return launch_bn<256, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+  if (mt == 2 && BN == 128) return launch_bn<128, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+  if (mt == 2 && BN == 64) return launch_bn<64, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
   switch (BN) {
-    case 256: return launch_bn<256, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
-    case 128: return launch_bn<128, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
-    case 64:  return launch_bn<64, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
-    case 32:  return launch_bn<32, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
-    default:  return launch_bn<16, 1, ST>(ma, mb, p, bias, y, grid, st, addend);
+    case 256: return launch_bn<256, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    case 128: return launch_bn<128, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    case 64:  return launch_bn<64, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    case 32:  return launch_bn<32, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    default:  return launch_bn<16, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
   }
 }
 
@@ -1180,17 +1253,34 @@ size_t conv_umma_bf16_workspace(const srgan_conv_desc* d, int pass) {
   return pass == 1 ? (size_t)d->K * d->R * d->S * d->C * sizeof(__nv_bfloat16) : 0;     // transposed filter
 }
 
+// Rows of per-tile statistics one image contributes when the pass is run with `stats` (0: not available): the
+// pixel grid of a class must be cut into 128-pixel boxes that lie inside one image.
+int conv_umma_bf16_stat_rows(const srgan_conv_desc* d, int pass) {
+  if (pass > 1 || !conv_umma_bf16_supported(d, pass)) return 0;
+  if ((pass == 0 ? d->K : d->C) < 32) return 0;
+  int P, Q, ncls = 1;
+  if (pass == 0) { P = d->P; Q = d->Q; }
+  else if (d->stride == 1) { P = d->H; Q = d->W; }
+  else { P = d->H / 2; Q = d->W / 2; ncls = 4; }
+  int lw, lh;
+  pick_box(P, Q, &lw, &lh);
+  if ((128 >> (lw + lh)) != 1) return 0;
+  return ncls * ceil_div(P, 1 << lh) * ceil_div(Q, 1 << lw);
+}
+
 int conv_fprop_umma_bf16_launch(const srgan_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                                int act, float slope, cudaStream_t st) {
+                                int act, float slope, cudaStream_t st, float* stats) {
   if (!conv_umma_bf16_supported(d, 0)) { set_error("bf16 conv fprop: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  if (stats && !conv_umma_bf16_stat_rows(d, 0)) { set_error("bf16 conv fprop: tile statistics not available for this shape"); return SRGAN_E_UNSUPPORTED; }
   Problem pr = {};
   fprop_problem(d, x, w, pr);
-  return run_problem_t<__nv_bfloat16>(pr, bias, (__nv_bfloat16*)y, act, slope, st, nullptr, nullptr);
+  return run_problem_t<__nv_bfloat16>(pr, bias, (__nv_bfloat16*)y, act, slope, st, nullptr, nullptr, stats);
 }
 
 int conv_dgrad_umma_bf16_launch(const srgan_conv_desc* d, const void* dy, const void* w, void* dx, void* ws,
-                                size_t ws_bytes, cudaStream_t st, const void* addend) {
+                                size_t ws_bytes, cudaStream_t st, const void* addend, float* stats) {
   if (!conv_umma_bf16_supported(d, 1)) { set_error("bf16 conv dgrad: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  if (stats && !conv_umma_bf16_stat_rows(d, 1)) { set_error("bf16 conv dgrad: tile statistics not available for this shape"); return SRGAN_E_UNSUPPORTED; }
   if (addend && d->stride != 1) { set_error("bf16 conv dgrad: fused addend only for stride 1"); return SRGAN_E_UNSUPPORTED; }
   const int T = d->R * d->S;
   const size_t need = conv_umma_bf16_workspace(d, 1);
@@ -1203,7 +1293,7 @@ int conv_dgrad_umma_bf16_launch(const srgan_conv_desc* d, const void* dy, const 
   Problem pr = {};
   dgrad_problem(d, dy, wt, pr);
   return run_problem_t<__nv_bfloat16>(pr, nullptr, (__nv_bfloat16*)dx, SRGAN_ACT_NONE, 0.f, st, nullptr,
-                                      (const __nv_bfloat16*)addend);
+                                      (const __nv_bfloat16*)addend, stats);
 }
 
 void splitk_reduce_launch(const float* part, float* out, long long n, int splits, cudaStream_t st);

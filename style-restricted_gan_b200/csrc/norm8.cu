@@ -461,12 +461,37 @@ static bool plan_norm8(int N, int HW, int C, int atom_rows, Norm8P* out) {
 
 static size_t norm8_ws_bytes(const Norm8P& p) { return (size_t)p.N * p.SL * p.C8 * 16 * sizeof(double); }
 
+// mean / rstd of every (image, channel) from the per-tile sums a convolution epilogue wrote (conv_umma.cu STATS):
+// rows of one image are added in row order in fp64: the result does not depend on the batch.
+__global__ void inorm_stats_from_tiles_kernel(const float2* __restrict__ tiles, int rows, int N, int C, float inv_hw,
+                                              float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const float2* src = tiles + (size_t)n * rows * C + c;
+  double s1 = 0., s2 = 0.;
+  int r = 0;
+  for (; r + 3 < rows; r += 4) {                       // 4 independent loads in flight, fixed summation order
+    const float2 a = __ldg(src + (size_t)r * C), b = __ldg(src + (size_t)(r + 1) * C);
+    const float2 c2 = __ldg(src + (size_t)(r + 2) * C), d = __ldg(src + (size_t)(r + 3) * C);
+    s1 += (double)a.x; s2 += (double)a.y; s1 += (double)b.x; s2 += (double)b.y;
+    s1 += (double)c2.x; s2 += (double)c2.y; s1 += (double)d.x; s2 += (double)d.y;
+  }
+  for (; r < rows; ++r) { const float2 a = __ldg(src + (size_t)r * C); s1 += (double)a.x; s2 += (double)a.y; }
+  const double m = s1 * (double)inv_hw;
+  double var = s2 * (double)inv_hw - m * m;
+  if (var < 0.) var = 0.;
+  mean[i] = (float)m;
+  rstd[i] = rsqrtf((float)var + eps);
+}
+
 template <typename TX, typename TY, int ACT>
 static void launch_fwd8(const Norm8P& p, const void* x, void* y, float* mean, float* rstd, const float* gamma,
                         const float* beta, const float* cbias, const void* residual, void* ws, int* counters,
-                        cudaStream_t st) {
-  inorm8_stats_kernel<TX><<<dim3(p.SL, p.N, p.chunks), kN8Threads, 0, st>>>(p, (const TX*)x, (double*)ws, counters,
-                                                                            mean, rstd);
+                        cudaStream_t st, bool stats_given) {
+  if (!stats_given)
+    inorm8_stats_kernel<TX><<<dim3(p.SL, p.N, p.chunks), kN8Threads, 0, st>>>(p, (const TX*)x, (double*)ws, counters,
+                                                                              mean, rstd);
   inorm8_apply_kernel<TX, TY, ACT><<<dim3(p.SLa, p.N, p.chunks), kN8Threads, 0, st>>>(
       p, (const TX*)x, (TY*)y, mean, rstd, gamma, beta, cbias, (const TY*)residual);
 }
@@ -521,8 +546,8 @@ static int check8(const void* a, const void* b, int N, int HW, int C, int x_dtyp
 
 extern "C" int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, float* mean, float* rstd,
                                      const float* gamma, const float* beta, const float* cbias, const void* residual,
-                                     int N, int HW, int C, float eps, int act, float slope, void* ws, size_t ws_bytes,
-                                     int* counters, void* stream) {
+                                     int N, int HW, int C, float eps, int act, float slope, int stats_given, void* ws,
+                                     size_t ws_bytes, int* counters, void* stream) {
   if (int e = check8(x, y, N, HW, C, x_dtype, y_dtype, counters)) return e;
   SRGAN_CHECK_ARG(mean && rstd, "null pointer");
   SRGAN_CHECK_ARG(((uintptr_t)x | (uintptr_t)y | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma |
@@ -535,7 +560,19 @@ extern "C" int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_
   if (!ws || ws_bytes < norm8_ws_bytes(p)) { set_error("inorm_fwd_mixed: workspace %zu < %zu", ws_bytes, norm8_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
-  SRGAN_N8_TYPES(launch_fwd8, p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, counters, st);
+  SRGAN_N8_TYPES(launch_fwd8, p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, counters, st, stats_given != 0);
+  SRGAN_RETURN_LAUNCH();
+}
+
+extern "C" int srgan_inorm_stats_from_tiles(const float* tile_stats, int rows, int N, int HW, int C, float eps,
+                                            float* mean, float* rstd, void* stream) {
+  SRGAN_CHECK_ARG(tile_stats && mean && rstd, "null pointer");
+  SRGAN_CHECK_ARG(rows > 0 && N >= 0 && HW > 0 && C > 0, "bad sizes");
+  SRGAN_CHECK_ARG((uintptr_t)tile_stats % 8 == 0, "tile statistics must be 8-byte aligned");
+  if (N == 0) return SRGAN_OK;
+  const int total = N * C;
+  inorm_stats_from_tiles_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
+      (const float2*)tile_stats, rows, N, C, 1.f / (float)HW, eps, mean, rstd);
   SRGAN_RETURN_LAUNCH();
 }
 

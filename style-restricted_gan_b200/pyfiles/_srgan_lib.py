@@ -33,15 +33,17 @@ SIGNATURES = {
     "srgan_conv2d_wgrad_plan": (c_int, [DP, P, P]),
     "srgan_conv2d_bf16_supported": (c_int, [DP, c_int]),
     "srgan_conv2d_bf16_workspace": (c_size_t, [DP, c_int]),
-    "srgan_conv2d_fprop_bf16": (c_int, [DP, P, P, P, P, c_int, c_float, P]),
-    "srgan_conv2d_dgrad_bf16": (c_int, [DP, P, P, P, P, P, c_size_t, P]),
+    "srgan_conv2d_fprop_bf16": (c_int, [DP, P, P, P, P, c_int, c_float, P, P]),
+    "srgan_conv2d_dgrad_bf16": (c_int, [DP, P, P, P, P, P, P, c_size_t, P]),
+    "srgan_conv2d_bf16_stat_rows": (c_int, [DP, c_int]),
+    "srgan_inorm_stats_from_tiles": (c_int, [P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "srgan_conv2d_wgrad_bf16": (c_int, [DP, P, P, P, P, c_size_t, P]),
     "srgan_conv2d_wgrad_bf16_plan": (c_int, [DP, P, P]),
     "srgan_cast_f32_bf16": (c_int, [P, P, c_size_t, P]),
     "srgan_inorm_mixed_workspace": (c_size_t, [c_int, c_int, c_int]),
     "srgan_inorm_mixed_counters": (c_size_t, [c_int, c_int]),
     "srgan_inorm_fwd_mixed": (c_int, [P, c_int, P, c_int, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int,
-                                      c_float, P, c_size_t, P, P]),
+                                      c_float, c_int, P, c_size_t, P, P]),
     "srgan_inorm_bwd_mixed": (c_int, [P, c_int, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float,
                                       P, c_size_t, P, P]),
     "srgan_conv2d_dgrad_add_supported": (c_int, [DP, c_int]),

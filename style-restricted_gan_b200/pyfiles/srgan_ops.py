@@ -428,14 +428,43 @@ def _need16(d, p):
             "counts that are multiples of 64" % (("fprop", "dgrad", "wgrad")[p], d.N, d.C, d.K, d.R, d.S, d.stride))
 
 
-def _fprop(d, x, w, bias, act, slope, out_dtype=None):
-    """w: the filter in the storage `x` asks for (see _conv_weight)."""
+# Per-tile statistics written by the epilogue of the last bf16 FORWARD convolution, waiting for the instance norm that
+# consumes its output: (data_ptr of the output, [N, rows, K, 2] fp32, rows).  See srgan_conv2d_fprop_bf16.
+_tile_stats = None
+_NO_TILE_STATS = os.environ.get("SRGAN_DBG_NO_TILE_STATS", "0") != "0"     # bring-up: norms compute their own statistics
+
+
+def _tile_stats_buffer(d, p, out, plain):
+    """fp32 [N, rows, K_out, 2] when the pass can deliver tile statistics for `out` (and the epilogue is plain)."""
+    if _NO_TILE_STATS or not plain:
+        return None, 0
+    rows = _lib().srgan_conv2d_bf16_stat_rows(d, p)
+    if rows <= 0:
+        return None, 0
+    return torch.empty((out.shape[0], rows, out.shape[1], 2), dtype=torch.float32, device=out.device), rows
+
+
+def _take_tile_stats(x):
+    """The pending tile statistics if they describe `x` (consumed), else None."""
+    global _tile_stats
+    ts, _tile_stats = _tile_stats, None
+    if ts is not None and ts[0] == x.data_ptr() and ts[1].shape[0] == x.shape[0] and ts[1].shape[2] == x.shape[1]:
+        return ts[1], ts[2]
+    return None
+
+
+def _fprop(d, x, w, bias, act, slope, out_dtype=None, want_stats=False):
+    """w: the filter in the storage `x` asks for (see _conv_weight).  want_stats (bf16, forward passes): also produce
+    the tile statistics for the instance norm that follows."""
+    global _tile_stats
     if x.dtype == BF16:
         y = _empty_nhwc(d.N, d.K, d.P, d.Q, x)
         if y.numel() == 0:
             return y
         _need16(d, 0)
-        _call("srgan_conv2d_fprop_bf16", d, _p(x), _p(w), _p(bias), _p(y), act, slope, _stream())
+        ts, rows = _tile_stats_buffer(d, 0, y, bias is None and act == ACT_NONE) if want_stats else (None, 0)
+        _call("srgan_conv2d_fprop_bf16", d, _p(x), _p(w), _p(bias), _p(y), act, slope, _p(ts), _stream())
+        _tile_stats = (y.data_ptr(), ts, rows) if ts is not None else None
         return y
     y = _empty_nhwc(d.N, d.K, d.P, d.Q, x)
     if y.numel() == 0:
@@ -447,8 +476,10 @@ def _fprop(d, x, w, bias, act, slope, out_dtype=None):
     return y
 
 
-def _dgrad(d, dy, w, like, addend=None):
-    """dx = dgrad(dy) (+ addend, fused into the epilogue where the engine supports it)."""
+def _dgrad(d, dy, w, like, addend=None, want_stats=False):
+    """dx = dgrad(dy) (+ addend, fused into the epilogue where the engine supports it).  want_stats: see _fprop (the
+    forward pass of a transposed convolution is a dgrad)."""
+    global _tile_stats
     dx = _empty_nhwc(d.N, d.C, d.H, d.W, like, dtype=dy.dtype)
     if dx.numel() == 0:
         return dx
@@ -462,7 +493,10 @@ def _dgrad(d, dy, w, like, addend=None):
             addend = _raw_to_nhwc(addend)
             if addend.dtype != BF16:
                 raise SrganKernelError("dgrad: the skip gradient must have the storage type of dy")
-        _call("srgan_conv2d_dgrad_bf16", d, _p(dy), _p(w), _p(addend) if fused else None, _p(dx), _p(ws), nb, _stream())
+        ts, rows = _tile_stats_buffer(d, 1, dx, addend is None) if want_stats else (None, 0)
+        _call("srgan_conv2d_dgrad_bf16", d, _p(dy), _p(w), _p(addend) if fused else None, _p(dx), _p(ts), _p(ws), nb,
+              _stream())
+        _tile_stats = (dx.data_ptr(), ts, rows) if ts is not None else None
         if addend is not None and not fused:
             dx.add_(addend)
         return dx
@@ -570,7 +604,7 @@ class _Conv2dFn(torch.autograd.Function):
         if C2 != C:
             raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
         d = _desc(N, H, W, C, K, R, S, stride, pad)
-        y = _fprop(d, x, _conv_weight(weight, x), bias, act, slope)
+        y = _fprop(d, x, _conv_weight(weight, x), bias, act, slope, want_stats=True)
         ctx.d, ctx.act, ctx.slope = d, act, slope
         ctx.weight, ctx.bias, ctx.has_bias = weight, bias, bias is not None
         ctx.save_for_backward(x, y if act != ACT_NONE else None)
@@ -606,7 +640,7 @@ class _Conv2dSkipFn(torch.autograd.Function):
         if C2 != C:
             raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
         d = _desc(N, H, W, C, K, R, S, stride, pad)
-        y = _fprop(d, x, _conv_weight(weight, x), None, ACT_NONE, 0.0)
+        y = _fprop(d, x, _conv_weight(weight, x), None, ACT_NONE, 0.0, want_stats=True)
         ctx.d, ctx.weight = d, weight
         ctx.save_for_backward(x)
         return y, x.view_as(x)
@@ -640,7 +674,7 @@ class _ConvTranspose2dFn(torch.autograd.Function):
         Wo = (W - 1) * stride - 2 * pad + S
         d = _desc(N, Ho, Wo, Cout, Cin, R, S, stride, pad)     # mirrored conv: (Ho,Wo,Cout) -> (H,W,Cin)
         assert d.P == H and d.Q == W
-        y = _dgrad(d, x, _conv_weight(weight, x), x)
+        y = _dgrad(d, x, _conv_weight(weight, x), x, want_stats=True)
         ctx.d, ctx.weight = d, weight
         ctx.save_for_backward(x)
         return y
@@ -801,12 +835,17 @@ class _InstanceNormFn(torch.autograd.Function):
         mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
         rstd = torch.empty((N, C), dtype=torch.float32, device=x.device)
         mixed = x.dtype != torch.float32 or out_dtype != torch.float32
+        tiles = _take_tile_stats(x)
         if x.numel():
             if mixed:
                 nb = _lib().srgan_inorm_mixed_workspace(N, H * W, C)
                 ws = _workspace(x.device, nb)
+                if tiles is not None:
+                    # the convolution that produced x left per-tile sums: no statistics pass over x
+                    _call("srgan_inorm_stats_from_tiles", _p(tiles[0]), tiles[1], N, H * W, C, eps, _p(mean), _p(rstd),
+                          _stream())
                 _call("srgan_inorm_fwd_mixed", _p(x), _dt(x), _p(y), _dt(y), _p(mean), _p(rstd), _p(gamma), _p(beta),
-                      _p(cbias), _p(residual), N, H * W, C, eps, act, slope, _p(ws), nb,
+                      _p(cbias), _p(residual), N, H * W, C, eps, act, slope, int(tiles is not None), _p(ws), nb,
                       _p(_norm_counters(x.device, N, C)), _stream())
             else:
                 nb = _lib().srgan_inorm_workspace(N, H * W, C)

@@ -41,7 +41,8 @@ def test_fprop_bf16(g):
     assert ops._lib().srgan_conv2d_bf16_supported(d, 0) == 1
     y = torch.empty((N, K, d.P, d.Q), dtype=torch.bfloat16, device=DEV).contiguous(memory_format=CL)
     for act, slope, fn in ((ops.ACT_NONE, 0.0, lambda t: t), (ops.ACT_LRELU, 0.2, lambda t: F.leaky_relu(t, 0.2))):
-        ops._call("srgan_conv2d_fprop_bf16", d, ops._p(x), ops._p(w), ops._p(b), ops._p(y), act, slope, ops._stream())
+        ops._call("srgan_conv2d_fprop_bf16", d, ops._p(x), ops._p(w), ops._p(b), ops._p(y), act, slope, None,
+                  ops._stream())
         ref = fn(F.conv2d(x.float(), w.float(), b, stride, pad))
         assert _rel(y.float(), ref) < TOL, (g, act)
 
@@ -61,12 +62,12 @@ def test_dgrad_bf16(g):
     nb = ops._lib().srgan_conv2d_bf16_workspace(d, 1)
     ws = ops._workspace(torch.device(DEV, torch.cuda.current_device()), nb)
     dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=DEV).contiguous(memory_format=CL)
-    ops._call("srgan_conv2d_dgrad_bf16", d, ops._p(dy), ops._p(w), None, ops._p(dx), ops._p(ws), nb, ops._stream())
+    ops._call("srgan_conv2d_dgrad_bf16", d, ops._p(dy), ops._p(w), None, ops._p(dx), None, ops._p(ws), nb, ops._stream())
     ref = torch.nn.grad.conv2d_input((N, C, H, W), w.float(), dy.float(), stride, pad)
     assert _rel(dx.float(), ref) < TOL, g
     if stride == 1:
         add = _nhwc_bf16(torch.randn(N, C, H, W))
-        ops._call("srgan_conv2d_dgrad_bf16", d, ops._p(dy), ops._p(w), ops._p(add), ops._p(dx), ops._p(ws), nb,
+        ops._call("srgan_conv2d_dgrad_bf16", d, ops._p(dy), ops._p(w), ops._p(add), ops._p(dx), None, ops._p(ws), nb,
                   ops._stream())
         assert _rel(dx.float(), ref + add.float()) < TOL, g
 
@@ -90,8 +91,13 @@ def test_bf16_res_conv_rate():
             ts.append(a.elapsed_time(b))
         ts.sort()
         return ts[len(ts) // 2]
-    t16 = timed(lambda: ops._call("srgan_conv2d_fprop_bf16", d, ops._p(x), ops._p(w), None, ops._p(y), 0, 0.0,
+    t16 = timed(lambda: ops._call("srgan_conv2d_fprop_bf16", d, ops._p(x), ops._p(w), None, ops._p(y), 0, 0.0, None,
                                   ops._stream()))
+    rows = ops._lib().srgan_conv2d_bf16_stat_rows(d, 0)
+    ts = torch.empty((N, rows, K, 2), device=DEV)
+    t16s = timed(lambda: ops._call("srgan_conv2d_fprop_bf16", d, ops._p(x), ops._p(w), None, ops._p(y), 0, 0.0,
+                                   ops._p(ts), ops._stream()))
+    print("res conv fprop with tile statistics in the epilogue: %.1f us" % (t16s * 1e3))
     t32 = timed(lambda: ops.conv2d(xf, wf, None, 1, 1))
     fl = 2.0 * N * H * W * K * C * 9
     print("res conv fprop: bf16 %.1f us (%.0f TF/s)   tf32 %.1f us (%.0f TF/s)" %
@@ -283,3 +289,51 @@ def test_bf16_cuda_graph_replay_is_bit_identical_to_eager():
         ops.set_conv_engine("auto")
     assert le == lg, (le, lg)
     assert torch.equal(pe, pg)
+
+
+STAT_GEOMS = [  # N, C, H, W, K, R, stride, pad, transposed
+    (5, 256, 32, 32, 256, 3, 1, 1, False),     # residual block: 8 tiles per image, 256-wide tiles (+ half-width tail)
+    (3, 64, 128, 128, 128, 4, 2, 1, False),    # down1: MT = 2 sub-tiles
+    (70, 256, 32, 32, 256, 3, 1, 1, False),    # more than three waves of tiles
+    (3, 256, 32, 32, 128, 4, 2, 1, True),      # up0: transposed conv = dgrad with 4 output-parity classes
+    (2, 128, 64, 64, 64, 4, 2, 1, True),       # up1
+]
+
+
+@pytest.mark.parametrize("g", STAT_GEOMS)
+def test_tile_statistics_from_the_conv_epilogue(g):
+    """The bf16 forward convolutions write per-tile sum / sum of squares of their (stored) outputs; the instance norm
+    behind them folds those instead of reading the tensor (srgan_inorm_stats_from_tiles).  Checks the raw sums against
+    torch on the stored output and the fused conv -> norm against the same norm run stand-alone."""
+    N, C, H, W, K, R, stride, pad, transposed = g
+    torch.manual_seed(5)
+    x = _nhwc_bf16(torch.randn(N, C, H, W)).requires_grad_(True)
+    gam, bet, cb = torch.randn(K, device=DEV), torch.randn(K, device=DEV), torch.randn(N, K, device=DEV)
+    if transposed:
+        w = (torch.randn(C, K, R, R, device=DEV) * 0.05).contiguous(memory_format=CL)
+        conv = lambda: ops.conv_transpose2d(x, w, stride, pad)
+    else:
+        w = (torch.randn(K, C, R, R, device=DEV) * 0.05).contiguous(memory_format=CL)
+        conv = lambda: ops.conv2d(x, w, None, stride, pad)
+    y = conv()
+    pending = ops._tile_stats
+    assert pending is not None and pending[0] == y.data_ptr(), "the forward convolution should leave tile statistics"
+    tiles, rows = pending[1], pending[2]
+    HW = y.shape[2] * y.shape[3]
+    assert rows * 128 == HW
+    yf = y.detach().float()
+    s1 = tiles[..., 0].sum(1)
+    s2 = tiles[..., 1].sum(1)
+    assert _rel(s1, yf.sum((2, 3))) < 1e-4 and _rel(s2, (yf * yf).sum((2, 3))) < 1e-5
+    fused = ops.instance_norm_act(y, gam, bet, cb, None, 1e-5, ops.ACT_RELU, 0.0)
+    assert ops._tile_stats is None                       # consumed
+    alone = ops.instance_norm_act(y.detach().clone(), gam, bet, cb, None, 1e-5, ops.ACT_RELU, 0.0)
+    assert _rel(fused, alone) < 2e-3                     # same statistics up to fp32 rounding, outputs rounded to bf16
+    assert float((fused.float() - alone.float()).abs().max()) < 0.1
+    # backward goes through the saved statistics
+    gy = _nhwc_bf16(torch.randn(*fused.shape))
+    dx_f, = torch.autograd.grad(fused, x, gy)
+    y2 = conv()
+    ops._tile_stats = None
+    dx_a, = torch.autograd.grad(ops.instance_norm_act(y2, gam, bet, cb, None, 1e-5, ops.ACT_RELU, 0.0), x, gy)
+    assert _rel(dx_f, dx_a) < 1e-2

@@ -175,27 +175,46 @@ def time_dominant_kernel(batch, dev):
 
 
 def time_norm_kernel(batch, dev):
-    """CUDA-event time of the fused instance-norm forward on [batch, 256, 32, 32], L2 flushed between launches."""
+    """CUDA-event time of the fused instance-norm forward on [batch, 256, 32, 32] as the training step runs it, L2
+    flushed between launches.  Returns (ms as shipped, ms stand-alone, description).
+    bf16 trunk: the convolution that produces the tensor leaves per-tile sums (conv_umma STATS), so the norm is ONE
+    pass (fold of the tile rows + apply kernel: read x, write y); stand-alone (and on fp32 storage) it is the
+    statistics kernel + the apply kernel."""
     import srgan_ops as ops
+    bf16 = ops.get_conv_engine() == "bf16"
     x = torch.randn(batch, 256, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
-    if ops.get_conv_engine() == "bf16":
-        x = x.to(torch.bfloat16)
     g, b = torch.ones(256, device=dev), torch.zeros(256, device=dev)
     cb = torch.randn(batch, 256, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
+    tiles = None
+    if bf16:
+        w = (torch.randn(256, 256, 3, 3, device=dev) * 0.02).contiguous(memory_format=torch.channels_last)
+        x = ops.conv2d(x.to(torch.bfloat16), w, None, 1, 1)          # a real trunk tensor (+ tile statistics if enabled)
+        tiles, ops._tile_stats = ops._tile_stats, None
+
+    def run(fused):
+        if fused:
+            ops._tile_stats = tiles
         ops.instance_norm_act(x, g, b, cb, None, 1e-5, ops.ACT_RELU, 0.0)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.instance_norm_act(x, g, b, cb, None, 1e-5, ops.ACT_RELU, 0.0)
-        e1.record()
+
+    def timed(fused):
+        for _ in range(3):
+            run(fused)
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return float(np.mean(ts))
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(fused)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts))
+    alone = timed(False)
+    if tiles is None:
+        return alone, alone, "statistics kernel + apply kernel"
+    return timed(True), alone, "tile statistics from the producing convolution's epilogue: fold + apply kernel"
 
 
 def measure_tf32_peak(dev):
@@ -472,13 +491,16 @@ def run_ours(args):
                 "step_tflops": value * GF_PER_IMG[args.workload] / 1e3}
         # secondary roofline: the fused instance-norm (+ conditional bias + affine + ReLU) forward of the residual
         # blocks, HBM bound; algorithmic bytes = read x + write y
-        nms = time_norm_kernel(batch, dev)
+        nms, nms_alone, nhow = time_norm_kernel(batch, dev)
         nbytes = 2.0 * (4 if is_tf32 or kname == "ffma_fp32" else 2) * batch * 256 * 1024
-        glue = {"bound": "hbm", "kernel": "instance norm + cond. bias + affine + ReLU forward, 256 ch @32x32",
+        glue = {"bound": "hbm", "kernel": "instance norm + cond. bias + affine + ReLU forward, 256 ch @32x32 (" + nhow + ")",
                 "achieved": nbytes / (nms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": nbytes / (nms * 1e-3) / 1e9 / pk["hbm"], "kernel_ms": nms,
-                "note": "two kernels (statistics, apply) = 3 passes over the plane for 2 algorithmic ones; a plain "
-                        "device copy of the same plane reaches ~4.7 TB/s (tools/stream_probe.cu)"}
+                "algorithmic_bytes": nbytes, "standalone_ms": nms_alone,
+                "standalone_frac": nbytes / (nms_alone * 1e-3) / 1e9 / pk["hbm"],
+                "note": "algorithmic bytes = read x + write y (SURVEY 8d); peak = MEASURED_PEAKS.json hbm_gbs, a copy "
+                        "of 2 GB - a plain device copy of a plane of this size reaches ~4.7 TB/s "
+                        "(tools/stream_probe.cu)"}
         cpu = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1

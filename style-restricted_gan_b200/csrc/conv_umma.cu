@@ -76,7 +76,8 @@ struct UmmaCfg {
   static constexpr int kStages = (212 * 1024) / kStageBytes < 8 ? (212 * 1024) / kStageBytes : 8;
   static constexpr int kAccBufs = 2 * MT * BN <= 512 ? 2 : 1;   // accumulator double buffering when TMEM allows
   static constexpr int kTmemCols = kAccBufs * MT * BN < 32 ? 32 : kAccBufs * MT * BN;
-  static constexpr size_t kStatBytes = 4 * BN * 2 * sizeof(float);   // per-quadrant column sums of one tile (STATS)
+  // STATS: per-quadrant column sums of one tile [4][BN][2] + a private 32 x 17 transpose pad per epilogue warp
+  static constexpr size_t kStatBytes = 4 * BN * 2 * sizeof(float) + 4 * 32 * 17 * sizeof(float);
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
   // TMA issue: measured with tools/tma_probe.cu, the bulk-tensor loads of ONE warp execute back to back (~750-1100
   // clk each, whatever their size) while loads of different warps overlap.  A stage is therefore cut into kBoxes
@@ -231,20 +232,6 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Column sums over the 32 rows (lanes) of a warp: every lane passes 32 values s[0..31] (one per column); on return
-// s[0] of lane L is the sum over all lanes of column L.  Butterfly transpose-reduce: 31 shuffles, fixed order.
-__device__ __forceinline__ void warp_colsum32(float (&s)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int j = 0; j < off; ++j) {
-      const float send = up ? s[j] : s[j + off];       // the half this lane does not keep
-      const float keep = up ? s[j + off] : s[j];
-      s[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // 4 epilogue warps
 
 // work item -> linear tile index, first column and width of the column range it covers
@@ -277,6 +264,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tempty = tfull + 2;                    // [NBUF] accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sstat = reinterpret_cast<float*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes + 256);   // [4][BN][2]
+  float* wpad = sstat + 4 * BN * 2;                                                                // [4][32][17]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bw = 1 << p.lw, bh = 1 << p.lh;
@@ -409,24 +397,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
             if (STATS) {
-              // column sums of the values as they are stored (rounded to ST), rows outside the image count as zero
-              float t[32];
+              // Column sums over the warp's 32 pixel rows of the values as they are stored (rounded to ST; rows outside
+              // the image count as zero), 16 columns at a time through a private 32 x 17 pad: every lane writes its
+              // row, then adds 16 rows of one column (lanes 0-15: even rows, lanes 16-31: odd rows), one shuffle joins
+              // the two halves.  ~240 instructions per 32 x 32 chunk (a shuffle butterfly costs ~1000: the epilogue
+              // warps, not the tensor pipe, then set the pace of the kernel); fixed summation order.
+              float* wst = wpad + quad * (32 * 17);
+              const int scol = lane & 15, srow = lane >> 4;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float a = valid ? v[j] : 0.f;
-                if (sizeof(ST) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
-                t[j] = a;
-              }
-              warp_colsum32(t, lane);
-              const float sum1 = t[0];
+              for (int h = 0; h < 2; ++h) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float a = valid ? v[j] : 0.f;
-                if (sizeof(ST) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
-                t[j] = a * a;
+                for (int j = 0; j < 16; ++j) {
+                  float a = valid ? v[h * 16 + j] : 0.f;
+                  if (sizeof(ST) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
+                  wst[lane * 17 + j] = a;
+                }
+                __syncwarp();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i2 = 0; i2 < 16; ++i2) {
+                  const float a = wst[(2 * i2 + srow) * 17 + scol];
+                  s1 += a;
+                  s2 = fmaf(a, a, s2);
+                }
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                if (lane < 16)
+                  *reinterpret_cast<float2*>(sstat + ((quad * BN) + c + h * 16 + lane) * 2) = make_float2(s1, s2);
+                __syncwarp();
               }
-              warp_colsum32(t, lane);
-              *reinterpret_cast<float2*>(sstat + ((quad * BN) + c + lane) * 2) = make_float2(sum1, t[0]);
             }
             if (valid) {
               if (col0 + c + 32 <= p.K && p.epi_vec) {

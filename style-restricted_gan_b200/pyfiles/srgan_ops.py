@@ -430,13 +430,25 @@ def _need16(d, p):
 
 # Per-tile statistics written by the epilogue of the last bf16 FORWARD convolution, waiting for the instance norm that
 # consumes its output: (data_ptr of the output, [N, rows, K, 2] fp32, rows).  See srgan_conv2d_fprop_bf16.
+# OPT-IN (SRGAN_TILE_STATS=1).  Measured on B200 (profiles/r2k_*): the residual-block convolution goes from 63.5 to
+# 78.6 us with the statistics in its epilogue (the kernel is bound by shared-memory bandwidth - TMA fill + MMA operand
+# reads - and the column sums need the same port: a shuffle butterfly made it 115.7 us), which is what the saved
+# statistics kernel costs (13.9 us + launch): the training step does not move (60.41 vs 60.45 ms, same box).  The norm
+# itself becomes one pass (fold + apply: 25.7 vs 33.0 us).  Kept for planes where the conv has smem headroom.
 _tile_stats = None
-_NO_TILE_STATS = os.environ.get("SRGAN_DBG_NO_TILE_STATS", "0") != "0"     # bring-up: norms compute their own statistics
+_TILE_STATS = os.environ.get("SRGAN_TILE_STATS", "0") != "0"
+
+
+def set_tile_stats(on):
+    """Enable / disable the conv-epilogue statistics path (see above); returns the previous setting."""
+    global _TILE_STATS
+    prev, _TILE_STATS = _TILE_STATS, bool(on)
+    return prev
 
 
 def _tile_stats_buffer(d, p, out, plain):
     """fp32 [N, rows, K_out, 2] when the pass can deliver tile statistics for `out` (and the epilogue is plain)."""
-    if _NO_TILE_STATS or not plain:
+    if not _TILE_STATS or not plain:
         return None, 0
     rows = _lib().srgan_conv2d_bf16_stat_rows(d, p)
     if rows <= 0:

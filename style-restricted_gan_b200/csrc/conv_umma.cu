@@ -489,6 +489,193 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 
+// ------------------------------------------------------------------------------------------ CTA pairs
+// 256-wide filter tiles on CTA PAIRS (tcgen05 cta_group::2): a cluster of two CTAs computes a 256-pixel x 256-channel
+// tile.  Each CTA loads ITS 128 pixel rows of A and HALF of the filter tile (128 of the 256 output channels); the
+// leader's MMAs (M = 256) read both shared memories and leave 128 accumulator rows in each CTA's tensor memory; each
+// CTA runs the epilogue of its own rows.  Why: the one-CTA kernel is bound by shared-memory bandwidth - per 128-clock
+// MMA it reads 4 KB of A + 8 KB of B while TMA writes the same 12 KB for the next stage: 192 B/clk against a 128 B/clk
+// port (tensor pipe active ~70 % of the time, profiles/r1q_res_ncu_raw.csv) - and, one level up, by the L2 -> SM
+// traffic of re-reading the whole filter for every 128 pixels (14 TB/s on the residual block).  A pair halves the B
+// bytes per CTA on both paths: 64 + 64 B/clk.
+//   barriers: full[s]   leader's; its producer warps arrive with expect_tx for BOTH CTAs' boxes, the peer's TMA
+//                       (cta_group::2) counts its bytes there;
+//             empty[s]  one per CTA, both released by the leader's multicast tcgen05.commit;
+//             tfull[b]  one per CTA (multicast commit), tempty[b] leader's (4 epilogue warps x 2 CTAs arrive).
+template <typename ST> struct Umma2Cfg {
+  static constexpr int kBN = 256, kBHalf = 128;
+  static constexpr int kStageBytes = kABytes + kBHalf * 128;                 // 16 KB of A + 16 KB of B per CTA
+  static constexpr int kStages = 6;
+  static constexpr int kBoxes = 2;                                           // A box, B-half box
+  static constexpr int kProducers = 2 * kBoxes;
+  static constexpr int kThreads = 32 * (5 + kProducers);
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
+  // instruction descriptor: D = f32, A = B = tf32 | bf16, K-major both, N = 256, M = 256 (128 rows per CTA)
+  static constexpr uint32_t kIdesc = (1u << 4) | (UmmaElem<ST>::kFmt << 7) | (UmmaElem<ST>::kFmt << 10) |
+                                     ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);
+};
+template <typename ST>
+__device__ __forceinline__ void umma_any_2sm(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (sizeof(ST) == 4) umma_tf32_2sm(d, a, b, idesc, acc);
+  else umma_f16_2sm(d, a, b, idesc, acc);
+}
+
+// p.gx = PAIRS of 128-pixel tiles per (filter tile, class); work item = (pair, filter tile, class)
+template <typename ST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Umma2Cfg<ST>::kThreads), 1)
+conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, ST* __restrict__ y,
+                  const ST* __restrict__ addend) {
+  using Cfg = Umma2Cfg<ST>;
+  constexpr int BN = Cfg::kBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tfull = empty + Cfg::kStages;          // [2]
+  uint64_t* tempty = tfull + 2;                    // [2] (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int bw = 1 << p.lw, bh = 1 << p.lh;
+  const int bn = 128 >> (p.lw + p.lh);
+  const int items = p.n_items;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kBoxes); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+  }
+  if (warp == 0) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                              // both CTAs' barriers and tensor memory exist
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ TMA producers (one box each, every 2nd stage)
+    if (lane == 0) {
+      const int pw = warp - 5;
+      const int box = pw % Cfg::kBoxes, par = pw / Cfg::kBoxes;
+      int gi0 = 0;
+      for (int item = cluster_id; item < items; item += nclusters) {
+        const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
+        const int tap0 = p.tap_begin[cls];
+        const int iters = (p.tap_begin[cls + 1] - tap0) * p.c_chunks;
+        int t = bx * 2 + (int)rank;                                  // this CTA's 128-pixel tile of the pair
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int qb = tw * bw, pb = (t % p.tiles_h) * bh, nb = (t / p.tiles_h) * bn;
+        for (int it = (gi0 + par) & 1; it < iters; it += 2) {
+          const int gi = gi0 + it;
+          const int stage = gi % Cfg::kStages;
+          const uint32_t phase = (uint32_t)(gi / Cfg::kStages) & 1u;
+          const int4 tp = p.taps[tap0 + it / p.c_chunks];
+          const int cc = (it % p.c_chunks) * UmmaElem<ST>::kRow;
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
+          // the leader's barrier counts this box of BOTH CTAs (same size, OOB rows are zero-filled but counted)
+          if (leader) mbar_expect_tx(full + stage, 2 * kABytes);
+          if (box == 0)
+            tma_load_5d_2sm(&map_a, full + stage, sa, cc + tp.x, qb + tp.y, tp.z & 0xff, pb + tp.w, nb);
+          else
+            tma_load_3d_2sm(&map_b, full + stage, sa + kABytes, cc, tp.z >> 8, by * BN + (int)rank * Cfg::kBHalf);
+        }
+        gi0 += iters;
+      }
+    }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader)
+    if (leader && lane == 0) {
+      int stage = 0, li = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < items; item += nclusters, ++li) {
+        const int cls = item / (p.gx * p.gy);
+        const int iters = (p.tap_begin[cls + 1] - p.tap_begin[cls]) * p.c_chunks;
+        const int buf = li & 1;
+        mbar_wait(tempty + buf, (((uint32_t)(li >> 1)) & 1u) ^ 1u);       // both epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+          const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_any_2sm<ST>(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc, (it | k) != 0);
+          umma_commit_2sm(empty + stage, 3);       // both CTAs may refill this stage
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull + buf, 3);           // accumulator complete, in both CTAs
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue of this CTA's 128 rows
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int wl = m & (bw - 1), hl = (m >> p.lw) & (bh - 1), nl = m >> (p.lw + p.lh);
+    const uint32_t tempty_leader = mapa_shared(smem_u32(tempty), 0);
+    int li = 0;
+    for (int item = cluster_id; item < items; item += nclusters, ++li) {
+      const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
+      const int col0 = by * BN;
+      const int buf = li & 1;
+      mbar_wait(tfull + buf, ((uint32_t)(li >> 1)) & 1u);
+      tc_fence_after();
+      int t = bx * 2 + (int)rank;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int n = (t / p.tiles_h) * bn + nl, pp = (t % p.tiles_h) * bh + hl, qq = tw * bw + wl;
+      const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
+      ST* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
+                      (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+      const float* brow = bias ? bias + col0 : nullptr;
+      const ST* arow = addend ? addend + (yrow - y) + col0 : nullptr;
+      uint32_t ra[32], rb[32];
+      tmem_ld32_issue(taddr, ra);
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t (&cur)[32] = ((c >> 5) & 1) ? rb : ra;
+        uint32_t (&nxt)[32] = ((c >> 5) & 1) ? ra : rb;
+        tmem_ld_wait();
+        if (c + 32 < BN) tmem_ld32_issue(taddr + c + 32, nxt);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
+        if (valid) {
+          if (col0 + c + 32 <= p.K && p.epi_vec) {
+            epi_row_chunk_any<32>(v, yrow + col0 + c, brow ? brow + c : nullptr, p.act, p.slope, p.epi_vec,
+                                  arow ? arow + c : nullptr);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + c + j < p.K)
+                st_from_float(yrow + col0 + c + j,
+                              apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f) +
+                                        (arow ? ld_as_float(arow + c + j) : 0.f), p.act, p.slope));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                              // nobody leaves while its partner still needs its memories
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ wgrad
 // dW[k][t][c] = sum over pixels m :  dY[m][k] * X_t[m][c]          (X_t = x shifted by tap t, zero outside)
 // Both operands are "MN-major": the reduction index (pixel) is the slow dimension in memory.  A stage holds a
@@ -730,6 +917,48 @@ static int pick_bn(int K) {
   return 16;
 }
 
+// CTA pairs for 256-wide tiles: SRGAN_CONV_PAIRS = 0 (off) | 1 (bf16 storage, default) | 2 (bf16 and TF32)
+template <typename ST>
+static bool use_cta_pairs(long tiles) {
+  static const int mode = getenv("SRGAN_CONV_PAIRS") ? atoi(getenv("SRGAN_CONV_PAIRS")) : 1;
+  if (mode <= 0 || (sizeof(ST) == 4 && mode < 2)) return false;
+  return tiles >= 2 * kNumSMs;                      // at least two full waves of single tiles: every pair has work
+}
+
+template <typename ST>
+static int launch_pairs(const CUtensorMap& ma, const CUtensorMap& mb_full, const UmmaConvP& p, const float* bias, ST* y,
+                        dim3 grid, cudaStream_t st, const ST* addend) {
+  using Cfg = Umma2Cfg<ST>;
+  static unsigned long long attr_done = 0;
+  static int max_clusters[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    cudaError_t e = ensure_dyn_smem(conv_umma2_kernel<ST>, (int)Cfg::kSmem, &attr_done);
+    if (e != cudaSuccess) { set_error("conv_umma2 smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  if (dev < 64 && max_clusters[dev] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * kNumSMs); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_umma2_kernel<ST>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = kNumSMs / 2; }
+    max_clusters[dev] = n;
+  }
+  const int nmax = dev < 64 ? max_clusters[dev] : kNumSMs / 2;
+  UmmaConvP q = p;
+  q.gx = (grid.x + 1) / 2; q.gy = grid.y; q.gz = grid.z;          // pairs of 128-pixel tiles
+  const long items = (long)q.gx * q.gy * q.gz;
+  q.n_full = q.n_items = (int)items;
+  const unsigned clusters = (unsigned)(items < nmax ? items : nmax);
+  // the filter map of the pair kernel: boxes of 128 filters (half a tile) - same geometry as mb_full's kBRows box
+  conv_umma2_kernel<ST><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb_full, q, bias, y, addend);
+  SRGAN_RETURN_LAUNCH();
+}
+
 template <int BN, int MT, typename ST>
 static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, ST* y,
                      dim3 grid, cudaStream_t st, const ST* addend, float* stats = nullptr) {
@@ -743,6 +972,10 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
   if (stats && !kCanStat) { set_error("conv_umma: tile statistics need bf16 storage and >= 32 output channels"); return SRGAN_E_UNSUPPORTED; }
+  if constexpr (BN == 256 && MT == 1) {
+    if (!stats && use_cta_pairs<ST>((long)grid.x * grid.y * grid.z))
+      return launch_pairs<ST>(ma, mb, p, bias, y, grid, st, addend);
+  }
   UmmaConvP q = p;
   q.gx = (grid.x + MT - 1) / MT; q.gy = grid.y; q.gz = grid.z;
   long items = (long)q.gx * q.gy * q.gz;

@@ -346,3 +346,39 @@ def _tile_stats_case(N, C, H, W, K, R, stride, pad, transposed):
     ops._tile_stats = None
     dx_a, = torch.autograd.grad(ops.instance_norm_act(y2, gam, bet, cb, None, 1e-5, ops.ACT_RELU, 0.0), x, gy)
     assert _rel(dx_f, dx_a) < 1e-2
+
+
+PAIR_GEOMS = [  # N, C, H, W, K, R, stride, pad  -- >= 296 tiles of 128 pixels and 256-wide filter tiles: CTA pairs
+    (64, 256, 32, 32, 256, 3, 1, 1),    # the residual block at the production batch (512 tiles, 256 pairs, 3.5 waves)
+    (99, 64, 24, 16, 256, 3, 1, 1),     # 3 tiles per image x 99 images: an odd tile count, the last pair is half empty
+    (40, 128, 64, 64, 512, 4, 2, 1),    # stride 2 (parity view of x), two filter tiles
+]
+
+
+@pytest.mark.parametrize("g", PAIR_GEOMS)
+def test_cta_pair_kernel_fprop_dgrad(g):
+    """conv_umma2_kernel (tcgen05 cta_group::2: two CTAs per 256 x 256 tile, leader issues the MMAs) against torch on
+    the same bf16-rounded operands, forward with bias + LeakyReLU and input gradient with the fused skip addend."""
+    N, C, H, W, K, R, stride, pad = g
+    torch.manual_seed(7)
+    d = ops._desc(N, H, W, C, K, R, R, stride, pad)
+    x = _nhwc_bf16(torch.randn(N, C, H, W))
+    w = _nhwc_bf16(torch.randn(K, C, R, R) * 0.05)
+    b = torch.randn(K, device=DEV)
+    y = torch.empty((N, K, d.P, d.Q), dtype=torch.bfloat16, device=DEV).contiguous(memory_format=CL)
+    ops._call("srgan_conv2d_fprop_bf16", d, ops._p(x), ops._p(w), ops._p(b), ops._p(y), ops.ACT_LRELU, 0.2, None,
+              ops._stream())
+    ref = F.leaky_relu(F.conv2d(x.float(), w.float(), b, stride, pad), 0.2)
+    assert _rel(y.float(), ref) < TOL, (g, _rel(y.float(), ref))
+    if C % 64 == 0 and K % 64 == 0 and C >= 129:         # the dgrad's filter tile (C output channels) is 256 wide
+        dy = _nhwc_bf16(torch.randn(N, K, d.P, d.Q))
+        nb = ops._lib().srgan_conv2d_bf16_workspace(d, 1)
+        ws = ops._workspace(torch.device(DEV, torch.cuda.current_device()), nb)
+        dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=DEV).contiguous(memory_format=CL)
+        add = _nhwc_bf16(torch.randn(N, C, H, W)) if stride == 1 else None
+        ops._call("srgan_conv2d_dgrad_bf16", d, ops._p(dy), ops._p(w), ops._p(add), ops._p(dx), None, ops._p(ws), nb,
+                  ops._stream())
+        refx = torch.nn.grad.conv2d_input((N, C, H, W), w.float(), dy.float(), stride, pad)
+        if add is not None:
+            refx = refx + add.float()
+        assert _rel(dx.float(), refx) < TOL, (g, _rel(dx.float(), refx))

@@ -73,7 +73,11 @@ template <int BN, int MT = 1, typename ST = float>
 struct UmmaCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kStages = (212 * 1024) / kStageBytes < 8 ? (212 * 1024) / kStageBytes : 8;
+#ifndef SRGAN_DBG_MAX_STAGES
+#define SRGAN_DBG_MAX_STAGES 8          // bring-up: -DSRGAN_DBG_MAX_STAGES=3 shows how the ring depth bounds the kernel
+#endif
+  static constexpr int kFit = (204 * 1024) / kStageBytes;
+  static constexpr int kStages = kFit < SRGAN_DBG_MAX_STAGES ? kFit : SRGAN_DBG_MAX_STAGES;
   static constexpr int kAccBufs = 2 * MT * BN <= 512 ? 2 : 1;   // accumulator double buffering when TMEM allows
   static constexpr int kTmemCols = kAccBufs * MT * BN < 32 ? 32 : kAccBufs * MT * BN;
   // STATS: per-quadrant column sums of one tile [4][BN][2] + a private 32 x 17 transpose pad per epilogue warp
@@ -508,7 +512,11 @@ template <typename ST> struct Umma2Cfg {
   static constexpr int kStages = 6;
   static constexpr int kBoxes = 2;                                           // A box, B-half box
   static constexpr int kProducers = 2 * kBoxes;
-  static constexpr int kThreads = 32 * (5 + kProducers);
+  // warp 0: MMA issuer; warps 1-8: epilogue (two warps per TMEM lane quadrant, each takes half of the columns: with
+  // bf16 operands the MMAs of a tile take ~20 k clocks and ONE warp per quadrant needs longer than that to drain and
+  // store 32 rows x 256 columns - the epilogue, not the tensor pipe, set the pace); warps 9-12: TMA producers
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kThreads = 32 * (1 + kEpiWarps + kProducers);
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
   // instruction descriptor: D = f32, A = B = tf32 | bf16, K-major both, N = 256, M = 256 (128 rows per CTA)
   static constexpr uint32_t kIdesc = (1u << 4) | (UmmaElem<ST>::kFmt << 7) | (UmmaElem<ST>::kFmt << 10) |
@@ -546,7 +554,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full + s, Cfg::kBoxes); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 2 * Cfg::kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
@@ -558,14 +566,16 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 5) {
+  if (warp > Cfg::kEpiWarps) {
     // ------------------------------------------------------------------ TMA producers (one box each, every 2nd stage)
     if (lane == 0) {
-      const int pw = warp - 5;
+      const int pw = warp - 1 - Cfg::kEpiWarps;
       const int box = pw % Cfg::kBoxes, par = pw / Cfg::kBoxes;
       int gi0 = 0;
       for (int item = cluster_id; item < items; item += nclusters) {
-        const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
+        const UmmaItem u = umma_item<BN>(p, item);                   // tail items cover half of the filter tile
+        const int bx = u.lin % p.gx, by = (u.lin / p.gx) % p.gy, cls = u.lin / (p.gx * p.gy);
+        const int brow = by * BN + u.n_off + (int)rank * (u.width >> 1);    // this CTA's half of the item's filters
         const int tap0 = p.tap_begin[cls];
         const int iters = (p.tap_begin[cls + 1] - tap0) * p.c_chunks;
         int t = bx * 2 + (int)rank;                                  // this CTA's 128-pixel tile of the pair
@@ -584,7 +594,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (box == 0)
             tma_load_5d_2sm(&map_a, full + stage, sa, cc + tp.x, qb + tp.y, tp.z & 0xff, pb + tp.w, nb);
           else
-            tma_load_3d_2sm(&map_b, full + stage, sa + kABytes, cc, tp.z >> 8, by * BN + (int)rank * Cfg::kBHalf);
+            tma_load_3d_2sm(&map_b, full + stage, sa + kABytes, cc, tp.z >> 8, brow);   // tail items use 64 of the 128 rows
         }
         gi0 += iters;
       }
@@ -595,8 +605,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0, li = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < items; item += nclusters, ++li) {
-        const int cls = item / (p.gx * p.gy);
+        const UmmaItem u = umma_item<BN>(p, item);
+        const int cls = u.lin / (p.gx * p.gy);
         const int iters = (p.tap_begin[cls + 1] - p.tap_begin[cls]) * p.c_chunks;
+        const uint32_t idesc = (Cfg::kIdesc & ~(0x3Fu << 17)) | ((uint32_t)(u.width >> 3) << 17);
         const int buf = li & 1;
         mbar_wait(tempty + buf, (((uint32_t)(li >> 1)) & 1u) ^ 1u);       // both epilogues drained this accumulator
         tc_fence_after();
@@ -608,7 +620,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_any_2sm<ST>(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::kIdesc, (it | k) != 0);
+            umma_any_2sm<ST>(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
           umma_commit_2sm(empty + stage, 3);       // both CTAs may refill this stage
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -617,14 +629,16 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue of this CTA's 128 rows
-    const int quad = warp & 3;
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may read (warp id % 4)
+    const int half = (warp - 1) >> 2;                  // which half of the item's columns this warp drains
     const int m = quad * 32 + lane;
     const int wl = m & (bw - 1), hl = (m >> p.lw) & (bh - 1), nl = m >> (p.lw + p.lh);
     const uint32_t tempty_leader = mapa_shared(smem_u32(tempty), 0);
     int li = 0;
     for (int item = cluster_id; item < items; item += nclusters, ++li) {
-      const int bx = item % p.gx, by = (item / p.gx) % p.gy, cls = item / (p.gx * p.gy);
-      const int col0 = by * BN;
+      const UmmaItem u = umma_item<BN>(p, item);
+      const int bx = u.lin % p.gx, by = (u.lin / p.gx) % p.gy, cls = u.lin / (p.gx * p.gy);
+      const int col0 = by * BN + u.n_off;
       const int buf = li & 1;
       mbar_wait(tfull + buf, ((uint32_t)(li >> 1)) & 1u);
       tc_fence_after();
@@ -634,30 +648,33 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
       ST* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
                       (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-      const float* brow = bias ? bias + col0 : nullptr;
-      const ST* arow = addend ? addend + (yrow - y) + col0 : nullptr;
+      const int hw = u.width >> 1, cbeg = half * hw;                  // this warp's columns [cbeg, cbeg + hw)
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + cbeg;
+      const float* brow = bias ? bias + col0 + cbeg : nullptr;
+      const ST* arow = addend ? addend + (yrow - y) + col0 + cbeg : nullptr;
+      yrow += cbeg;
       uint32_t ra[32], rb[32];
       tmem_ld32_issue(taddr, ra);
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = 0; c < BN / 2; c += 32) {
+        if (c >= hw) break;
         uint32_t (&cur)[32] = ((c >> 5) & 1) ? rb : ra;
         uint32_t (&nxt)[32] = ((c >> 5) & 1) ? ra : rb;
         tmem_ld_wait();
-        if (c + 32 < BN) tmem_ld32_issue(taddr + c + 32, nxt);
+        if (c + 32 < hw) tmem_ld32_issue(taddr + c + 32, nxt);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
         if (valid) {
-          if (col0 + c + 32 <= p.K && p.epi_vec) {
+          if (col0 + cbeg + c + 32 <= p.K && p.epi_vec) {
             epi_row_chunk_any<32>(v, yrow + col0 + c, brow ? brow + c : nullptr, p.act, p.slope, p.epi_vec,
                                   arow ? arow + c : nullptr);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + c + j < p.K)
+              if (col0 + cbeg + c + j < p.K)
                 st_from_float(yrow + col0 + c + j,
-                              apply_act(v[j] + (bias ? __ldg(bias + col0 + c + j) : 0.f) +
+                              apply_act(v[j] + (brow ? __ldg(brow + c + j) : 0.f) +
                                         (arow ? ld_as_float(arow + c + j) : 0.f), p.act, p.slope));
           }
         }
@@ -917,10 +934,18 @@ static int pick_bn(int K) {
   return 16;
 }
 
-// CTA pairs for 256-wide tiles: SRGAN_CONV_PAIRS = 0 (off) | 1 (bf16 storage, default) | 2 (bf16 and TF32)
+// CTA pairs for 256-wide tiles: SRGAN_CONV_PAIRS = 0 (off, default) | 1 (bf16 storage) | 2 (bf16 and TF32).
+// Measured on B200 (tools/conv_k_probe.py, profiles/r2q_*): per 64-channel stage (4 MMAs = 512 tensor clocks) both
+// kernels need ~390 ns in steady state - one CTA 734 "1.9 GHz clocks", pairs 770 - whatever the ring depth (3 stages:
+// 779, 4: 734, pairs with 6: 770) and whatever the epilogue width (4 or 8 warps).  390 ns for 512 clocks is 1.32 GHz:
+// the clock the driver's own cuBLAS peak measurement records under load (MEASURED_PEAKS.json sm_mhz_median 1320, 1000 W
+// power limit).  In steady state the MMAs are therefore back to back in both kernels and the pair's halved operand
+// traffic (ncu: shared-memory wavefronts 43 % -> 30 %, tensor pipe active 59 % -> 73 % of active cycles at the 1.8 GHz
+// of a cold profiling run) buys nothing under the power cap, while its fixed cost per launch (cluster launch, two
+// cluster barriers) is 4 us higher: residual block 62.4 vs 58.8 us back to back.  Off by default, kept selectable.
 template <typename ST>
 static bool use_cta_pairs(long tiles) {
-  static const int mode = getenv("SRGAN_CONV_PAIRS") ? atoi(getenv("SRGAN_CONV_PAIRS")) : 1;
+  static const int mode = getenv("SRGAN_CONV_PAIRS") ? atoi(getenv("SRGAN_CONV_PAIRS")) : 0;
   if (mode <= 0 || (sizeof(ST) == 4 && mode < 2)) return false;
   return tiles >= 2 * kNumSMs;                      // at least two full waves of single tiles: every pair has work
 }
@@ -951,8 +976,13 @@ static int launch_pairs(const CUtensorMap& ma, const CUtensorMap& mb_full, const
   const int nmax = dev < 64 ? max_clusters[dev] : kNumSMs / 2;
   UmmaConvP q = p;
   q.gx = (grid.x + 1) / 2; q.gy = grid.y; q.gz = grid.z;          // pairs of 128-pixel tiles
-  const long items = (long)q.gx * q.gy * q.gz;
-  q.n_full = q.n_items = (int)items;
+  long items = (long)q.gx * q.gy * q.gz;
+  q.n_full = (int)items;
+  // last, partial wave of clusters: when it fills at most half of them, its items run as twice as many half-width
+  // items (128 of the 256 filters; both CTAs then use 64 rows of their filter box) - see launch_bn
+  const long rem = items % nmax;
+  if (rem > 0 && 2 * rem <= nmax) { q.n_full = (int)(items - rem); items += rem; }
+  q.n_items = (int)items;
   const unsigned clusters = (unsigned)(items < nmax ? items : nmax);
   // the filter map of the pair kernel: boxes of 128 filters (half a tile) - same geometry as mb_full's kBRows box
   conv_umma2_kernel<ST><<<2 * clusters, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb_full, q, bias, y, addend);

@@ -355,10 +355,26 @@ PAIR_GEOMS = [  # N, C, H, W, K, R, stride, pad  -- >= 296 tiles of 128 pixels a
 ]
 
 
+def _run_in_subprocess_with_pairs(test_id):
+    """The kernel choice is read from the environment once per process: run the test body in a child with
+    SRGAN_CONV_PAIRS=1."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SRGAN_CONV_PAIRS="1", SRGAN_PAIR_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__ + "::" + test_id],
+                       capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("g", PAIR_GEOMS)
-def test_cta_pair_kernel_fprop_dgrad(g):
-    """conv_umma2_kernel (tcgen05 cta_group::2: two CTAs per 256 x 256 tile, leader issues the MMAs) against torch on
-    the same bf16-rounded operands, forward with bias + LeakyReLU and input gradient with the fused skip addend."""
+def test_cta_pair_kernel_fprop_dgrad(g, request):
+    """conv_umma2_kernel (tcgen05 cta_group::2: two CTAs per 256 x 256 tile, leader issues the MMAs; opt-in with
+    SRGAN_CONV_PAIRS=1) against torch on the same bf16-rounded operands, forward with bias + LeakyReLU and input
+    gradient with the fused skip addend."""
+    import os
+    if os.environ.get("SRGAN_PAIR_CHILD") != "1":
+        return _run_in_subprocess_with_pairs(request.node.name)
     N, C, H, W, K, R, stride, pad = g
     torch.manual_seed(7)
     d = ops._desc(N, H, W, C, K, R, R, stride, pad)

@@ -219,6 +219,14 @@ int srgan_condbias_bwd(const float* dt, const float* t, const float* con, const 
  * ref: nn.AvgPool2d(2,2) pyfiles/model.py:365,368,426,429 ; nn.AvgPool2d(3, stride=2, padding=1,
  *      count_include_pad=False) :286,324 ; LeakyReLU(0.2)+AdaptiveAvgPool2d(1) :394,454 ;
  *      LeakyReLU(0.01) :263,270,303,310 ; Tanh :248 ; residual/shortcut adds :201,375,436 */
+/* bf16 storage variants for the encoder's trunk under the bf16 engine (ref BasicBlock_classification / BasicBlock
+ * pyfiles/model.py:412-450, 355-380: reflect-padded 3x3 convolutions, average pooling joined with the shortcut):
+ * reflect padding of bf16 NHWC tensors; avgpool2(a: bf16) + b (fp32) -> y (fp32) and its backward dy (fp32) -> da (bf16).
+ * C % 8 == 0. */
+int srgan_reflect_pad_fwd_bf16(const void* x, void* y, int N, int H, int W, int C, int pad, void* stream);
+int srgan_reflect_pad_bwd_bf16(const void* dy, void* dx, int N, int H, int W, int C, int pad, void* stream);
+int srgan_avgpool2_add_fwd_mixed(const void* a_bf16, const float* b, float* y, int N, int H, int W, int C, void* stream);
+int srgan_avgpool2_bwd_mixed(const float* dy, void* dx_bf16, int N, int H, int W, int C, void* stream);
 int srgan_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
 int srgan_avgpool2_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 /* y = avgpool2(a) + b  (encoder block tail: cmp-conv pooled + shortcut) */

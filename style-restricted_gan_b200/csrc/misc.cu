@@ -145,6 +145,94 @@ __global__ void avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx
     dx[i] = (p < P && q < Q) ? vscale(__ldg(dy + (((size_t)n * P + p) * Q + q) * C + c), 0.25f) : vzero<T>();
   }
 }
+// ---- bf16 storage (the encoder's trunk under the bf16 engine): 8 channels = 16 bytes per thread and access
+__device__ __forceinline__ void bf8_unpack(const uint4& q, float (&v)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// reflect pad backward on bf16: the (up to 4) mirrored contributions are added in fp32 and rounded once (C8 = C / 8)
+__global__ void reflect_pad_bwd_bf16_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W,
+                                            int C8, int pad) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const size_t total = (size_t)N * H * W * C8;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % (unsigned)C8);
+    size_t t = i / (unsigned)C8;
+    int w = (int)(t % (unsigned)W); t /= (unsigned)W;
+    int h = (int)(t % (unsigned)H);
+    int n = (int)(t / (unsigned)H);
+    int hs[3], ws[3], nh = 0, nw = 0;
+    hs[nh++] = h + pad;
+    if (h >= 1 && h <= pad) hs[nh++] = pad - h;
+    if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h + pad;
+    ws[nw++] = w + pad;
+    if (w >= 1 && w <= pad) ws[nw++] = pad - w;
+    if (w <= W - 2 && w >= W - 1 - pad) ws[nw++] = 2 * (W - 1) - w + pad;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        float v[8];
+        bf8_unpack(__ldg(dy + (((size_t)n * Hp + hs[a]) * Wp + ws[b]) * C8 + c), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += v[e];
+      }
+    dx[i] = bf8_pack(s);
+  }
+}
+// y (fp32) = avgpool2(a: bf16) + b (fp32): the tail of an encoder block, big tensor in bf16, block output in fp32
+__global__ void avgpool2_add_mixed_kernel(const uint4* __restrict__ a, const float4* __restrict__ b,
+                                          float4* __restrict__ y, int N, int H, int W, int C8) {
+  const int P = H / 2, Q = W / 2;
+  const size_t total = (size_t)N * P * Q * C8;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % (unsigned)C8);
+    size_t t = i / (unsigned)C8;
+    int q = (int)(t % (unsigned)Q); t /= (unsigned)Q;
+    int p = (int)(t % (unsigned)P);
+    int n = (int)(t / (unsigned)P);
+    const uint4* s = a + (((size_t)n * H + 2 * p) * W + 2 * q) * C8 + c;
+    float v0[8], v1[8], v2[8], v3[8], o[8];
+    bf8_unpack(__ldg(s), v0); bf8_unpack(__ldg(s + C8), v1);
+    bf8_unpack(__ldg(s + (size_t)W * C8), v2); bf8_unpack(__ldg(s + (size_t)W * C8 + C8), v3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = ((v0[e] + v1[e]) + (v2[e] + v3[e])) * 0.25f;
+    const float4 b0 = __ldg(b + 2 * i), b1 = __ldg(b + 2 * i + 1);
+    y[2 * i] = make_float4(o[0] + b0.x, o[1] + b0.y, o[2] + b0.z, o[3] + b0.w);
+    y[2 * i + 1] = make_float4(o[4] + b1.x, o[5] + b1.y, o[6] + b1.z, o[7] + b1.w);
+  }
+}
+// dx (bf16) = 0.25 * dy (fp32) broadcast over the 2x2 window (zero in a dropped trailing row / column)
+__global__ void avgpool2_bwd_mixed_kernel(const float4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W,
+                                          int C8) {
+  const int P = H / 2, Q = W / 2;
+  const size_t total = (size_t)N * H * W * C8;
+  GRID_STRIDE(i, total) {
+    int c = (int)(i % (unsigned)C8);
+    size_t t = i / (unsigned)C8;
+    int w = (int)(t % (unsigned)W); t /= (unsigned)W;
+    int h = (int)(t % (unsigned)H);
+    int n = (int)(t / (unsigned)H);
+    int p = h >> 1, q = w >> 1;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p < P && q < Q) {
+      const float4* s = dy + ((((size_t)n * P + p) * Q + q) * C8 + c) * 2;
+      const float4 a = __ldg(s), b = __ldg(s + 1);
+      o[0] = a.x * 0.25f; o[1] = a.y * 0.25f; o[2] = a.z * 0.25f; o[3] = a.w * 0.25f;
+      o[4] = b.x * 0.25f; o[5] = b.y * 0.25f; o[6] = b.z * 0.25f; o[7] = b.w * 0.25f;
+    }
+    dx[i] = bf8_pack(o);
+  }
+}
 // AvgPool2d(3, stride 2, padding 1, count_include_pad=False)
 __global__ void avgpool3s2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W,
                                       int C) {
@@ -396,6 +484,40 @@ extern "C" int srgan_reflect_pad_bwd(const float* dy, float* dx, int N, int H, i
     reflect_pad_bwd_kernel<float4><<<grid_for(total / 4, 256), 256, 0, ST>>>((const float4*)dy, (float4*)dx, N, H, W, C / 4, pad);
   else
     reflect_pad_bwd_kernel<float><<<grid_for(total, 256), 256, 0, ST>>>(dy, dx, N, H, W, C, pad);
+  SRGAN_RETURN_LAUNCH();
+}
+// ---- bf16 storage variants (C % 8 == 0, 16-byte aligned tensors)
+extern "C" int srgan_reflect_pad_fwd_bf16(const void* x, void* y, int N, int H, int W, int C, int pad, void* stream) {
+  SRGAN_CHECK_ARG(x && y && pad >= 0 && pad < H && pad < W, "reflect pad needs pad < H,W");
+  SRGAN_CHECK_ARG(C % 8 == 0 && ((uintptr_t)x | (uintptr_t)y) % 16 == 0, "bf16 reflect pad: C % 8 == 0, 16-byte aligned");
+  size_t total = (size_t)N * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
+  if (total == 0) return SRGAN_OK;
+  reflect_pad_fwd_kernel<uint4><<<grid_for(total, 256), 256, 0, ST>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8, pad);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_reflect_pad_bwd_bf16(const void* dy, void* dx, int N, int H, int W, int C, int pad, void* stream) {
+  SRGAN_CHECK_ARG(dy && dx && pad >= 0 && pad < H && pad < W, "reflect pad needs pad < H,W");
+  SRGAN_CHECK_ARG(C % 8 == 0 && ((uintptr_t)dy | (uintptr_t)dx) % 16 == 0, "bf16 reflect pad: C % 8 == 0, 16-byte aligned");
+  size_t total = (size_t)N * H * W * (C / 8);
+  if (total == 0) return SRGAN_OK;
+  reflect_pad_bwd_bf16_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const uint4*)dy, (uint4*)dx, N, H, W, C / 8, pad);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool2_add_fwd_mixed(const void* a_bf16, const float* b, float* y, int N, int H, int W, int C,
+                                            void* stream) {
+  SRGAN_CHECK_ARG(a_bf16 && b && y, "null pointer");
+  SRGAN_CHECK_ARG(C % 8 == 0 && ((uintptr_t)a_bf16 | (uintptr_t)b | (uintptr_t)y) % 16 == 0, "C % 8 == 0, 16-byte aligned");
+  size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return SRGAN_OK;
+  avgpool2_add_mixed_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const uint4*)a_bf16, (const float4*)b, (float4*)y, N, H, W, C / 8);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_avgpool2_bwd_mixed(const float* dy, void* dx_bf16, int N, int H, int W, int C, void* stream) {
+  SRGAN_CHECK_ARG(dy && dx_bf16, "null pointer");
+  SRGAN_CHECK_ARG(C % 8 == 0 && ((uintptr_t)dy | (uintptr_t)dx_bf16) % 16 == 0, "C % 8 == 0, 16-byte aligned");
+  size_t total = (size_t)N * H * W * (C / 8);
+  if (total == 0) return SRGAN_OK;
+  avgpool2_bwd_mixed_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const float4*)dy, (uint4*)dx_bf16, N, H, W, C / 8);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {

@@ -68,6 +68,10 @@ SIGNATURES = {
     "srgan_inorm_param_grads": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P]),
     "srgan_condbias_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "srgan_condbias_bwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "srgan_reflect_pad_fwd_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "srgan_reflect_pad_bwd_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "srgan_avgpool2_add_fwd_mixed": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    "srgan_avgpool2_bwd_mixed": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "srgan_avgpool2_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "srgan_avgpool2_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "srgan_avgpool2_add_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),

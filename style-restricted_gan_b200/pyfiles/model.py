@@ -463,6 +463,18 @@ def _block_tail(nch_in, nch_out):
     return cmp, shortcut
 
 
+def _encoder_block_dtype(block, norm1, norm2):
+    """Engine 'bf16': the block's big tensors (first norm's output, both reflect-padded tensors, conv1's output, the
+    second norm's output and the pre-pool output of the compression conv) are bf16 - the first norm converts on its
+    way out; the block's input / output (pooled, 4x smaller) and the 1x1 shortcut stay fp32.  Needs instance norms and
+    a width that is a multiple of 64."""
+    if not ops.bf16_trunk_enabled() or block.conv1.in_channels % 64:
+        return None
+    if not all(isinstance(m, (_CBINorm, _KernelInstanceNorm2d)) for m in (norm1, norm2)):
+        return None
+    return torch.bfloat16
+
+
 def _block_forward(x, h, cmp, shortcut):
     """out = avgpool2(cmp_conv(h)) + shortcut_conv(avgpool2(x)); pool + add is one kernel."""
     return ops.avg_pool2_add(cmp[0](h), shortcut[1](shortcut[0](x)))
@@ -483,7 +495,8 @@ class BasicBlock(nn.Module):
         x, d = input
         a1, s1 = _activation_of(self.nl1)
         a2, s2 = _activation_of(self.nl2)
-        h = self.conv1(self.cnorm1(x, d, act=a1, slope=s1))
+        lo = _encoder_block_dtype(self, self.cnorm1, self.cnorm2)
+        h = self.conv1(self.cnorm1(x, d, act=a1, slope=s1, out_dtype=lo))
         h = self.cnorm2(h, d, act=a2, slope=s2)
         return [_block_forward(x, h, self.cmp, self.shortcut), d]
 
@@ -536,7 +549,8 @@ class BasicBlock_classification(nn.Module):
         x = input
         a1, s1 = _activation_of(self.nl1)
         a2, s2 = _activation_of(self.nl2)
-        h = self.conv1(self.norm1(x, act=a1, slope=s1))
+        lo = _encoder_block_dtype(self, self.norm1, self.norm2)
+        h = self.conv1(self.norm1(x, act=a1, slope=s1, out_dtype=lo))
         h = self.norm2(h, act=a2, slope=s2)
         return _block_forward(x, h, self.cmp, self.shortcut)
 

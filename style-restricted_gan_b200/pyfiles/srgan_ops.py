@@ -711,7 +711,8 @@ class _ReflectPadFn(torch.autograd.Function):
         x = _raw_to_nhwc(x)
         N, C, H, W = x.shape
         y = _empty_nhwc(N, C, H + 2 * pad, W + 2 * pad, x)
-        _call("srgan_reflect_pad_fwd", _p(x), _p(y), N, H, W, C, pad, _stream())
+        _call("srgan_reflect_pad_fwd_bf16" if x.dtype == BF16 else "srgan_reflect_pad_fwd", _p(x), _p(y), N, H, W, C,
+              pad, _stream())
         ctx.shape, ctx.pad = (N, C, H, W), pad
         return y
 
@@ -720,7 +721,8 @@ class _ReflectPadFn(torch.autograd.Function):
         N, C, H, W = ctx.shape
         dy = _raw_to_nhwc(dy)
         dx = _empty_nhwc(N, C, H, W, dy)
-        _call("srgan_reflect_pad_bwd", _p(dy), _p(dx), N, H, W, C, ctx.pad, _stream())
+        _call("srgan_reflect_pad_bwd_bf16" if dy.dtype == BF16 else "srgan_reflect_pad_bwd", _p(dy), _p(dx), N, H, W, C,
+              ctx.pad, _stream())
         return dx, None
 
 
@@ -1082,16 +1084,21 @@ def avg_pool3s2(x):
 
 
 class _AvgPool2AddFn(torch.autograd.Function):
+    """a may be bf16 (the big pre-pool tensor of an encoder block under the bf16 engine); b and the result are fp32."""
+
     @staticmethod
     def forward(ctx, a, b):
         a, b = _raw_to_nhwc(a), _raw_to_nhwc(b)
         N, C, H, W = a.shape
+        if b.dtype != torch.float32:
+            raise SrganKernelError("avg_pool2_add: the shortcut operand is fp32")
         y = torch.empty_like(b)
         if tuple(b.shape) != (N, C, H // 2, W // 2):
             raise ValueError("avg_pool2_add: shape mismatch")
         if y.numel():
-            _call("srgan_avgpool2_add_fwd", _p(a), _p(b), _p(y), N, H, W, C, _stream())
-        ctx.shape = (N, C, H, W)
+            _call("srgan_avgpool2_add_fwd_mixed" if a.dtype == BF16 else "srgan_avgpool2_add_fwd", _p(a), _p(b), _p(y),
+                  N, H, W, C, _stream())
+        ctx.shape, ctx.a_dtype = (N, C, H, W), a.dtype
         return y
 
     @staticmethod
@@ -1100,9 +1107,10 @@ class _AvgPool2AddFn(torch.autograd.Function):
         dy = _raw_to_nhwc(dy)
         da = None
         if ctx.needs_input_grad[0]:
-            da = _empty_nhwc(N, C, H, W, dy)
+            da = _empty_nhwc(N, C, H, W, dy, dtype=ctx.a_dtype)
             if da.numel():
-                _call("srgan_avgpool2_bwd", _p(dy), _p(da), N, H, W, C, _stream())
+                _call("srgan_avgpool2_bwd_mixed" if ctx.a_dtype == BF16 else "srgan_avgpool2_bwd", _p(dy), _p(da), N, H,
+                      W, C, _stream())
         return da, (dy if ctx.needs_input_grad[1] else None)
 
 

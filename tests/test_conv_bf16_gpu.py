@@ -398,3 +398,63 @@ def test_cta_pair_kernel_fprop_dgrad(g, request):
         if add is not None:
             refx = refx + add.float()
         assert _rel(dx.float(), refx) < TOL, (g, _rel(dx.float(), refx))
+
+
+def test_encoder_bf16_trunk_against_fp32_engine():
+    """Encoder (ref pyfiles/model.py:452-482) forward / backward with the bf16 block trunk against the exact-fp32
+    engine on the same weights; the TF32 engine's distance is printed next to it.  Stated bf16 tolerance: mu / logvar
+    2e-2 relative L2, parameter gradients 2e-1 and cosine >= 0.97 (the generator probe explains why whole-network
+    gradients sit well above the per-element rounding)."""
+    import cases
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(0)
+    E = model.Encoder(3, 8, 64, 4, "instance", 4, DEV).to(DEV)
+    x = (torch.rand(6, 3, 128, 128, device=DEV) * 2 - 1).requires_grad_(True)
+    gmu, glv = torch.randn(6, 8, device=DEV), torch.randn(6, 8, device=DEV)
+    out = {}
+    for eng in ("fp32", "auto", "bf16"):
+        ops.set_conv_engine(eng)
+        try:
+            for p in E.parameters():
+                p.grad = None
+            torch.manual_seed(1)
+            _, mu, logvar, cls, _ = E(x)
+            dx, = torch.autograd.grad([mu, logvar], x, [gmu, glv], retain_graph=True)
+            torch.autograd.backward([mu, logvar], [gmu, glv])
+            out[eng] = (torch.cat([mu, logvar], 1).detach().clone(), dx.clone(),
+                        {n: p.grad.detach().clone() for n, p in E.named_parameters() if p.grad is not None})
+        finally:
+            ops.set_conv_engine("auto")
+    y0, dx0, g0 = out["fp32"]
+    for eng in ("auto", "bf16"):
+        y, dx, g = out[eng]
+        e = (_rel(y, y0), _rel(dx, dx0), _rel_dict(g, g0), _cos_dict(g, g0))
+        print("encoder %s vs fp32 engine: mu/logvar %.2e  dx %.2e  param grads %.2e (cos %.4f)" % ((eng,) + e))
+        if eng == "bf16":
+            assert e[0] < 2e-2 and e[2] < 2e-1 and e[3] > 0.97, e
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 62, 62, 1), (2, 128, 9, 7, 1), (2, 64, 8, 8, 2)])
+def test_reflect_pad_and_pool_bf16(shape):
+    """bf16 reflect padding (pure copy forward; backward adds the mirrored contributions in fp32, one rounding) and the
+    mixed pool-add tail of the encoder block, against torch."""
+    N, C, H, W, pad = shape
+    torch.manual_seed(2)
+    x = _nhwc_bf16(torch.randn(N, C, H, W)).requires_grad_(True)
+    y = ops._ReflectPadFn.apply(x, pad)
+    ref = F.pad(x.detach().float(), (pad,) * 4, mode="reflect")
+    assert y.dtype == torch.bfloat16 and torch.equal(y.float(), ref)
+    gy = _nhwc_bf16(torch.randn(*y.shape))
+    dx, = torch.autograd.grad(y, x, gy)
+    xr = x.detach().float().requires_grad_(True)
+    dxr, = torch.autograd.grad(F.pad(xr, (pad,) * 4, mode="reflect"), xr, gy.float())
+    assert dx.dtype == torch.bfloat16 and _rel(dx, dxr) < 4e-3
+    a = _nhwc_bf16(torch.randn(N, C, H, W)).requires_grad_(True)
+    b = torch.randn(N, C, H // 2, W // 2, device=DEV).contiguous(memory_format=CL).requires_grad_(True)
+    z = ops.avg_pool2_add(a, b)
+    assert z.dtype == torch.float32 and _rel(z, F.avg_pool2d(a.detach().float(), 2) + b.detach()) < 1e-6
+    gz = torch.randn_like(z)
+    da, db = torch.autograd.grad(z, [a, b], gz)
+    ar = a.detach().float().requires_grad_(True)
+    dar, = torch.autograd.grad(F.avg_pool2d(ar, 2), ar, gz)
+    assert da.dtype == torch.bfloat16 and _rel(da, dar) < 4e-3 and torch.equal(db, gz)

@@ -41,14 +41,13 @@ def main():
             jobs.append((name + " wgrad", lambda: ops._wgrad(d, x, dy, True, False)))
         else:
             d = ops._desc(B, H, H, C, K, R, R, stride, pad)
-            thin = C <= 4 or K <= 4
-            xd = torch.float32 if C <= 4 else act_dtype
-            yd = torch.float32 if K <= 4 else act_dtype
+            thin = C <= 4 or K <= 4            # the RGB stem / head keep fp32 tensors on both sides (norms convert)
+            xd = torch.float32 if thin else act_dtype
+            yd = torch.float32 if thin else act_dtype
             x = torch.randn(B, C, H, H, device=dev).to(xd).contiguous(memory_format=CL)
             dy = torch.randn(B, K, d.P, d.Q, device=dev).to(yd).contiguous(memory_format=CL)
             w = (torch.randn(K, C, R, R, device=dev) * 0.05).contiguous(memory_format=CL)
-            jobs.append((name + " fprop", lambda: ops._fprop(d, x, ops._conv_weight(w, x), None, 0, 0.0,
-                                                             out_dtype=yd if thin else None)))
+            jobs.append((name + " fprop", lambda: ops._fprop(d, x, ops._conv_weight(w, x), None, 0, 0.0)))
             jobs.append((name + " dgrad", lambda: ops._dgrad(d, dy, ops._conv_weight(w, dy), x)))
             jobs.append((name + " wgrad", lambda: ops._wgrad(d, x, dy, True, False)))
 
@@ -59,6 +58,7 @@ def main():
     conv_job("G.down0 3>64 k7 @128 (thin input)", 3, 128, 64, 7, 1, 3)
     conv_job("E.first 3>64 k7s2 @128", 3, 128, 64, 7, 2, 1)
     conv_job("E.l3.cmp 512>1024 k3 @9", 512, 9, 1024, 3, 1, 0)
+    conv_job("D1.1 64>128 k4s2 @64 (fp32 storage, TF32)", 64, 64, 128, 4, 2, 1) if a.engine != "bf16" else None
 
     def norm_job(name, C, H):
         x = torch.randn(B, C, H, H, device=dev).to(act_dtype).contiguous(memory_format=CL).requires_grad_(True)

@@ -559,7 +559,9 @@ def main():
                     help="--impl reference: stop after this many seconds of timed steps")
     ap.add_argument("--skip-checks", action="store_true",
                     help="skip the pre-timing parity check (N=1: vs the CPU oracle; N>1: rank / single-GPU invariance)")
-    ap.add_argument("--engine", default=None, choices=[None, "auto", "fp32", "tf32", "bf16"])
+    ap.add_argument("--engine", default="bf16", choices=["auto", "fp32", "tf32", "bf16"],
+                    help="bf16 (default): bf16 storage in the generator and encoder trunks (tcgen05 kind::f16, stated "
+                         "tolerance: losses 1e-2); auto: TF32 on fp32 storage; fp32: exact FFMA engine")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (sg.enable_cuda_graph) or issue every kernel from Python; "

@@ -168,6 +168,19 @@ int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_dtype, floa
                           int N, int HW, int C, float eps, int act, float slope, int stats_given,
                           void* workspace, size_t workspace_bytes, int* counters, void* stream);
 /* stats_given != 0: mean / rstd are inputs (srgan_inorm_stats_from_tiles); only the apply kernel runs. */
+/* One-pass form (norm8c.cu): when a thread-block cluster of <= 8 CTAs can hold the resident tensor of one image (x
+ * forward, dy backward; <= 64 KB per CTA, C <= 256) the two entry points above run ONE kernel that reads x once and
+ * writes y once (backward: dy resident, x streamed twice, dx written once).  The choice depends on (HW, C, storage
+ * type) only - never on N - and the statistics keep the atoms of the two-kernel path.  Returns 1 and the cluster size
+ * / pixels per CTA when the plane is eligible, 0 otherwise (or while the path is switched off, the default: measured
+ * slower than two kernels at batch 64, see srgan_inorm_onepass_enable). */
+int srgan_inorm_onepass_plan(int HW, int C, int resident_dtype, int* cluster, int* slice_px);
+/* Process-wide switch of the one-pass form (default: OFF, or SRGAN_NORM_ONEPASS from the environment); on < 0 only
+ * queries.  Returns the previous setting.  Do not flip it while a captured CUDA graph of a step is alive. */
+int srgan_inorm_onepass_enable(int on);
+/* Introspection: clusters of the one-pass forward kernel the current device holds at once for this plane
+ * (cudaOccupancyMaxActiveClusters); 0 = plane not eligible, -1 = query failed. */
+int srgan_inorm_onepass_max_clusters(int HW, int C, int resident_dtype);
 int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x, int x_dtype, const float* mean,
                           const float* rstd, const float* gamma, const float* beta, const float* cbias,
                           void* dx, float* s1, float* s2, int N, int HW, int C, int act, float slope,

@@ -19,8 +19,7 @@
 // images a rank holds.
 // Algorithmic HBM bytes: forward read x + write y, backward read dy, x + write dx; the second read of x
 // (apply after statistics) and of dy / x (backward apply) is an L2 hit for planes below the 126 MB L2.
-#include <cuda_bf16.h>
-#include "common.cuh"
+#include "norm8.cuh"
 #include <stdlib.h>
 
 namespace srgan {
@@ -39,48 +38,6 @@ struct Norm8P {
   int act;
 };
 
-// ---- 8-channel vector access
-template <typename T> struct Raw8;
-template <> struct Raw8<float> { float4 a, b; };
-template <> struct Raw8<__nv_bfloat16> { uint4 q; };
-
-__device__ __forceinline__ Raw8<float> ld_raw(const float* p) {
-  Raw8<float> r;
-  r.a = __ldg(reinterpret_cast<const float4*>(p));
-  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  return r;
-}
-__device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw(const __nv_bfloat16* p) {
-  Raw8<__nv_bfloat16> r;
-  r.q = __ldg(reinterpret_cast<const uint4*>(p));
-  return r;
-}
-__device__ __forceinline__ void unpack(const Raw8<float>& r, float (&v)[8]) {
-  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
-}
-__device__ __forceinline__ void unpack(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
-  const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
-}
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    w[e] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {      // per-(n,c) tables and parameters
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <typename T> struct Flight { static constexpr int kRows = sizeof(T) == 2 ? 8 : 4; };   // 128 B per thread
 
 struct N8Idx { int cg, row, v, px0, px1; bool active; };
 __device__ __forceinline__ N8Idx n8_idx(const Norm8P& p, int slice) {
@@ -198,28 +155,13 @@ __global__ void __launch_bounds__(kN8Threads, 2) inorm8_stats_kernel(Norm8P p, c
     const int c = (blockIdx.z * p.TPR + cgi) * 8 + e;
     float pv[8];
     unpack(ld_raw(x + ((size_t)n * p.HW * p.C8 + blockIdx.z * p.TPR + cgi) * 8), pv);
-    const float inv = 1.f / (float)p.HW;
-    const float m = (float)sred[cgi * 16 + e] * inv;
-    const float var = fmaxf((float)sred[cgi * 16 + 8 + e] * inv - m * m, 0.f);
-    mean[(size_t)n * p.C + c] = pv[e] + m;
-    rstd[(size_t)n * p.C + c] = rsqrtf(var + p.eps);
+    float mu, rs;
+    n8_mean_rstd(sred[cgi * 16 + e], sred[cgi * 16 + 8 + e], pv[e], 1.f / (float)p.HW, p.eps, &mu, &rs);
+    mean[(size_t)n * p.C + c] = mu;
+    rstd[(size_t)n * p.C + c] = rs;
   }
 }
 
-template <int ACT>
-__device__ __forceinline__ float n8_act(float v, float slope) {
-  if (ACT == SRGAN_ACT_RELU) return fmaxf(v, 0.f);
-  if (ACT == SRGAN_ACT_LRELU) return v > 0.f ? v : v * slope;
-  if (ACT == SRGAN_ACT_TANH) return tanhf(v);
-  return v;
-}
-template <int ACT>
-__device__ __forceinline__ float n8_act_grad(float v, float slope) {
-  if (ACT == SRGAN_ACT_RELU) return v > 0.f ? 1.f : 0.f;
-  if (ACT == SRGAN_ACT_LRELU) return v > 0.f ? 1.f : slope;
-  if (ACT == SRGAN_ACT_TANH) { const float t = tanhf(v); return 1.f - t * t; }
-  return 1.f;
-}
 
 // y = act(x * k + o) (+ residual):  k = rstd*gamma, o = (cbias - mean*rstd)*gamma + beta
 template <typename TX, typename TY, int ACT>
@@ -241,7 +183,7 @@ __global__ void __launch_bounds__(kN8Threads, 3) inorm8_apply_kernel(
     if (beta) ld8f(beta + c, b);
     if (cbias) ld8f(cbias + (size_t)n * p.C + c, tb);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { k[e] = rs[e] * g[e]; o[e] = (tb[e] - mu[e] * rs[e]) * g[e] + b[e]; }
+    for (int e = 0; e < 8; ++e) { float cc; n8_consts(mu[e], rs[e], g[e], b[e], tb[e], &k[e], &o[e], &cc); }
   }
   const size_t rs_ = (size_t)p.C8 * 8;
   const size_t base = ((size_t)n * p.HW * p.C8 + i.v) * 8;
@@ -301,9 +243,7 @@ __global__ void __launch_bounds__(kN8Threads, 2) inorm8_bwd_reduce_kernel(
       if (beta) ld8f(beta + c, b);
       if (cbias) ld8f(cbias + (size_t)n * p.C + c, tb);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        k[e] = rs[e] * g[e]; o[e] = (tb[e] - mu[e] * rs[e]) * g[e] + b[e]; cc[e] = -mu[e] * rs[e];
-      }
+      for (int e = 0; e < 8; ++e) n8_consts(mu[e], rs[e], g[e], b[e], tb[e], &k[e], &o[e], &cc[e]);
     }
     const size_t rs_ = (size_t)p.C8 * 8;
     const size_t base = ((size_t)n * p.HW * p.C8 + i.v) * 8;
@@ -390,12 +330,9 @@ __global__ void __launch_bounds__(kN8Threads, 3) inorm8_bwd_apply_kernel(
     const float inv = 1.f / (float)p.HW;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float cc = -mu[e] * rs[e];
-      k[e] = rs[e] * g[e];
-      o[e] = (tb[e] + cc) * g[e] + b[e];
-      const float a1 = m1[e] * inv, a2 = m2[e] * inv;
-      A[e] = -k[e] * a2 * rs[e];
-      B[e] = -k[e] * (a1 + a2 * cc);
+      float cc;
+      n8_consts(mu[e], rs[e], g[e], b[e], tb[e], &k[e], &o[e], &cc);
+      n8_bwd_consts(k[e], rs[e], cc, m1[e], m2[e], inv, &A[e], &B[e]);
     }
   }
   const size_t rs_ = (size_t)p.C8 * 8;
@@ -560,6 +497,13 @@ extern "C" int srgan_inorm_fwd_mixed(const void* x, int x_dtype, void* y, int y_
   if (!ws || ws_bytes < norm8_ws_bytes(p)) { set_error("inorm_fwd_mixed: workspace %zu < %zu", ws_bytes, norm8_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
+  if (!stats_given) {                    // one pass over HBM when a cluster can hold the image (norm8c.cu)
+    cudaError_t ce;
+    if (norm8c_fwd(x, xb, y, yb, mean, rstd, gamma, beta, cbias, residual, N, HW, C, eps, act, slope, st, &ce)) {
+      if (ce != cudaSuccess) { set_error("inorm_fwd_mixed (one pass): %s", cudaGetErrorString(ce)); return (int)ce; }
+      SRGAN_RETURN_LAUNCH();
+    }
+  }
   SRGAN_N8_TYPES(launch_fwd8, p, x, y, mean, rstd, gamma, beta, cbias, residual, ws, counters, st, stats_given != 0);
   SRGAN_RETURN_LAUNCH();
 }
@@ -592,6 +536,13 @@ extern "C" int srgan_inorm_bwd_mixed(const void* dy, int y_dtype, const void* x,
   if (!ws || ws_bytes < norm8_ws_bytes(p)) { set_error("inorm_bwd_mixed: workspace %zu < %zu", ws_bytes, norm8_ws_bytes(p)); return SRGAN_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const bool xb = x_dtype == SRGAN_DT_BF16, yb = y_dtype == SRGAN_DT_BF16;
+  {
+    cudaError_t ce;
+    if (norm8c_bwd(dy, yb, x, xb, mean, rstd, gamma, beta, cbias, dx, s1, s2, N, HW, C, act, slope, st, &ce)) {
+      if (ce != cudaSuccess) { set_error("inorm_bwd_mixed (one pass): %s", cudaGetErrorString(ce)); return (int)ce; }
+      SRGAN_RETURN_LAUNCH();
+    }
+  }
   SRGAN_N8_TYPES(launch_bwd8, p, dy, x, mean, rstd, gamma, beta, cbias, dx, s1, s2, ws, counters, st);
   SRGAN_RETURN_LAUNCH();
 }

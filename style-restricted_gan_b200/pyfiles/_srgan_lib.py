@@ -46,6 +46,9 @@ SIGNATURES = {
                                       c_float, c_int, P, c_size_t, P, P]),
     "srgan_inorm_bwd_mixed": (c_int, [P, c_int, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float,
                                       P, c_size_t, P, P]),
+    "srgan_inorm_onepass_plan": (c_int, [c_int, c_int, c_int, P, P]),
+    "srgan_inorm_onepass_enable": (c_int, [c_int]),
+    "srgan_inorm_onepass_max_clusters": (c_int, [c_int, c_int, c_int]),
     "srgan_conv2d_dgrad_add_supported": (c_int, [DP, c_int]),
     "srgan_conv2d_dgrad_add": (c_int, [DP, P, P, P, P, c_int, P, c_size_t, P]),
     "srgan_conv2d_wgrad": (c_int, [DP, P, P, P, P, c_int, P, c_size_t, P]),

@@ -341,6 +341,32 @@ int srgan_face_transform(const uint8_t* img, int B, int H, int W, int crop, int 
                          const int* bounds_h, int ksize_h, const int* coef_v, const int* bounds_v, int ksize_v,
                          const uint8_t* flip, float* y, void* stream);
 
+/* ---------------------------------------------------------------- notebook-04 classifier loss, PRDC evaluation (f4)
+ * ref: criterion = nn.CrossEntropyLoss() ; loss = criterion(net(x), label)   notebook 04_Facial_Recognition-Encoder
+ *      cells 18, 22 (the net already ends in a softmax, pyfiles/model.py:484-508: the loss sees probabilities).
+ *   loss = mean_n (logsumexp_j x[n][j] - x[n][label[n]]) ; loss_rows [N] scratch holds the per-row terms (fixed-order
+ *   mean) ; bwd: dx[n][j] = (softmax(x[n])[j] - [j == label[n]]) * gout[0] / N.   label: int64. */
+int srgan_cross_entropy_fwd(const float* x, const long long* label, float* loss, float* loss_rows, int N, int J,
+                            void* stream);
+int srgan_cross_entropy_bwd(const float* x, const long long* label, const float* gout, float* dx, int N, int J,
+                            void* stream);
+/* ref: GAN_evaluation.get_prdc pyfiles/evaluation.py:98-110 -> prdc.compute_prdc(real_features, fake_features,
+ *      nearest_k) of the un-vendored dependency prdc==0.2 (Docker/requirements.txt:13; published algorithm restated in
+ *      oracle/eval_oracle.py).
+ *   srgan_prdc_pairdist2 : d2[i][j] = sum_k (a[i][k] - b[j][k])^2, fp64, k ascending  (a [N][D], b [M][D] fp32)
+ *   srgan_prdc_kth_radius: radius[i] = (k+1)-th smallest entry of row i of the SELF distance matrix [N][N]
+ *                          (= squared distance to the k-th nearest other sample; duplicates counted one by one)
+ *   srgan_prdc_counts    : on d2 of (real x fake) [N][M]:
+ *                            col_hits_real[j] = #{i : d2[i][j] < r_real[i]}   (precision = mean_j [hits > 0],
+ *                                                                             density = sum_j hits / (k M))
+ *                            row_hits_fake[i] = #{j : d2[i][j] < r_fake[j]}   (recall = mean_i [hits > 0])
+ *                            row_min_in[i]    = [min_j d2[i][j] < r_real[i]]  (coverage = mean_i)
+ *   Squared distances order like the reference's Euclidean distances; the integer counts are the result. */
+int srgan_prdc_pairdist2(const float* a, const float* b, double* d2, int N, int M, int D, void* stream);
+int srgan_prdc_kth_radius(const double* d2_self, double* radius, int N, int k, void* stream);
+int srgan_prdc_counts(const double* d2_real_fake, const double* r_real, const double* r_fake, int* col_hits_real,
+                      int* row_hits_fake, int* row_min_in, int N, int M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

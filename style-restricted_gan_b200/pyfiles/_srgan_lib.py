@@ -87,6 +87,11 @@ SIGNATURES = {
     "srgan_colsum": (c_int, [P, P, c_size_t, c_int, P]),
     "srgan_softmax_fwd": (c_int, [P, P, c_int, c_int, P]),
     "srgan_softmax_bwd": (c_int, [P, P, P, c_int, c_int, P]),
+    "srgan_cross_entropy_fwd": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "srgan_cross_entropy_bwd": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "srgan_prdc_pairdist2": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    "srgan_prdc_kth_radius": (c_int, [P, P, c_int, c_int, P]),
+    "srgan_prdc_counts": (c_int, [P, P, P, P, P, P, c_int, c_int, P]),
     "srgan_reparam_fwd": (c_int, [P, P, P, P, c_size_t, P]),
     "srgan_reparam_bwd": (c_int, [P, P, P, P, P, c_size_t, P]),
     "srgan_reduce_scratch_bytes": (c_size_t, [c_size_t]),

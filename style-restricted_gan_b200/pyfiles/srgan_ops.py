@@ -1200,6 +1200,95 @@ def softmax_rows(x):
     return _SoftmaxFn.apply(x)
 
 
+class _CrossEntropyFn(torch.autograd.Function):
+    """mean_n (logsumexp(x_n) - x_n[label_n]); ref: nn.CrossEntropyLoss() in notebook 04 cells 18 / 22."""
+
+    @staticmethod
+    def forward(ctx, x, label):
+        x = x.contiguous()
+        N, J = x.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        rows = torch.empty((N,), dtype=torch.float32, device=x.device)
+        _call("srgan_cross_entropy_fwd", _p(x), _p(label), _p(loss), _p(rows), N, J, _stream())
+        ctx.save_for_backward(x, label)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, label = ctx.saved_tensors
+        N, J = x.shape
+        dx = torch.empty_like(x)
+        _call("srgan_cross_entropy_bwd", _p(x), _p(label), _p(gout.contiguous()), _p(dx), N, J, _stream())
+        return dx, None
+
+
+def cross_entropy(x, label):
+    """nn.CrossEntropyLoss()(x, label) (mean reduction) for [N, J] fp32 scores and int64 labels."""
+    _req(x)
+    if x.dim() != 2 or x.shape[0] == 0:
+        raise ValueError("cross_entropy: expected a non-empty [N, J] tensor")
+    if not (label.is_cuda and label.dtype == torch.int64 and label.shape == (x.shape[0],)):
+        raise SrganKernelError("cross_entropy: label must be a CUDA int64 tensor of shape [N]")
+    if label.device != x.device:
+        raise SrganKernelError("cross_entropy: label lives on another device")
+    return _CrossEntropyFn.apply(x, label.contiguous())
+
+
+class CrossEntropyLoss(torch.nn.Module):
+    """Drop-in for the `criterion = nn.CrossEntropyLoss()` of notebook 04 on the kernels of this package."""
+
+    def forward(self, x, label):
+        return cross_entropy(x, label)
+
+
+def prdc_counts(real_features, fake_features, nearest_k):
+    """The integer counts behind precision / recall / density / coverage (prdc.compute_prdc, ref
+    pyfiles/evaluation.py:98-110): {"col_hits_real" [M], "row_hits_fake" [N], "row_min_in" [N]} as int32 CUDA tensors,
+    plus the squared k-NN radii.  Features: CUDA fp32 [N, D] and [M, D]."""
+    a, b = real_features.contiguous(), fake_features.contiguous()
+    _req(a, b)
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise SrganKernelError("prdc: features must be float32")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or a.shape[1] == 0:
+        raise ValueError("prdc: expected [N, D] and [M, D] features")
+    N, D = a.shape
+    M = b.shape[0]
+    k = int(nearest_k)
+    if not (0 < k < N and k < M):
+        raise ValueError("prdc: need 0 < nearest_k < number of samples")
+    dev, st = a.device, _stream()
+    f64 = dict(dtype=torch.float64, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    radii = []
+    for t in (a, b):
+        n = t.shape[0]
+        d2 = torch.empty((n, n), **f64)
+        r = torch.empty((n,), **f64)
+        _call("srgan_prdc_pairdist2", _p(t), _p(t), _p(d2), n, n, D, st)
+        _call("srgan_prdc_kth_radius", _p(d2), _p(r), n, k, st)
+        radii.append(r)
+    d2 = torch.empty((N, M), **f64)
+    _call("srgan_prdc_pairdist2", _p(a), _p(b), _p(d2), N, M, D, st)
+    col = torch.empty((M,), **i32)
+    row = torch.empty((N,), **i32)
+    rmin = torch.empty((N,), **i32)
+    _call("srgan_prdc_counts", _p(d2), _p(radii[0]), _p(radii[1]), _p(col), _p(row), _p(rmin), N, M, st)
+    return {"col_hits_real": col, "row_hits_fake": row, "row_min_in": rmin, "r2_real": radii[0], "r2_fake": radii[1]}
+
+
+def compute_prdc(real_features, fake_features, nearest_k):
+    """prdc.compute_prdc on the GPU: dict(precision, recall, density, coverage) of Python floats.  numpy / CPU inputs
+    are moved to the current CUDA device (the reference hands over numpy feature arrays)."""
+    def dev(t):
+        t = torch.as_tensor(np.asarray(t) if not torch.is_tensor(t) else t, dtype=torch.float32)
+        return t if t.is_cuda else t.cuda()
+    a, b = dev(real_features), dev(fake_features)
+    c = prdc_counts(a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1), nearest_k)
+    col, row, rmin = (c[k_].cpu().numpy().astype(np.int64) for k_ in ("col_hits_real", "row_hits_fake", "row_min_in"))
+    return dict(precision=float((col > 0).mean()), recall=float((row > 0).mean()),
+                density=float((1.0 / float(nearest_k)) * col.mean()), coverage=float(rmin.mean()))
+
+
 class _ReparamFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu, logvar, eps):

@@ -918,3 +918,73 @@ def get_samples(netG, netE, dataset, index, latent=None, classes=tuple(range(4))
     if image_type == "tensor":
         data["source"] = torch.Tensor(np.asarray(data["source"])).unsqueeze(0)
     return data, label
+
+
+# ------------------------------------------------------------------------------------------- notebook 04 (f4)
+def do_test(net, testloader, device="cuda", mode="eval"):
+    """ref notebook 04 cell 13: labels and outputs of `net` over a loader of (images, labels) batches."""
+    if mode == "train":
+        net.train()
+    elif mode == "eval":
+        net.eval()
+    else:
+        return None
+    labels, outputs = [], []
+    with torch.no_grad():
+        for data in testloader:
+            outputs.append(net(data[0].to(device)).detach().cpu().numpy())
+            labels.append(np.asarray(data[1].detach().cpu().numpy() if torch.is_tensor(data[1]) else data[1]))
+    return np.concatenate(labels).astype(np.float64), np.concatenate(outputs, axis=0)
+
+
+class Classifier_training(object):
+    """The training job of notebook 04 (`04_Facial_Recognition-Encoder.ipynb` cells 18 and 22) on the kernels of this
+    package: `Encoder_classifier` forward / backward through the tcgen05 convolutions and fused norms, the
+    cross-entropy kernel on the softmax outputs (the reference applies nn.CrossEntropyLoss to probabilities - kept),
+    one fused Adam launch (lr, default betas) and `ExponentialLR(gamma)` stepped once per epoch.  Its result, the
+    `state_dict` of the net, is what notebook 05 loads into `Encoder` (`freeze_melt`, keys of Appendix E).
+
+        job = Classifier_training(net, lr=1e-4)            # net = Encoder_classifier(...).to(device)
+        loss, acc = job.train_step(x, label)               # one iteration of the inner loop of cell 22
+        job.fit(loader, epochs, valloader, test_interval)  # the whole cell: per-epoch means, validation accuracy
+    """
+
+    def __init__(self, net, lr=0.0001, gamma=0.99, device=None):
+        self.net = net
+        self.device = device if device is not None else next(net.parameters()).device
+        self.criterion = ops.CrossEntropyLoss()
+        self.optimizer = ops.FusedAdam(net.parameters(), lr=lr)
+        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, gamma=gamma)
+        self.losses_epoch, self.acc_epoch, self.acc_test_list = [], [], []
+        self.best_acc, self.best_epoch = 0, 0
+
+    def train_step(self, x, label):
+        """-> (loss, accuracy) as 0-dim CUDA tensors (no host synchronisation)."""
+        self.net.train()
+        x = ops.to_nhwc(x.to(self.device))
+        label = label.to(self.device).long()
+        _zero_grads(self.net, self.optimizer)
+        y = self.net(x)
+        loss = self.criterion(y, label)
+        with ops.direct_param_grads():
+            loss.backward()
+        _sync_grads(self.net, self.optimizer)
+        self.optimizer.step()
+        acc = (y.detach().argmax(dim=1) == label).float().mean()
+        return loss.detach(), acc
+
+    def fit(self, dataloader, epoch_num, valloader=None, test_interval=3, on_epoch=None):
+        for epoch in range(epoch_num):
+            stats = [self.train_step(data[0], data[1]) for data in dataloader]
+            self.scheduler.step()
+            self.losses_epoch.append(float(torch.stack([s[0] for s in stats]).mean()))
+            self.acc_epoch.append(float(torch.stack([s[1] for s in stats]).mean()))
+            if valloader is not None and epoch % test_interval == 0:
+                labels, outputs = do_test(self.net, valloader, self.device, "eval")
+                acc_test = float((np.argmax(outputs, axis=1) == labels).mean())
+                self.acc_test_list.append(acc_test)
+                if self.best_acc < acc_test:
+                    self.best_acc, self.best_epoch = acc_test, epoch
+            if on_epoch is not None:
+                on_epoch(self, epoch)
+        return self.losses_epoch, self.acc_epoch, self.acc_test_list

@@ -107,6 +107,22 @@ int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy, const void
  *   provide them: tiles must lie inside one image; needs bias == NULL, act none, no addend).
  * srgan_inorm_stats_from_tiles folds the rows of every image in row order in fp64 (independent of the batch). */
 int srgan_conv2d_bf16_stat_rows(const srgan_conv_desc* d, int pass);
+/* Thin RGB layers of the bf16 engine ("thin16"): the 3-channel side (image / image gradient) and the filter are fp32,
+ * the fat side (the 64-channel activation of the bf16 trunk or its gradient) is bfloat16 - the stem writes what the
+ * trunk reads and the head reads what the trunk wrote, without an fp32 copy of the largest tensors of the step.
+ * ref: nn.Conv2d(nch_in, nch, 7, 1, 3) / nn.Conv2d(nch, nch_in, 7, 1, 3) + Tanh, SingleGenerator pyfiles/model.py:
+ * 280-318 (first and last layer), and their backward passes.
+ *   fprop : C <= 4: x fp32 -> y bf16 (bias, activation)           K <= 4: x bf16 -> y fp32 (bias, activation)
+ *   dgrad : K <= 4: dy fp32 -> dx bf16                            C <= 4: dy bf16 -> dx fp32
+ *   wgrad : C <= 4: x fp32, dy bf16 -> dw, dbias fp32             K <= 4: x bf16, dy fp32 -> dw, dbias fp32
+ * TF32 tensor-core arithmetic on the fp32 side's packed rows where the fp32 tensor is the streamed operand, kind::f16
+ * (thin side rounded to bf16) where the bf16 tensor is.  pass: 0 fprop, 1 dgrad, 2 wgrad. */
+int srgan_conv2d_thin16_supported(const srgan_conv_desc* d, int pass);
+size_t srgan_conv2d_thin16_workspace(const srgan_conv_desc* d, int pass);
+int srgan_conv2d_fprop_thin16(const srgan_conv_desc* d, const void* x, const float* w, const float* bias, void* y,
+                              int act, float slope, void* workspace, size_t workspace_bytes, void* stream);
+int srgan_conv2d_dgrad_thin16(const srgan_conv_desc* d, const void* dy, const float* w, void* dx, void* workspace,
+                              size_t workspace_bytes, void* stream);
 int srgan_inorm_stats_from_tiles(const float* tile_stats, int rows, int N, int HW, int C, float eps, float* mean,
                                  float* rstd, void* stream);
 int srgan_conv2d_wgrad_bf16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,

@@ -51,6 +51,12 @@ size_t conv_umma_bf16_wgrad_workspace(const srgan_conv_desc* d);
 void conv_umma_bf16_wgrad_plan(const srgan_conv_desc* d, int* splits, int* ctas);
 int conv_wgrad_umma_bf16_launch(const srgan_conv_desc*, const void*, const void*, float*, void*, size_t, cudaStream_t);
 
+// conv_umma.cu / conv_thinout.cu: thin RGB layers with a bf16 fat side
+bool conv_thin16_supported(const srgan_conv_desc* d, int pass);
+size_t conv_thin16_workspace(const srgan_conv_desc* d, int pass);
+int conv_thin16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias, void* out,
+                       int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static int check_desc(const srgan_conv_desc* d) {
   if (!d) { set_error("conv: null descriptor"); return SRGAN_E_BADARG; }
   if (d->N < 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->K <= 0 || d->R <= 0 || d->S <= 0 || d->stride <= 0 ||
@@ -185,6 +191,27 @@ extern "C" int srgan_conv2d_dgrad_bf16(const srgan_conv_desc* d, const void* dy,
   if (int e = check_desc(d)) return e;
   SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
   return conv_dgrad_umma_bf16_launch(d, dy, w, dx, ws, ws_bytes, (cudaStream_t)stream, addend, tile_stats);
+}
+extern "C" int srgan_conv2d_thin16_supported(const srgan_conv_desc* d, int pass) {
+  if (check_desc(d) || !dense_x(d)) return 0;
+  return conv_thin16_supported(d, pass) ? 1 : 0;
+}
+extern "C" size_t srgan_conv2d_thin16_workspace(const srgan_conv_desc* d, int pass) {
+  if (check_desc(d)) return 0;
+  return conv_thin16_workspace(d, pass);
+}
+extern "C" int srgan_conv2d_fprop_thin16(const srgan_conv_desc* d, const void* x, const float* w, const float* bias,
+                                         void* y, int act, float slope, void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(x && w && y, "null pointer");
+  SRGAN_CHECK_ARG(dense_x(d), "thin16 conv: dense NHWC input only");
+  return conv_thin16_launch(d, 0, x, w, bias, y, act, slope, ws, ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int srgan_conv2d_dgrad_thin16(const srgan_conv_desc* d, const void* dy, const float* w, void* dx, void* ws,
+                                         size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
+  return conv_thin16_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, (cudaStream_t)stream);
 }
 extern "C" int srgan_conv2d_bf16_stat_rows(const srgan_conv_desc* d, int pass) {
   if (check_desc(d)) return 0;

@@ -60,6 +60,7 @@ struct UmmaConvP {
   int epi_vec;                   // widest aligned vector store of a row: 8, 4 or 0 (scalar) floats
   int cls_oph[4], cls_opw[4];    // output pixel parity of each class
   int gx, gy, gz;                // work items: tile groups (MT tiles each) x filter tiles x parity classes
+  int cls_fast;                  // 1: the class is the fastest index of an item (see umma_decode)
   int n_full, n_items;           // the first n_full items are whole tiles; the rest are half-width (BN/2 column)
                                  // tiles, two per remaining tile (balances the last partial wave of CTAs)
   int tap_begin[5];
@@ -248,16 +249,35 @@ __device__ __forceinline__ UmmaItem umma_item(const UmmaConvP& p, int item) {
   return u;
 }
 
+// linear tile index -> (tile group, filter tile, parity class).  With several classes (stride-2 dgrad / transposed
+// forward: 4 classes that read the SAME input boxes through different 2 x 2 taps) the class is the fastest index, so the
+// CTAs that run at the same time work on the four classes of the same tiles and the input is fetched from HBM once
+// instead of once per class (class-major order: 198 MB read for a 67 MB input on G.up1, profiles/r2s_*).
+__device__ __forceinline__ void umma_decode(const UmmaConvP& p, int lin, int* bx, int* by, int* cls) {
+  if (p.cls_fast) {
+    *cls = lin % p.gz;
+    const int r = lin / p.gz;
+    *bx = r % p.gx;
+    *by = r / p.gx;
+  } else {
+    *bx = lin % p.gx;
+    *by = (lin / p.gx) % p.gy;
+    *cls = lin / (p.gx * p.gy);
+  }
+}
+
 // STATS: the epilogue also writes, per 128-pixel tile and output channel, the sum and the sum of squares of the values
 // it stores (as stored, i.e. after rounding to ST): stats[(tile_row * K + k) * 2 + {0, 1}], tile_row =
 // ((n * classes + cls) * tiles_h + th) * tiles_w + tw - what the instance norm that follows the convolution needs,
 // without its own pass over the tensor (srgan_inorm_stats_from_tiles folds the rows of an image in fp64).  Needs tiles
 // that lie inside one image (box of 128 pixels of one image), no bias / activation / addend.
-template <int BN, int MT, typename ST, bool STATS = false>
+// OT: storage type of the OUTPUT (and of the addend); differs from ST only on the thin RGB layers of the bf16 engine
+// (TF32 operands from the fp32 image, bf16 result for the bf16 trunk - and the mirrored head dgrad).
+template <int BN, int MT, typename ST, bool STATS = false, typename OT = ST>
 __global__ void __launch_bounds__((UmmaCfg<BN, MT, ST>::kThreads), 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, ST* __restrict__ y,
-                 const ST* __restrict__ addend, float* __restrict__ stats) {
+                 const __grid_constant__ UmmaConvP p, const float* __restrict__ bias, OT* __restrict__ y,
+                 const OT* __restrict__ addend, float* __restrict__ stats) {
   using Cfg = UmmaCfg<BN, MT, ST>;
   constexpr int NBUF = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -296,7 +316,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int gi0 = 0;                                   // ring index of the first stage of the current item
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const UmmaItem u = umma_item<BN>(p, item);
-        const int bx = u.lin % p.gx, by = (u.lin / p.gx) % p.gy, cls = u.lin / (p.gx * p.gy);
+        int bx, by, cls;
+        umma_decode(p, u.lin, &bx, &by, &cls);
         const int tap0 = p.tap_begin[cls];
         const int iters = (p.tap_begin[cls + 1] - tap0) * p.c_chunks;
         int qb = 0, pb = 0, nb = 0;
@@ -336,7 +357,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
         const UmmaItem u = umma_item<BN>(p, item);
-        const int cls = u.lin / (p.gx * p.gy);
+        int bx_, by_, cls;
+        umma_decode(p, u.lin, &bx_, &by_, &cls);
         const int iters = (p.tap_begin[cls + 1] - p.tap_begin[cls]) * p.c_chunks;
         const uint32_t idesc = (Cfg::kIdesc & ~(0x3Fu << 17)) | ((uint32_t)(u.width >> 3) << 17);
         const int buf = li % NBUF;
@@ -370,7 +392,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int li = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
       const UmmaItem u = umma_item<BN>(p, item);
-      const int bx = u.lin % p.gx, by = (u.lin / p.gx) % p.gy, cls = u.lin / (p.gx * p.gy);
+      int bx, by, cls;
+      umma_decode(p, u.lin, &bx, &by, &cls);
       const int col0 = by * BN + u.n_off;
       const int buf = li % NBUF;
       mbar_wait(tfull + buf, ((uint32_t)(li / NBUF)) & 1u);
@@ -381,11 +404,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int n = (t / p.tiles_h) * bn + nl, pp = (t % p.tiles_h) * bh + hl, qq = tw * bw + wl;
         const bool valid = n < p.Nn && pp < p.P && qq < p.Q;
-        ST* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
+        OT* yrow = y + (((size_t)n * p.out_H + (size_t)(pp * p.os + p.cls_oph[cls])) * p.out_W +
                         (size_t)(qq * p.os + p.cls_opw[cls])) * p.out_C;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (MT * BN) + mt * BN;
         const float* brow = bias ? bias + col0 : nullptr;
-        const ST* arow = addend ? addend + (yrow - y) + col0 : nullptr;         // addend has the layout of y
+        const OT* arow = addend ? addend + (yrow - y) + col0 : nullptr;         // addend has the layout of y
         if (kChunk == 32) {
           // the TMEM load of chunk c + 1 is in flight while chunk c is converted and stored
           uint32_t ra[32], rb[32];
@@ -413,7 +436,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   float a = valid ? v[h * 16 + j] : 0.f;
-                  if (sizeof(ST) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
+                  if (sizeof(OT) == 2) a = __bfloat162float(__float2bfloat16_rn(a));
                   wst[lane * 17 + j] = a;
                 }
                 __syncwarp();
@@ -989,25 +1012,29 @@ static int launch_pairs(const CUtensorMap& ma, const CUtensorMap& mb_full, const
   SRGAN_RETURN_LAUNCH();
 }
 
-template <int BN, int MT, typename ST>
-static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, ST* y,
-                     dim3 grid, cudaStream_t st, const ST* addend, float* stats = nullptr) {
+template <int BN, int MT, typename ST, typename OT = ST>
+static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaConvP& p, const float* bias, OT* y,
+                     dim3 grid, cudaStream_t st, const OT* addend, float* stats = nullptr) {
   using Cfg = UmmaCfg<BN, MT, ST>;
-  constexpr bool kCanStat = sizeof(ST) == 2 && BN >= 32;       // tile statistics: bf16 trunk only
+  constexpr bool kSame = sizeof(ST) == sizeof(OT);
+  constexpr bool kCanStat = kSame && sizeof(ST) == 2 && BN >= 32;       // tile statistics: bf16 trunk only
   static unsigned long long attr_done = 0, attr_done_s = 0;
   {
-    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST, false>, (int)Cfg::kSmem, &attr_done);
+    cudaError_t e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST, false, OT>, (int)Cfg::kSmem, &attr_done);
     if (e == cudaSuccess && kCanStat && stats)
-      e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST, kCanStat>, (int)Cfg::kSmem, &attr_done_s);
+      e = ensure_dyn_smem(conv_umma_kernel<BN, MT, ST, kCanStat, OT>, (int)Cfg::kSmem, &attr_done_s);
     if (e != cudaSuccess) { set_error("conv_umma smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   }
   if (stats && !kCanStat) { set_error("conv_umma: tile statistics need bf16 storage and >= 32 output channels"); return SRGAN_E_UNSUPPORTED; }
-  if constexpr (BN == 256 && MT == 1) {
+  if constexpr (BN == 256 && MT == 1 && kSame) {
     if (!stats && use_cta_pairs<ST>((long)grid.x * grid.y * grid.z))
       return launch_pairs<ST>(ma, mb, p, bias, y, grid, st, addend);
   }
   UmmaConvP q = p;
   q.gx = (grid.x + MT - 1) / MT; q.gy = grid.y; q.gz = grid.z;
+  // A/B switch: SRGAN_DBG_CLASS_MAJOR=1 restores the class-major item order
+  static const bool class_major = getenv("SRGAN_DBG_CLASS_MAJOR") && atoi(getenv("SRGAN_DBG_CLASS_MAJOR")) != 0;
+  q.cls_fast = (q.gz > 1 && !class_major) ? 1 : 0;
   long items = (long)q.gx * q.gy * q.gz;
   q.n_full = (int)items;
   // The CTAs of the last, partial wave would each run a whole tile while the other SMs idle.  With 256-wide tiles
@@ -1023,9 +1050,9 @@ static int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const UmmaCon
   q.n_items = (int)items;
   const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);     // persistent: one CTA per SM
   if (kCanStat && stats)
-    conv_umma_kernel<BN, MT, ST, kCanStat><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend, stats);
+    conv_umma_kernel<BN, MT, ST, kCanStat, OT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend, stats);
   else
-    conv_umma_kernel<BN, MT, ST, false><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend, nullptr);
+    conv_umma_kernel<BN, MT, ST, false, OT><<<ctas, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, q, bias, y, addend, nullptr);
   SRGAN_RETURN_LAUNCH();
 }
 
@@ -1041,9 +1068,11 @@ struct Problem {
   UmmaConvP p;               // taps / classes prefilled
 };
 
-template <typename ST>
-static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float slope, cudaStream_t st,
-                         const CUtensorMap* ma_prebuilt, const ST* addend, float* stats = nullptr) {
+template <typename T> struct NoDeduce { using type = T; };
+template <typename ST, typename OT = ST>
+static int run_problem_t(Problem& pr, const float* bias, OT* y, int act, float slope, cudaStream_t st,
+                         const CUtensorMap* ma_prebuilt, const typename NoDeduce<OT>::type* addend,
+                         float* stats = nullptr) {
   constexpr uint64_t ES = sizeof(ST);
   constexpr uint32_t ROW = UmmaElem<ST>::kRow;
   constexpr CUtensorMapDataType DT = UmmaElem<ST>::kTma;
@@ -1086,7 +1115,7 @@ static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float s
   p.out_H = pr.out_H; p.out_W = pr.out_W; p.out_C = pr.fK; p.os = pr.os; p.K = pr.fK;
   p.act = act; p.slope = slope;
   // epi_vec 8: a row segment of 32 accumulator columns is written with 32-byte stores, 4: 16-byte stores, 0: scalar
-  constexpr int V8 = 32 / (int)ES, V4 = 16 / (int)ES;      // outputs per 32-byte / 16-byte store
+  constexpr int V8 = 32 / (int)sizeof(OT), V4 = 16 / (int)sizeof(OT);      // outputs per 32-byte / 16-byte store
   p.epi_vec = (pr.fK % V8 == 0 && (uintptr_t)y % 32 == 0) ? 8 : (pr.fK % V4 == 0 ? 4 : 0);
   if (bias && (uintptr_t)bias % 16) p.epi_vec = 0;            // vector bias loads need an aligned bias
   if (addend && ((uintptr_t)addend % 16 || pr.fK % V4)) { set_error("conv: addend must be 16-byte aligned"); return SRGAN_E_BADARG; }
@@ -1102,15 +1131,24 @@ static int run_problem_t(Problem& pr, const float* bias, ST* y, int act, float s
   static const char* e_mt = getenv("SRGAN_DBG_CONV_MT");
   const long ctas = (long)grid.x * grid.y * grid.z;
   const int mt = e_mt ? atoi(e_mt) : ((BN == 128 || BN == 64) && ctas >= 2 * kNumSMs ? 2 : 1);
-  if (mt == 2 && BN == 256) return launch_bn<256, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-  if (mt == 2 && BN == 128) return launch_bn<128, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-  if (mt == 2 && BN == 64) return launch_bn<64, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-  switch (BN) {
-    case 256: return launch_bn<256, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-    case 128: return launch_bn<128, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-    case 64:  return launch_bn<64, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-    case 32:  return launch_bn<32, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
-    default:  return launch_bn<16, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+  if constexpr (sizeof(ST) != sizeof(OT)) {
+    // mixed storage exists for the thin RGB layers only: 64 / 32 output channels (stems, the head's input gradient)
+    if (mt == 2 && BN == 64) return launch_bn<64, 2, ST, OT>(ma, mb, p, bias, y, grid, st, addend, stats);
+    if (BN == 64) return launch_bn<64, 1, ST, OT>(ma, mb, p, bias, y, grid, st, addend, stats);
+    if (BN == 32) return launch_bn<32, 1, ST, OT>(ma, mb, p, bias, y, grid, st, addend, stats);
+    set_error("tcgen05 conv: mixed storage needs 32 or 64 output channels (got %d)", pr.fK);
+    return SRGAN_E_UNSUPPORTED;
+  } else {
+    if (mt == 2 && BN == 256) return launch_bn<256, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    if (mt == 2 && BN == 128) return launch_bn<128, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    if (mt == 2 && BN == 64) return launch_bn<64, 2, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    switch (BN) {
+      case 256: return launch_bn<256, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+      case 128: return launch_bn<128, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+      case 64:  return launch_bn<64, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+      case 32:  return launch_bn<32, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+      default:  return launch_bn<16, 1, ST>(ma, mb, p, bias, y, grid, st, addend, stats);
+    }
   }
 }
 
@@ -1251,8 +1289,9 @@ static int thin_pad_launch(const ThinPlan& t, const float* thin, float* tp, cuda
 }
 
 // y = act(conv(x) + bias) with thin x (pass 0)  /  dx = conv_transpose(dy) with thin dy (pass 1)
+template <typename OT = float>
 static int conv_thin_fwdlike_launch(const srgan_conv_desc* d, int pass, const float* thin, const float* w,
-                                    const float* bias, float* out, int act, float slope, void* ws, size_t ws_bytes,
+                                    const float* bias, OT* out, int act, float slope, void* ws, size_t ws_bytes,
                                     cudaStream_t st) {
   ThinPlan t;
   if (!thin_plan(d, pass, &t)) { set_error("thin conv: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
@@ -1273,7 +1312,7 @@ static int conv_thin_fwdlike_launch(const srgan_conv_desc* d, int pass, const fl
   pick_box(pr.P, pr.Q, &p.lw, &p.lh);
   CUtensorMap ma;
   if (int e = thin_map(&ma, tp, t, p.lw, p.lh, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  return run_problem(pr, bias, out, act, slope, st, &ma);
+  return run_problem_t<float, OT>(pr, bias, out, act, slope, st, &ma, nullptr);
 }
 
 static inline int floordiv2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
@@ -1494,6 +1533,31 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
   Problem pr = {};
   dgrad_problem(d, dy, wt, pr);
   return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st, nullptr, addend);
+}
+
+// ------------------------------------------------------------------------------------------ thin layers, bf16 fat side
+// The RGB layers of the bf16 engine: the 3-channel side (image, image gradient) and the filter stay fp32, the fat
+// 64-channel side is bf16 (it belongs to the bf16 trunk).  Same kernels as above with another storage type on one side:
+//   pass 0, thin input  (stem fprop)          fp32 image -> bf16 activation     conv_umma_kernel<.., float, .., bf16>
+//   pass 1, thin output (head input gradient) fp32 dy    -> bf16 dx             same
+// (pass 0 thin output / pass 1 thin input: conv_thinout.cu; pass 2: thin wgrad below)
+bool conv_thin16_supported(const srgan_conv_desc* d, int pass) {
+  ThinPlan t;
+  if (d->N < 1) return false;
+  if (pass == 0 && d->C <= 4) return thin_plan(d, 0, &t) && d->K % 8 == 0 && d->K <= 64 && d->K > 16;
+  if (pass == 1 && d->K <= 4) return thin_plan(d, 1, &t) && d->C % 8 == 0 && d->C <= 64 && d->C > 16;
+  return false;
+}
+size_t conv_thin16_workspace(const srgan_conv_desc* d, int pass) {
+  ThinPlan t;
+  if (!conv_thin16_supported(d, pass) || !thin_plan(d, pass, &t)) return 0;
+  return thin_workspace(d, pass, t);
+}
+int conv_thin16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias, void* out,
+                       int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!conv_thin16_supported(d, pass)) { set_error("thin16 conv: unsupported shape / pass %d", pass); return SRGAN_E_UNSUPPORTED; }
+  return conv_thin_fwdlike_launch<__nv_bfloat16>(d, pass, (const float*)in, w, bias, (__nv_bfloat16*)out, act, slope, ws,
+                                                 ws_bytes, st);
 }
 
 // ------------------------------------------------------------------------------------------ bf16 storage

@@ -36,6 +36,10 @@ SIGNATURES = {
     "srgan_conv2d_fprop_bf16": (c_int, [DP, P, P, P, P, c_int, c_float, P, P]),
     "srgan_conv2d_dgrad_bf16": (c_int, [DP, P, P, P, P, P, P, c_size_t, P]),
     "srgan_conv2d_bf16_stat_rows": (c_int, [DP, c_int]),
+    "srgan_conv2d_thin16_supported": (c_int, [DP, c_int]),
+    "srgan_conv2d_thin16_workspace": (c_size_t, [DP, c_int]),
+    "srgan_conv2d_fprop_thin16": (c_int, [DP, P, P, P, P, c_int, c_float, P, c_size_t, P]),
+    "srgan_conv2d_dgrad_thin16": (c_int, [DP, P, P, P, P, c_size_t, P]),
     "srgan_inorm_stats_from_tiles": (c_int, [P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "srgan_conv2d_wgrad_bf16": (c_int, [DP, P, P, P, P, c_size_t, P]),
     "srgan_conv2d_wgrad_bf16_plan": (c_int, [DP, P, P]),

@@ -1,0 +1,73 @@
+"""GPU: the thin RGB layers of the bf16 engine ("thin16", include/srgan_b200.h): the 3-channel side stays fp32, the fat
+64-channel side is bf16.  Against fp64 torch convolutions on the SAME inputs (the bf16 side rounded as stored); the
+error left is the tensor-core operand format (TF32 where the fp32 tensor streams, bf16 where the bf16 tensor does) and
+the rounding of a bf16 result: rel-L2 <= 4e-3.
+ref: first / last layer of SingleGenerator pyfiles/model.py:280-318, Encoder first_layer :519, discriminator stems."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import srgan_ops as ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CL = torch.channels_last
+BF = torch.bfloat16
+TOL = 4e-3
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def _ws(d, p):
+    nb = ops._lib().srgan_conv2d_thin16_workspace(d, p)
+    return ops._workspace(torch.device(DEV, torch.cuda.current_device()), nb), nb
+
+
+# N, H, W, fat channels, R, stride, pad
+STEMS = [
+    (3, 128, 128, 64, 7, 1, 3),      # generator stem
+    (64, 128, 128, 64, 7, 1, 3),     # ... at the production batch (multi-wave persistent loop)
+    (4, 128, 128, 64, 7, 2, 1),      # encoder first layer
+    (5, 128, 128, 64, 4, 2, 1),      # discriminator 1 stem
+    (5, 64, 64, 32, 4, 2, 1),        # discriminator 2 stem (32-wide tile)
+    (2, 37, 53, 64, 7, 1, 3),        # ragged plane
+]
+
+
+@pytest.mark.parametrize("g", STEMS)
+def test_fprop_thin_input_bf16_output(g):
+    N, H, W, K, R, stride, pad = g
+    torch.manual_seed(0)
+    x = (torch.rand(N, 3, H, W, device=DEV) * 2 - 1).contiguous(memory_format=CL)
+    w = (torch.randn(K, 3, R, R, device=DEV) * 0.1).contiguous(memory_format=CL)
+    b = torch.randn(K, device=DEV) * 0.1
+    d = ops._desc(N, H, W, 3, K, R, R, stride, pad)
+    assert ops._lib().srgan_conv2d_thin16_supported(d, 0) == 1
+    y = torch.empty((N, K, d.P, d.Q), dtype=BF, device=DEV).contiguous(memory_format=CL)
+    ws, nb = _ws(d, 0)
+    for act, slope, fn in ((ops.ACT_NONE, 0.0, lambda t: t), (ops.ACT_LRELU, 0.2, lambda t: F.leaky_relu(t, 0.2))):
+        ops._call("srgan_conv2d_fprop_thin16", d, ops._p(x), ops._p(w), ops._p(b), ops._p(y), act, slope, ops._p(ws), nb,
+                  ops._stream())
+        ref = fn(F.conv2d(x.double(), w.double(), b.double(), stride, pad))
+        assert _rel(y, ref) < TOL, (g, act, _rel(y, ref))
+
+
+HEADS = [(3, 128, 128, 64, 7, 1, 3), (64, 128, 128, 64, 7, 1, 3), (2, 40, 24, 64, 7, 1, 3), (2, 32, 32, 32, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("g", HEADS)
+def test_dgrad_thin_output_bf16_dx(g):
+    """input gradient of the RGB head: dy [N, 3, P, Q] fp32 -> dx [N, C, H, W] bf16"""
+    N, H, W, C, R, stride, pad = g
+    torch.manual_seed(1)
+    d = ops._desc(N, H, W, C, 3, R, R, stride, pad)
+    dy = torch.randn(N, 3, d.P, d.Q, device=DEV).contiguous(memory_format=CL)
+    w = (torch.randn(3, C, R, R, device=DEV) * 0.1).contiguous(memory_format=CL)
+    assert ops._lib().srgan_conv2d_thin16_supported(d, 1) == 1
+    dx = torch.empty((N, C, H, W), dtype=BF, device=DEV).contiguous(memory_format=CL)
+    ws, nb = _ws(d, 1)
+    ops._call("srgan_conv2d_dgrad_thin16", d, ops._p(dy), ops._p(w), ops._p(dx), ops._p(ws), nb, ops._stream())
+    ref = torch.nn.grad.conv2d_input((N, C, H, W), w.double(), dy.double(), stride, pad)
+    assert _rel(dx, ref) < TOL, (g, _rel(dx, ref))

@@ -123,6 +123,8 @@ int srgan_conv2d_fprop_thin16(const srgan_conv_desc* d, const void* x, const flo
                               int act, float slope, void* workspace, size_t workspace_bytes, void* stream);
 int srgan_conv2d_dgrad_thin16(const srgan_conv_desc* d, const void* dy, const float* w, void* dx, void* workspace,
                               size_t workspace_bytes, void* stream);
+int srgan_conv2d_wgrad_thin16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                              void* workspace, size_t workspace_bytes, void* stream);   /* dw or dbias may be NULL */
 int srgan_inorm_stats_from_tiles(const float* tile_stats, int rows, int N, int HW, int C, float eps, float* mean,
                                  float* rstd, void* stream);
 int srgan_conv2d_wgrad_bf16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,

@@ -57,6 +57,9 @@ size_t conv_thin16_workspace(const srgan_conv_desc* d, int pass);
 int conv_thin16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias, void* out,
                        int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int conv_thin16_wgrad_launch(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* ws,
+                             size_t ws_bytes, cudaStream_t st);
+
 static int check_desc(const srgan_conv_desc* d) {
   if (!d) { set_error("conv: null descriptor"); return SRGAN_E_BADARG; }
   if (d->N < 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->K <= 0 || d->R <= 0 || d->S <= 0 || d->stride <= 0 ||
@@ -212,6 +215,13 @@ extern "C" int srgan_conv2d_dgrad_thin16(const srgan_conv_desc* d, const void* d
   if (int e = check_desc(d)) return e;
   SRGAN_CHECK_ARG(dy && w && dx, "null pointer");
   return conv_thin16_launch(d, 1, dy, w, nullptr, dx, SRGAN_ACT_NONE, 0.f, ws, ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int srgan_conv2d_wgrad_thin16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                                         void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  SRGAN_CHECK_ARG(x && dy && (dw || dbias), "null pointer");
+  SRGAN_CHECK_ARG(dense_x(d), "thin16 conv: dense NHWC input only");
+  return conv_thin16_wgrad_launch(d, x, dy, dw, dbias, ws, ws_bytes, (cudaStream_t)stream);
 }
 extern "C" int srgan_conv2d_bf16_stat_rows(const srgan_conv_desc* d, int pass) {
   if (check_desc(d)) return 0;

@@ -1541,9 +1541,14 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
 //   pass 0, thin input  (stem fprop)          fp32 image -> bf16 activation     conv_umma_kernel<.., float, .., bf16>
 //   pass 1, thin output (head input gradient) fp32 dy    -> bf16 dx             same
 // (pass 0 thin output / pass 1 thin input: conv_thinout.cu; pass 2: thin wgrad below)
+static bool thin16_wgrad_supported(const srgan_conv_desc* d, ThinPlan* t);
+static size_t thin16_wgrad_workspace(const srgan_conv_desc* d, const ThinPlan& t);
+static int conv_wgrad_thin16_launch(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                                    void* ws, size_t ws_bytes, cudaStream_t st);
 bool conv_thin16_supported(const srgan_conv_desc* d, int pass) {
   ThinPlan t;
   if (d->N < 1) return false;
+  if (pass == 2) return thin16_wgrad_supported(d, &t);
   if (pass == 0 && d->C <= 4) return thin_plan(d, 0, &t) && d->K % 8 == 0 && d->K <= 64 && d->K > 16;
   if (pass == 1 && d->K <= 4) return thin_plan(d, 1, &t) && d->C % 8 == 0 && d->C <= 64 && d->C > 16;
   return false;
@@ -1551,7 +1556,12 @@ bool conv_thin16_supported(const srgan_conv_desc* d, int pass) {
 size_t conv_thin16_workspace(const srgan_conv_desc* d, int pass) {
   ThinPlan t;
   if (!conv_thin16_supported(d, pass) || !thin_plan(d, pass, &t)) return 0;
+  if (pass == 2) return thin16_wgrad_workspace(d, t);
   return thin_workspace(d, pass, t);
+}
+int conv_thin16_wgrad_launch(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* ws,
+                             size_t ws_bytes, cudaStream_t st) {
+  return conv_wgrad_thin16_launch(d, x, dy, dw, dbias, ws, ws_bytes, st);
 }
 int conv_thin16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias, void* out,
                        int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1761,6 +1771,154 @@ static int conv_wgrad_thin_launch(const srgan_conv_desc* d, const ThinPlan& t, c
   dim3 grid(1, 1, w.splits);
   if (int e = launch_wgrad(w.BN, 1, mfat, mthin, p, part, grid, st)) return e;
   thin_unpack_wgrad_kernel<<<ceil_div(d->K * d->R * d->S * d->C, 256), 256, 0, st>>>(
+      part, dw, d->K, d->C, d->R, d->S, t.mode, w.splits, (long long)part_elems);
+  SRGAN_RETURN_LAUNCH();
+}
+
+// ---- thin wgrad with a bf16 fat tensor ("thin16"): the thin tensor is packed as bf16 NHWC8 (16 B per pixel, the same
+// byte geometry as fp32 NHWC4: an im2col row of a filter row is S x 8 <= 64 contiguous bf16 = one 128-byte row), both
+// operands are MN-major bf16 boxes of 64 x 64 (WgradElem<bf16>).  A filter row is a 64-column N block, so the R rows
+// are run as tap groups of 4 (N = 256) on adjacent CTAs: the fat tensor comes from HBM once, the second group's read
+// is an L2 hit.  out[row][r][s*8 + c].
+constexpr int kThin16Gt = 4;
+struct Thin16WgradPlan { int lw, lh, tiles_w, tiles_h, tiles_n, chunks, cps, splits, groups; };
+static Thin16WgradPlan plan_thin16_wgrad(const ThinPlan& t) {
+  Thin16WgradPlan w;
+  thin_box(t.fH, t.fW, 64, &w.lw, &w.lh);
+  const int bw = 1 << w.lw, bh = 1 << w.lh, bn = 64 / (bw * bh);
+  w.tiles_w = ceil_div(t.fW, bw); w.tiles_h = ceil_div(t.fH, bh); w.tiles_n = ceil_div(t.N, bn);
+  w.chunks = w.tiles_w * w.tiles_h * w.tiles_n;
+  w.groups = ceil_div(t.R, kThin16Gt);
+  const int slots = kNumSMs / w.groups > 0 ? kNumSMs / w.groups : 1;      // one resident CTA per SM
+  int splits = w.chunks < slots ? w.chunks : slots;
+  w.cps = ceil_div(w.chunks, splits);
+  w.splits = ceil_div(w.chunks, w.cps);
+  return w;
+}
+// TP16[n][hp][wp][0..7] (bf16) = thin[n][hp - padH][wp - padW][0..tc) or 0
+__global__ void thin_pad16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int tH, int tW, int tc,
+                                  int Hp, int Wp, int padH, int padW) {
+  const size_t total = (size_t)N * Hp * Wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp);
+    const size_t t = i / Wp;
+    const int hp = (int)(t % Hp);
+    const int n = (int)(t / Hp);
+    const int h = hp - padH, w = wp - padW;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < tH && w >= 0 && w < tW) {
+      const float* s = src + (((size_t)n * tH + h) * tW + w) * tc;
+      for (int c = 0; c < tc; ++c) v[c] = __ldg(s + c);
+    }
+    dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
+  }
+}
+// dw[k][r][s][c] = sum over splits of  part[.][k][r][s*8+c]  (mode 0)  or  part[.][c][R-1-r][(S-1-s)*8+k]  (mode 1)
+__global__ void thin16_unpack_wgrad_kernel(const float* __restrict__ part, float* __restrict__ dw, int K, int C, int R, int S,
+                                           int mode, int splits, long long split_stride) {
+  const int total = K * R * S * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, s = (i / C) % S, r = (i / (C * S)) % R, k = i / (C * S * R);
+    const size_t src = mode == 0 ? (((size_t)k * R + r) * 64 + s * 8 + c)
+                                 : (((size_t)c * R + (R - 1 - r)) * 64 + (S - 1 - s) * 8 + k);
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += part[(size_t)z * split_stride + src];
+    dw[i] = acc;
+  }
+}
+// column sums of a bf16 [rows][C] tensor (bias gradient of the stem: dy is the bf16 fat tensor), two fixed-order stages
+__global__ void colsum16_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, long long rows, int C,
+                                        long long rows_per_block) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += __bfloat162float(x[r * C + c]);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    part[(long long)blockIdx.y * C + c] = t;
+  }
+}
+constexpr int kColsum16Blocks = 592;
+
+static bool thin16_wgrad_supported(const srgan_conv_desc* d, ThinPlan* t) {
+  if (d->N < 1 || !thin_plan(d, 2, t)) return false;
+  return d->S * 8 <= 64 && (t->fC == 64 || t->fC == 128);       // whole 64-channel boxes of the fat tensor
+}
+static size_t thin16_wgrad_workspace(const srgan_conv_desc* d, const ThinPlan& t) {
+  const Thin16WgradPlan w = plan_thin16_wgrad(t);
+  size_t b = thin_tp_bytes(t);                                                // bf16 NHWC8: 16 B per pixel as well
+  b += align256((size_t)w.splits * t.fC * t.R * 64 * sizeof(float));
+  b += align256((size_t)kColsum16Blocks * d->K * sizeof(float));
+  return b;
+}
+static int conv_wgrad_thin16_launch(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                                    void* ws, size_t ws_bytes, cudaStream_t st) {
+  using El = WgradElem<__nv_bfloat16>;
+  ThinPlan t;
+  if (!thin16_wgrad_supported(d, &t)) { set_error("thin16 wgrad: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  const Thin16WgradPlan w = plan_thin16_wgrad(t);
+  const size_t need = thin16_wgrad_workspace(d, t);
+  if (need > ws_bytes || !ws) { set_error("thin16 wgrad: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)ws) % 16) { set_error("thin16 wgrad: tensors must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  const size_t part_elems = (size_t)t.fC * t.R * 64;
+  uint8_t* tp = (uint8_t*)ws;
+  float* part = (float*)((uint8_t*)ws + thin_tp_bytes(t));
+  float* csum = (float*)((uint8_t*)part + align256((size_t)w.splits * part_elems * sizeof(float)));
+  const long long pixels = (long long)d->N * d->P * d->Q;
+  if (dbias) {
+    if (t.mode == 0) {                       // dy is the bf16 fat tensor
+      const long long rpb = ceil_div64(pixels, kColsum16Blocks);
+      const int nb = (int)ceil_div64(pixels, rpb);
+      colsum16_partial_kernel<<<dim3(ceil_div(d->K, 32), nb), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)dy, csum, pixels,
+                                                                                  d->K, rpb);
+      if (int e = colsum_launch(csum, dbias, nb, d->K, nullptr, 0, st)) return e;
+    } else {                                 // dy is the thin fp32 tensor
+      if (int e = colsum_launch((const float*)dy, dbias, pixels, d->K, csum, 64, st)) return e;
+    }
+  }
+  if (!dw) return SRGAN_OK;
+  const float* thin = (const float*)(t.mode == 0 ? x : dy);
+  const void* fat = t.mode == 0 ? dy : x;
+  {
+    const size_t total = (size_t)t.N * t.Hp * t.Wp;
+    unsigned blocks = (unsigned)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+    thin_pad16_kernel<<<blocks, 256, 0, st>>>(thin, (uint4*)tp, t.N, t.tH, t.tW, t.tc, t.Hp, t.Wp, t.padH, t.padW);
+  }
+  CUtensorMap mfat, mthin;
+  const uint32_t bw = 1u << w.lw, bh = 1u << w.lh, bn = 64u / (bw * bh);
+  const CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    uint64_t dims[5] = {(uint64_t)t.fC, (uint64_t)t.fW, 1, (uint64_t)t.fH, (uint64_t)t.N};
+    uint64_t str[4] = {(uint64_t)t.fC * 2, (uint64_t)t.fW * t.fC * 2, (uint64_t)t.fW * t.fC * 2,
+                       (uint64_t)t.fH * t.fW * t.fC * 2};
+    uint32_t box[5] = {(uint32_t)El::kCh, bw, 1, bh, bn};
+    if (int e = encode_map(&mfat, fat, 5, dims, str, box, El::kSwz, DT)) return e;
+  }
+  {
+    // {64 packed bf16, fat column (stride st pixels), row parity, fat row, image}; strides overlap on purpose
+    uint64_t dims[5] = {64, (uint64_t)t.fW, (uint64_t)t.st, (uint64_t)(t.Hp / t.st), (uint64_t)t.N};
+    uint64_t str[4] = {(uint64_t)t.st * 16, (uint64_t)t.Wp * 16, (uint64_t)t.st * t.Wp * 16, (uint64_t)t.Hp * t.Wp * 16};
+    uint32_t box[5] = {64, bw, 1, bh, bn};
+    if (int e = encode_map(&mthin, tp, 5, dims, str, box, El::kSwz, DT)) return e;
+  }
+  UmmaWgradP p = {};
+  p.tiles_c = 1; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
+  p.lw = w.lw; p.lh = w.lh; p.chunks = w.chunks; p.chunks_per_split = w.cps;
+  p.K = t.fC; p.C = 64; p.T = t.R;                // out[row][r][64]
+  p.gt = kThin16Gt; p.cpb = 1;
+  p.split_stride = (long long)part_elems;
+  p.desc_hi = mn_desc_hi(El::kLbo, El::kSbo, El::kLayout);
+  for (int r = 0; r < t.R; ++r) p.taps[r] = make_int4(0, 0, r % t.st, r / t.st);
+  dim3 grid(1, w.groups, w.splits);
+  if (int e = launch_wgrad_bf16(256, 1, mfat, mthin, p, part, grid, st)) return e;
+  thin16_unpack_wgrad_kernel<<<ceil_div(d->K * d->R * d->S * d->C, 256), 256, 0, st>>>(
       part, dw, d->K, d->C, d->R, d->S, t.mode, w.splits, (long long)part_elems);
   SRGAN_RETURN_LAUNCH();
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "srgan_conv2d_thin16_workspace": (c_size_t, [DP, c_int]),
     "srgan_conv2d_fprop_thin16": (c_int, [DP, P, P, P, P, c_int, c_float, P, c_size_t, P]),
     "srgan_conv2d_dgrad_thin16": (c_int, [DP, P, P, P, P, c_size_t, P]),
+    "srgan_conv2d_wgrad_thin16": (c_int, [DP, P, P, P, P, P, c_size_t, P]),
     "srgan_inorm_stats_from_tiles": (c_int, [P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "srgan_conv2d_wgrad_bf16": (c_int, [DP, P, P, P, P, c_size_t, P]),
     "srgan_conv2d_wgrad_bf16_plan": (c_int, [DP, P, P]),

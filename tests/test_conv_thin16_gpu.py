@@ -71,3 +71,52 @@ def test_dgrad_thin_output_bf16_dx(g):
     ops._call("srgan_conv2d_dgrad_thin16", d, ops._p(dy), ops._p(w), ops._p(dx), ops._p(ws), nb, ops._stream())
     ref = torch.nn.grad.conv2d_input((N, C, H, W), w.double(), dy.double(), stride, pad)
     assert _rel(dx, ref) < TOL, (g, _rel(dx, ref))
+
+
+WGRADS = [  # N, H, W, fat channels, R, stride, pad
+    (3, 128, 128, 64, 7, 1, 3),
+    (64, 128, 128, 64, 7, 1, 3),     # production batch: 1024 pixel chunks over 74 splits x 2 tap groups
+    (4, 128, 128, 64, 7, 2, 1),      # encoder first layer (stride-2 packed view)
+    (5, 128, 128, 64, 4, 2, 1),      # discriminator stem: one tap group
+    (2, 37, 53, 64, 7, 1, 3),        # ragged plane
+]
+
+
+@pytest.mark.parametrize("g", WGRADS)
+def test_wgrad_thin_input_bf16_dy(g):
+    """stem: x [N, 3, H, W] fp32, dy [N, K, P, Q] bf16 -> dw [K, 3, R, R], dbias [K] fp32"""
+    N, H, W, K, R, stride, pad = g
+    torch.manual_seed(2)
+    d = ops._desc(N, H, W, 3, K, R, R, stride, pad)
+    x = (torch.rand(N, 3, H, W, device=DEV) * 2 - 1).contiguous(memory_format=CL)
+    dy = torch.randn(N, K, d.P, d.Q, device=DEV).to(BF).contiguous(memory_format=CL)
+    assert ops._lib().srgan_conv2d_thin16_supported(d, 2) == 1
+    dw = torch.empty((K, 3, R, R), device=DEV).contiguous(memory_format=CL)
+    db = torch.empty((K,), device=DEV)
+    ws, nb = _ws(d, 2)
+    ops._call("srgan_conv2d_wgrad_thin16", d, ops._p(x), ops._p(dy), ops._p(dw), ops._p(db), ops._p(ws), nb, ops._stream())
+    ref = torch.nn.grad.conv2d_weight(x.double(), (K, 3, R, R), dy.double(), stride, pad)
+    assert _rel(dw, ref) < TOL, (g, _rel(dw, ref))
+    assert _rel(db, dy.double().sum(dim=(0, 2, 3))) < 1e-5
+    dw2 = torch.empty_like(dw)
+    ops._call("srgan_conv2d_wgrad_thin16", d, ops._p(x), ops._p(dy), ops._p(dw2), None, ops._p(ws), nb, ops._stream())
+    assert torch.equal(dw, dw2)                                       # fixed-order reduction
+
+
+@pytest.mark.parametrize("g", [(3, 128, 128, 64, 7, 1, 3), (64, 128, 128, 64, 7, 1, 3), (2, 40, 24, 64, 7, 1, 3),
+                               (2, 32, 32, 128, 3, 1, 1)])
+def test_wgrad_thin_output_bf16_x(g):
+    """head: x [N, C, H, W] bf16, dy [N, 3, P, Q] fp32 -> dw [3, C, R, R], dbias [3] fp32"""
+    N, H, W, C, R, stride, pad = g
+    torch.manual_seed(3)
+    d = ops._desc(N, H, W, C, 3, R, R, stride, pad)
+    x = torch.randn(N, C, H, W, device=DEV).to(BF).contiguous(memory_format=CL)
+    dy = torch.randn(N, 3, d.P, d.Q, device=DEV).contiguous(memory_format=CL)
+    assert ops._lib().srgan_conv2d_thin16_supported(d, 2) == 1
+    dw = torch.empty((3, C, R, R), device=DEV).contiguous(memory_format=CL)
+    db = torch.empty((3,), device=DEV)
+    ws, nb = _ws(d, 2)
+    ops._call("srgan_conv2d_wgrad_thin16", d, ops._p(x), ops._p(dy), ops._p(dw), ops._p(db), ops._p(ws), nb, ops._stream())
+    ref = torch.nn.grad.conv2d_weight(x.double(), (3, C, R, R), dy.double(), stride, pad)
+    assert _rel(dw, ref) < TOL, (g, _rel(dw, ref))
+    assert _rel(db, dy.double().sum(dim=(0, 2, 3))) < 1e-5

@@ -13,6 +13,7 @@
 // of rows, so each input row is read from global memory once per band).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM allocator), warps 2..5 epilogue.
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "umma_ptx.cuh"
 
 namespace srgan {
@@ -196,9 +197,14 @@ struct ThinOut2P {
   float slope;
 };
 
+// ST: storage type of the FAT input (and of the packed filter): float -> 32 channels per 128-byte row, TF32 MMAs;
+// __nv_bfloat16 ("thin16", the bf16 engine's head fprop / stem dgrad) -> 64 channels per row, kind::f16 - half as many
+// chunks, i.e. half as many of the N = 32 MMAs whose issue rate bounds this kernel.  The thin output stays fp32.
+template <typename ST>
 __global__ void __launch_bounds__(kTOThreads, 1)
 conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ ThinOut2P p, const float* __restrict__ bias, float* __restrict__ out) {
+  constexpr int kCh = 128 / (int)sizeof(ST);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = p.S * p.nchunks * 4096;           // Bs[s][chunk][32 rows][32 f]
@@ -250,14 +256,15 @@ conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
         uint8_t* dst = sa + stage * a_bytes;
         mbar_expect_tx(a_full + stage, p.nchunks * box_bytes);
         for (int j = 0; j < p.nchunks; ++j)
-          tma_load_4d(&map_in, a_full + stage, dst + j * kTO2ABytes, 32 * j, -p.padW, hp, n);
+          tma_load_4d(&map_in, a_full + stage, dst + j * kTO2ABytes, kCh * j, -p.padW, hp, n);
         if (++stage == kTOStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // D = f32, A = B = tf32, both K-major, N = 32, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      // D = f32, A = B = tf32 (format 2) or bf16 (format 1), both K-major, N = 32, M = 128
+      constexpr uint32_t kFmt = sizeof(ST) == 4 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
       mbar_wait(b_full, 0);
       int stage = 0, i = 0;
       uint32_t phase = 0;
@@ -278,7 +285,10 @@ conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
             const uint64_t bdesc = smem_desc_sw128(b0 + (s * p.nchunks + j) * 4096);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_tf32(tmem_base + buf * 32, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ^ 1);
+              if constexpr (sizeof(ST) == 4)
+                umma_tf32(tmem_base + buf * 32, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ^ 1);
+              else
+                umma_f16(tmem_base + buf * 32, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ^ 1);
               first = 0;
             }
           }
@@ -340,20 +350,24 @@ conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
 
 // Bs[s][chunk][r*4 + t][f32]  (rows of 32 floats = one 128-byte swizzle row)
 // mode 0: = w[t][r][s][chunk*32 + f] ; mode 1: = w[chunk*32 + f][R-1-r][S-1-s][t]
-__global__ void thinout2_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ bp, int K, int C, int R,
+__device__ __forceinline__ void st_elem(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_elem(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <typename ST>
+__global__ void thinout2_pack_filter_kernel(const float* __restrict__ w, ST* __restrict__ bp, int K, int C, int R,
                                             int S, int mode) {
+  constexpr int kCh = 128 / (int)sizeof(ST);                 // channels per 128-byte row
   const int F = mode == 0 ? C : K, tc = mode == 0 ? K : C;
-  const int nch = F / 32;
-  const int total = S * nch * 32 * 32;
+  const int nch = F / kCh;
+  const int total = S * nch * 32 * kCh;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int f = i & 31, row = (i >> 5) & 31, j = (i >> 10) % nch, s = i / (1024 * nch);
-    const int r = row >> 2, t = row & 3, ff = j * 32 + f;
+    const int f = i % kCh, row = (i / kCh) & 31, j = (i / (kCh * 32)) % nch, s = i / (kCh * 32 * nch);
+    const int r = row >> 2, t = row & 3, ff = j * kCh + f;
     float v = 0.f;
     if (r < R && t < tc) {
       if (mode == 0) v = w[(((size_t)t * R + r) * S + s) * C + ff];
       else           v = w[(((size_t)ff * R + (R - 1 - r)) * S + (S - 1 - s)) * C + t];
     }
-    bp[i] = v;
+    st_elem(bp + i, v);
   }
 }
 
@@ -418,6 +432,58 @@ size_t conv_thinout_workspace(const srgan_conv_desc* d, int pass) {
   return (size_t)rs * 32 * t.F * sizeof(float);
 }
 
+// the MMA-column-shift kernel for a fat input of storage type ST
+template <typename ST>
+static int thinout2_launch(const srgan_conv_desc* d, const ThinOutPlan& t, const void* in, const float* w,
+                           const float* bias, float* out, int act, float slope, void* ws, cudaStream_t st) {
+  constexpr int kCh = 128 / (int)sizeof(ST);
+  constexpr uint64_t ES = sizeof(ST);
+  const CUtensorMapDataType DT = sizeof(ST) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  ST* bp = (ST*)ws;
+  thinout2_pack_filter_kernel<ST><<<ceil_div(d->S * t.F * 32, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
+  CUtensorMap min2, mb2;
+  {
+    uint64_t dims[4] = {(uint64_t)t.F, (uint64_t)t.Wi, (uint64_t)t.Hi, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)t.F * ES, (uint64_t)t.Wi * t.F * ES, (uint64_t)t.Hi * t.Wi * t.F * ES};
+    uint32_t box[4] = {(uint32_t)kCh, (uint32_t)(128 + d->S - 1), 1, 1};
+    if (int e = encode_map(&min2, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, DT)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)kCh, (uint64_t)d->S * (t.F / kCh) * 32};
+    uint64_t str[1] = {128};
+    uint32_t box[2] = {(uint32_t)kCh, 32};
+    if (int e = encode_map(&mb2, bp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, DT)) return e;
+  }
+  ThinOut2P q = {};
+  q.Hi = t.Hi; q.Wi = t.Wi; q.Ho = t.Ho; q.Wo = t.Wo; q.tc = t.tc; q.R = d->R; q.S = d->S;
+  q.padH = t.padH; q.padW = t.padW; q.nchunks = t.F / kCh; q.bands = t.bands; q.BH = t.BH;
+  q.act = act; q.slope = slope;
+  const size_t smem2 = 1024 + (size_t)d->S * q.nchunks * 4096 + (size_t)kTOStages * q.nchunks * kTO2ABytes +
+                       8 * 4 * 128 * sizeof(float) + 256;
+  static unsigned long long attr2 = 0;
+  {
+    cudaError_t e = ensure_dyn_smem(conv_thinout2_kernel<ST>, 227 * 1024, &attr2);
+    if (e != cudaSuccess) { set_error("conv_thinout2 smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  conv_thinout2_kernel<ST><<<d->N * t.bands, kTOThreads, smem2, st>>>(min2, mb2, q, bias, out);
+  SRGAN_RETURN_LAUNCH();
+}
+
+// "thin16": bf16 fat input (64 channels), fp32 thin output.  pass 0: in = x (bf16), out = y;  pass 1: in = dy (bf16), out = dx
+bool conv_thinout16_supported(const srgan_conv_desc* d, int pass) {
+  ThinOutPlan t;
+  return thinout_plan(d, pass, &t) && t.F == 64;
+}
+int conv_thinout16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias,
+                          float* out, int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
+  ThinOutPlan t;
+  if (!thinout_plan(d, pass, &t) || t.F != 64) { set_error("thin16 thin-output conv: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
+  const size_t need = conv_thinout_workspace(d, pass);
+  if (!ws || ws_bytes < need) { set_error("thin-output conv: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  if (((uintptr_t)in | (uintptr_t)ws) % 16) { set_error("thin-output conv: tensors must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  return thinout2_launch<__nv_bfloat16>(d, t, in, w, bias, out, act, slope, ws, st);
+}
+
 // pass 0: in = x, out = y (bias/activation fused);  pass 1: in = dy, out = dx
 int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, const float* w, const float* bias,
                         float* out, int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -429,35 +495,7 @@ int conv_thinout_launch(const srgan_conv_desc* d, int pass, const float* in, con
   float* bp = (float*)ws;
   static const char* e_var = getenv("SRGAN_DBG_THINOUT");       // bring-up: 1 = transpose epilogue, 2 = MMA column shift
   const int variant = e_var ? atoi(e_var) : 2;
-  if (variant >= 2) {
-    thinout2_pack_filter_kernel<<<ceil_div(d->S * t.F * 32, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
-    CUtensorMap min2, mb2;
-    {
-      uint64_t dims[4] = {(uint64_t)t.F, (uint64_t)t.Wi, (uint64_t)t.Hi, (uint64_t)d->N};
-      uint64_t str[3] = {(uint64_t)t.F * 4, (uint64_t)t.Wi * t.F * 4, (uint64_t)t.Hi * t.Wi * t.F * 4};
-      uint32_t box[4] = {32, (uint32_t)(128 + d->S - 1), 1, 1};
-      if (int e = encode_map(&min2, in, 4, dims, str, box)) return e;
-    }
-    {
-      uint64_t dims[2] = {32, (uint64_t)d->S * (t.F / 32) * 32};
-      uint64_t str[1] = {128};
-      uint32_t box[2] = {32, 32};
-      if (int e = encode_map(&mb2, bp, 2, dims, str, box)) return e;
-    }
-    ThinOut2P q = {};
-    q.Hi = t.Hi; q.Wi = t.Wi; q.Ho = t.Ho; q.Wo = t.Wo; q.tc = t.tc; q.R = d->R; q.S = d->S;
-    q.padH = t.padH; q.padW = t.padW; q.nchunks = t.F / 32; q.bands = t.bands; q.BH = t.BH;
-    q.act = act; q.slope = slope;
-    const size_t smem2 = 1024 + (size_t)d->S * q.nchunks * 4096 + (size_t)kTOStages * q.nchunks * kTO2ABytes +
-                         8 * 4 * 128 * sizeof(float) + 256;
-    static unsigned long long attr2 = 0;
-    {
-      cudaError_t e = ensure_dyn_smem(conv_thinout2_kernel, 227 * 1024, &attr2);
-      if (e != cudaSuccess) { set_error("conv_thinout2 smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    }
-    conv_thinout2_kernel<<<d->N * t.bands, kTOThreads, smem2, st>>>(min2, mb2, q, bias, out);
-    SRGAN_RETURN_LAUNCH();
-  }
+  if (variant >= 2) return thinout2_launch<float>(d, t, in, w, bias, out, act, slope, ws, st);
   thinout_pack_filter_kernel<<<ceil_div(d->R * 32 * t.F, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
   CUtensorMap min, mb;
   {

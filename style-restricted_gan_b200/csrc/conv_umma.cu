@@ -1545,17 +1545,23 @@ static bool thin16_wgrad_supported(const srgan_conv_desc* d, ThinPlan* t);
 static size_t thin16_wgrad_workspace(const srgan_conv_desc* d, const ThinPlan& t);
 static int conv_wgrad_thin16_launch(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
                                     void* ws, size_t ws_bytes, cudaStream_t st);
+bool conv_thinout16_supported(const srgan_conv_desc* d, int pass);
+int conv_thinout16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias,
+                          float* out, int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st);
 bool conv_thin16_supported(const srgan_conv_desc* d, int pass) {
   ThinPlan t;
   if (d->N < 1) return false;
   if (pass == 2) return thin16_wgrad_supported(d, &t);
+  if ((pass == 0 && d->K <= 4) || (pass == 1 && d->C <= 4)) return conv_thinout16_supported(d, pass);
   if (pass == 0 && d->C <= 4) return thin_plan(d, 0, &t) && d->K % 8 == 0 && d->K <= 64 && d->K > 16;
   if (pass == 1 && d->K <= 4) return thin_plan(d, 1, &t) && d->C % 8 == 0 && d->C <= 64 && d->C > 16;
   return false;
 }
 size_t conv_thin16_workspace(const srgan_conv_desc* d, int pass) {
   ThinPlan t;
-  if (!conv_thin16_supported(d, pass) || !thin_plan(d, pass, &t)) return 0;
+  if (!conv_thin16_supported(d, pass)) return 0;
+  if ((pass == 0 && d->K <= 4) || (pass == 1 && d->C <= 4)) return conv_thinout_workspace(d, pass);
+  if (!thin_plan(d, pass, &t)) return 0;
   if (pass == 2) return thin16_wgrad_workspace(d, t);
   return thin_workspace(d, pass, t);
 }
@@ -1566,6 +1572,8 @@ int conv_thin16_wgrad_launch(const srgan_conv_desc* d, const void* x, const void
 int conv_thin16_launch(const srgan_conv_desc* d, int pass, const void* in, const float* w, const float* bias, void* out,
                        int act, float slope, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!conv_thin16_supported(d, pass)) { set_error("thin16 conv: unsupported shape / pass %d", pass); return SRGAN_E_UNSUPPORTED; }
+  if ((pass == 0 && d->K <= 4) || (pass == 1 && d->C <= 4))      // bf16 fat input -> fp32 thin output
+    return conv_thinout16_launch(d, pass, in, w, bias, (float*)out, act, slope, ws, ws_bytes, st);
   return conv_thin_fwdlike_launch<__nv_bfloat16>(d, pass, (const float*)in, w, bias, (__nv_bfloat16*)out, act, slope, ws,
                                                  ws_bytes, st);
 }

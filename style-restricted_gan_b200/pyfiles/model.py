@@ -36,9 +36,19 @@ class _KernelConv2d(nn.Conv2d):
             raise NotImplementedError("asymmetric stride / padding")
         self.weight.data = self.weight.data.contiguous(memory_format=CL)
 
-    def forward(self, x, act=ops.ACT_NONE, slope=0.0):
+    def forward(self, x, act=ops.ACT_NONE, slope=0.0, out_dtype=None):
         return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0],
-                          self.padding_mode, act, slope)
+                          self.padding_mode, act, slope, out_dtype)
+
+    def thin16_ok(self, N, H, W, need_dgrad=True):
+        """Can this RGB layer run with its fat side in bf16 on [N, in_channels, H, W] inputs (engine bf16)?"""
+        key = (N, H, W, need_dgrad)
+        cache = self.__dict__.setdefault("_thin16_cache", {})
+        if key not in cache:
+            cache[key] = self.padding_mode == "zeros" and self.kernel_size[0] == self.kernel_size[1] and \
+                ops.thin16_supported(N, H, W, self.in_channels, self.out_channels, self.kernel_size[0], self.stride[0],
+                                     self.padding[0], need_dgrad)
+        return cache[key]
 
 
 class _KernelConvTranspose2d(nn.ConvTranspose2d):
@@ -328,14 +338,21 @@ class SingleGenerator(nn.Module):
 
     def forward(self, x, c):
         lo = torch.bfloat16 if self._bf16_trunk() else None
-        for conv, cnorm in zip(self.down_convs, self.down_cnorms):
-            x = cnorm(conv(x), c, act=ops.ACT_RELU, out_dtype=lo)
+        # "thin16": the RGB stem writes bf16 and the RGB head reads bf16 (TF32 / kind::f16 kernels with mixed storage),
+        # so the two largest tensors of the generator (64 channels at full resolution) never exist in fp32; where the
+        # shapes do not qualify the norms next to them convert (fp32 in / bf16 out and back), as in round 2's first cut
+        head = self.up_convs[-1]
+        N, _, H, W = x.shape
+        thin = lo is not None and N > 0 and self.down_convs[0].thin16_ok(N, H, W) and head.thin16_ok(N, H, W)
+        for i, (conv, cnorm) in enumerate(zip(self.down_convs, self.down_cnorms)):
+            h = conv(x, out_dtype=lo) if (thin and i == 0) else conv(x)
+            x = cnorm(h, c, act=ops.ACT_RELU, out_dtype=lo)
         x = self.resBlocks([x, c])[0]
         for i in range(self.num_cls):
             last = i == self.num_cls - 1
             x = self.up_norms[i](self.up_convs[i](x), act=ops.ACT_RELU,
-                                 out_dtype=torch.float32 if (last and lo is not None) else None)
-        return self.up_convs[-1](x, act=ops.ACT_TANH)
+                                 out_dtype=torch.float32 if (last and lo is not None and not thin) else None)
+        return head(x, act=ops.ACT_TANH)
 
 
 # --------------------------------------------------------------------------------------------

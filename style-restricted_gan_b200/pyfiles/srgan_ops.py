@@ -639,6 +639,85 @@ class _Conv2dFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+_THIN16 = os.environ.get("SRGAN_THIN16", "1") != "0"      # A/B switch: 0 keeps the RGB layers of the bf16 engine in fp32
+
+
+def thin16_supported(N, H, W, C, K, R, stride, pad, need_dgrad=True):
+    """Can this RGB layer (C <= 4 or K <= 4) run with its fat side in bf16 (srgan_conv2d_*_thin16)?"""
+    if not _THIN16 or not (C <= 4 or K <= 4):
+        return False
+    d = _desc(N, H, W, C, K, R, R, stride, pad)
+    lib = _lib()
+    passes = (0, 1, 2) if need_dgrad else (0, 2)
+    return all(lib.srgan_conv2d_thin16_supported(d, p) == 1 for p in passes)
+
+
+class _Conv2dThin16Fn(torch.autograd.Function):
+    """The RGB stem / head of the bf16 trunk: y = act(conv2d(x, w) + b) with the 3-channel side in fp32 and the fat
+    side in bf16 (stem: fp32 image -> bf16 activation; head: bf16 activation -> fp32 image).  ref: first and last
+    convolution of SingleGenerator, pyfiles/model.py:280-318."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act, slope):
+        x = _raw_to_nhwc(x)
+        N, C, H, W = x.shape
+        K, C2, R, S = weight.shape
+        if C2 != C:
+            raise ValueError("conv2d: input has %d channels, filter expects %d" % (C, C2))
+        thin_in = C <= 4
+        if (x.dtype == BF16) == thin_in:
+            raise SrganKernelError("thin16 conv: the 3-channel side must be fp32 and the fat side bf16")
+        d = _desc(N, H, W, C, K, R, S, stride, pad)
+        lib = _lib()
+        if lib.srgan_conv2d_thin16_supported(d, 0) != 1:
+            raise SrganKernelError("thin16 conv: shape not supported (N=%d C=%d K=%d %dx%d stride %d)"
+                                   % (N, C, K, R, S, stride))
+        if thin_in and act != ACT_NONE:
+            raise SrganKernelError("thin16 stem: no fused activation (the norm behind it activates)")
+        y = _empty_nhwc(N, K, d.P, d.Q, x, dtype=BF16 if thin_in else torch.float32)
+        if y.numel():
+            nb = lib.srgan_conv2d_thin16_workspace(d, 0)
+            ws = _workspace(x.device, nb) if nb else None
+            _call("srgan_conv2d_fprop_thin16", d, _p(x), _p(_krsc(weight)), _p(bias), _p(y), act, slope, _p(ws), nb,
+                  _stream())
+        ctx.d, ctx.act, ctx.slope = d, act, slope
+        ctx.weight, ctx.bias, ctx.has_bias = weight, bias, bias is not None
+        ctx.save_for_backward(x, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        d = ctx.d
+        lib = _lib()
+        dz = _act_bwd(_raw_to_nhwc(dy), y, ctx.act, ctx.slope)
+        dx = dw = db = None
+        if d.N == 0:
+            return (torch.zeros_like(x) if ctx.needs_input_grad[0] else None), None, None, None, None, None, None
+        if ctx.needs_input_grad[0]:
+            if lib.srgan_conv2d_thin16_supported(d, 1) != 1:
+                raise SrganKernelError("thin16 conv: no input-gradient kernel for this shape")
+            dx = torch.empty_like(x)
+            nb = lib.srgan_conv2d_thin16_workspace(d, 1)
+            ws = _workspace(x.device, nb) if nb else None
+            _call("srgan_conv2d_dgrad_thin16", d, _p(dz), _p(_krsc(ctx.weight)), _p(dx), _p(ws), nb, _stream())
+        want_w = ctx.needs_input_grad[1]
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            sink_w, sink_b = _grad_sink(ctx.weight, want_w, True), _grad_sink(ctx.bias, want_b)
+            dw = sink_w if sink_w is not None else (
+                torch.empty((d.K, d.C, d.R, d.S), dtype=torch.float32, device=x.device, memory_format=CL)
+                if want_w else None)
+            db = sink_b if sink_b is not None else (
+                torch.empty((d.K,), dtype=torch.float32, device=x.device) if want_b else None)
+            nb = lib.srgan_conv2d_thin16_workspace(d, 2)
+            ws = _workspace(x.device, nb) if nb else None
+            _call("srgan_conv2d_wgrad_thin16", d, _p(x), _p(dz), _p(dw), _p(db), _p(ws), nb, _stream())
+            dw = None if sink_w is not None else dw
+            db = None if sink_b is not None else db
+        return dx, dw, db, None, None, None, None
+
+
 class _Conv2dSkipFn(torch.autograd.Function):
     """(y, x) = (conv2d(x, w), x): the first convolution of a residual block together with the skip connection that
     leaves the same tensor (ref SingleResidualBlock.forward pyfiles/model.py:196-201).  Both gradients of x arrive in
@@ -726,7 +805,9 @@ class _ReflectPadFn(torch.autograd.Function):
         return dx, None
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, padding_mode="zeros", act=ACT_NONE, slope=0.0):
+def conv2d(x, weight, bias=None, stride=1, padding=0, padding_mode="zeros", act=ACT_NONE, slope=0.0, out_dtype=None):
+    """out_dtype=torch.bfloat16 on an fp32 3-channel input, or a bf16 input of a <= 4-filter layer: the RGB layers of
+    the bf16 trunk (_Conv2dThin16Fn); otherwise the output has the storage type of x."""
     _req(x, weight, bias)
     if x.dim() != 4:
         raise ValueError("expected 4D input (got {}D input)".format(x.dim()))
@@ -735,6 +816,12 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, padding_mode="zeros", act=
         padding = 0
     elif padding_mode not in ("zeros", "reflect"):
         raise NotImplementedError("padding_mode %r" % (padding_mode,))
+    stem16 = out_dtype == BF16 and x.dtype == torch.float32
+    head16 = x.dtype == BF16 and weight.shape[0] <= 4
+    if stem16 or head16:
+        return _Conv2dThin16Fn.apply(x, weight, bias, int(stride), int(padding), int(act), float(slope))
+    if out_dtype is not None and out_dtype != x.dtype:
+        raise SrganKernelError("conv2d: out_dtype %s on a %s input is only available for the RGB stem" % (out_dtype, x.dtype))
     return _Conv2dFn.apply(x, weight, bias, int(stride), int(padding), int(act), float(slope))
 
 

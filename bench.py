@@ -33,7 +33,8 @@ WORKLOADS = {
                             "(class1 cycle5 idt5 reg.5 idt_reg.5 bKL10 corr100 hist100), unrolled k=5"),
     "srgan_nb05": dict(kind="srgan", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu", frozen=True,
                        desc="SRGAN nb05 recipe: nb03 with the encoder trunk frozen while optE is built "
-                            "(Adam lr 1e-3 over fcmean / fcvar only), random-init 'pretrained' weights"),
+                            "(Adam lr 1e-3 over fcmean / fcvar only); the trunk comes out of the notebook-04 "
+                            "classifier job (Classifier_training, --pretrain-iters)"),
     "nb02_solo": dict(kind="single_solo", nch=64, dis_nch=64, enc_nch=64, res_num=6, k=5, feature="mu",
                       desc="SingleGAN nb02 recipe: Encoder_original + solo-multi D, proposed losses, k=5"),
 }
@@ -395,7 +396,7 @@ def run_ours(args):
     np.random.seed(0)
     nets = cases.build_nets(model, case, dev)
     G, D, E = nets
-    sg = cases.build_trainer(nb, case, (G.to(dev), D.to(dev), E.to(dev)), dev, adam=ops.FusedAdam)
+    G, D, E = G.to(dev), D.to(dev), E.to(dev)
     # every rank gets its own slice of the synthetic global batch
     xg, lab = synthetic(batch * world, 123, util.get_target)
     sl = slice(rank * batch, (rank + 1) * batch)
@@ -404,6 +405,20 @@ def run_ours(args):
     tgt = lab["target"][sl].contiguous()
     x_dev = x_host.to(dev)
     label_dev = {"source": src_host.to(dev), "target": tgt}
+    pretrained = None
+    if case.get("frozen") and args.pretrain_iters > 0:
+        # notebook 04 -> 05: the encoder trunk handed to freeze_melt comes out of the classifier job (synthetic labels
+        # here), data parallel like the step (gradients all-reduced, identical weights on every rank)
+        cls = model.Encoder_classifier(3, 8, case["enc_nch"], 4, "instance", 4).to(dev)
+        cls.load_state_dict({k: v for k, v in E.state_dict().items() if not k.startswith(("fcmean", "fcvar"))})
+        job = nb.Classifier_training(cls, lr=1e-4)
+        for _ in range(args.pretrain_iters):
+            ploss, pacc = job.train_step(x_dev, label_dev["source"])
+        E.load_state_dict(cls.state_dict(), strict=False)
+        pretrained = "Encoder_classifier via Classifier_training (notebook 04 job), %d iterations on the synthetic " \
+                     "batch: loss %.4f, accuracy %.3f" % (args.pretrain_iters, float(ploss), float(pacc))
+        del cls, job
+    sg = cases.build_trainer(nb, case, (G, D, E), dev, adam=ops.FusedAdam)
 
     def barrier():
         if world > 1:
@@ -527,6 +542,8 @@ def run_ours(args):
                 "clocks": clocks, "roofline": roof, "roofline_glue": glue,
                 "latent_loss_pair": time_latent_losses(batch * world, dev),
                 "cpu_baseline": cpu}
+        if pretrained:
+            line["config"]["encoder_pretraining"] = pretrained
         line.update(checks)
         print(json.dumps(line))
     sys.stdout.flush()
@@ -563,6 +580,8 @@ def main():
                     help="bf16 (default): bf16 storage in the generator and encoder trunks (tcgen05 kind::f16, stated "
                          "tolerance: losses 1e-2); auto: TF32 on fp32 storage; fp32: exact FFMA engine")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pretrain-iters", type=int, default=4,
+                    help="srgan_nb05: iterations of the notebook-04 classifier job that produce the frozen encoder trunk")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (sg.enable_cuda_graph) or issue every kernel from Python; "
                          "auto = on")

@@ -130,6 +130,11 @@ int srgan_inorm_stats_from_tiles(const float* tile_stats, int rows, int N, int H
 int srgan_conv2d_wgrad_bf16(const srgan_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
                             size_t workspace_bytes, void* stream);
 int srgan_conv2d_wgrad_bf16_plan(const srgan_conv_desc* d, int* splits, int* ctas);
+/* g[i] += p1[i] (+ p2[i], may be NULL), then p1[i] = p2[i] = 0; n % 4 == 0, 16-byte aligned.  Folds the later
+ * gradient contributions of one backward pass (written by the wgrad / norm kernels into zeroed copies of the flat
+ * gradient buffer instead of being added tensor by tensor; ref: autograd accumulation of `.grad` across the several
+ * generator / encoder passes of one loss.backward(), pyfiles/util_notebook.py:664-665, 689) in arrival order. */
+int srgan_grad_fold(float* g, float* p1, float* p2, size_t n, void* stream);
 /* dst[i] = bf16(src[i]) (round to nearest even), n elements; both 16-byte aligned */
 int srgan_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
 /* introspection (tests, tools): pixel splits and CTAs of the tcgen05 wgrad launch for this layer (host only) */

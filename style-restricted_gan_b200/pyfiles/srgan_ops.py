@@ -529,12 +529,22 @@ _direct_grads = False
 _NO_DIRECT_GRADS = os.environ.get("SRGAN_DBG_NO_DIRECT_GRADS", "0") != "0"      # bring-up: autograd accumulates every gradient
 
 
+# Later contributions (a generator / encoder that runs several times inside one loss) are parked in up to
+# _MAX_PENDING zeroed copies of the optimizer's flat gradient buffer - contribution k + 1 of a parameter goes into copy
+# k at the parameter's offset - and folded into the gradient buffer by ONE launch per optimizer when the backward pass
+# ends (srgan_grad_fold, arrival order: bit-identical to autograd's tensor-by-tensor adds; ~400 small launches less per
+# step).  0 restores the tensor-by-tensor accumulation.
+_MAX_PENDING = max(0, min(2, int(os.environ.get("SRGAN_PENDING_GRADS", "2"))))
+_pending_states = []          # flat states (FusedAdam) with parked contributions, in first-use order
+
+
 class direct_param_grads(object):
-    """with direct_param_grads(): backward kernels write the FIRST gradient contribution of a parameter straight into
-    the optimizer's flat gradient buffer (FusedAdam.zero_grad() marks the buffer views as fresh) and hand autograd
-    None for it - no per-parameter accumulation kernel.  Later contributions accumulate as usual.  Only for
-    backward() calls that follow a FusedAdam.zero_grad() and accumulate into .grad (the trainers); never around
-    torch.autograd.grad()."""
+    """with direct_param_grads(): backward kernels write the gradient contributions of a parameter straight into the
+    optimizer's flat buffers (FusedAdam.zero_grad() arms the parameters) and hand autograd None for them - no
+    per-parameter accumulation kernels: the FIRST contribution goes into the gradient buffer itself, the next
+    _MAX_PENDING ones into parking copies that are folded in when the block exits; anything beyond accumulates as
+    usual.  Only for backward() calls that follow a FusedAdam.zero_grad() and accumulate into .grad (the trainers);
+    never around torch.autograd.grad()."""
 
     def __enter__(self):
         global _direct_grads
@@ -543,19 +553,54 @@ class direct_param_grads(object):
     def __exit__(self, *exc):
         global _direct_grads
         _direct_grads = self.prev
+        if not self.prev:
+            fold_pending_grads()
+
+
+def fold_pending_grads():
+    """Fold the parked gradient contributions into the flat gradient buffers (one launch per optimizer group)."""
+    while _pending_states:
+        st = _pending_states.pop()
+        used, st["pend_used"] = st.get("pend_used", 0), 0
+        if used:
+            pend = st["pend"]
+            _call("srgan_grad_fold", _p(st["g"]), _p(pend[0]), _p(pend[1]) if used > 1 else None, st["g"].numel(),
+                  _stream())
 
 
 def _grad_sink(p, wanted, channels_last=False):
-    """The flat-buffer view to write this parameter's gradient into, or None."""
-    if not (wanted and _direct_grads) or p is None or not getattr(p, "_srgan_fresh", False):
+    """The flat-buffer view to write this parameter's gradient into (overwrite semantics), or None."""
+    if not (wanted and _direct_grads) or p is None:
         return None
-    g = p.grad
-    if g is None or g.shape != p.shape:
+    k = getattr(p, "_srgan_arrivals", None)
+    if k is None:
         return None
-    if not (g.is_contiguous(memory_format=CL) if (channels_last and g.dim() == 4) else g.is_contiguous()):
+    if k == 0:
+        g = p.grad
+        if g is None or g.shape != p.shape:
+            return None
+        if not (g.is_contiguous(memory_format=CL) if (channels_last and g.dim() == 4) else g.is_contiguous()):
+            p._srgan_arrivals = None
+            return None
+        p._srgan_arrivals = 1
+        return g
+    owner = getattr(p, "_srgan_owner", None)
+    if k > _MAX_PENDING or owner is None:
         return None
-    p._srgan_fresh = False
-    return g
+    st, view = owner[0], owner[1]
+    pend = st.setdefault("pend", [])
+    while len(pend) < k:
+        pend.append(torch.zeros_like(st["g"]))
+    views = p.__dict__.setdefault("_srgan_pend_views", {})
+    t = views.get(k)
+    if t is None or t.data_ptr() < pend[k - 1].data_ptr() or \
+            t.data_ptr() >= pend[k - 1].data_ptr() + pend[k - 1].numel() * 4:
+        t = views[k] = view(pend[k - 1])
+    if st.get("pend_used", 0) == 0:
+        _pending_states.append(st)
+    st["pend_used"] = max(st.get("pend_used", 0), k)
+    p._srgan_arrivals = k + 1
+    return t
 
 
 def _wgrad(d, x, dy, want_w, want_b, dw_out=None, db_out=None):
@@ -1718,7 +1763,7 @@ class FusedAdam(torch.optim.Optimizer):
             st["g"].zero_()
             for p, view in st["views"]:
                 p.grad = view(st["g"])
-                p._srgan_fresh = True          # see direct_param_grads
+                p._srgan_arrivals = 0          # see direct_param_grads / _grad_sink
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -447,6 +447,24 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
   }
 }
 
+// g += p1 (+ p2), then p1 = p2 = 0: the later gradient contributions of a backward pass, parked in "pending" copies of
+// the optimizer's flat gradient buffer, are folded in ARRIVAL order - bit-identical to autograd's one-add-per-tensor
+// accumulation - and the parking buffers are left zero for the next pass.
+__global__ void grad_fold_kernel(float4* __restrict__ g, float4* __restrict__ p1, float4* __restrict__ p2, size_t n4) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = g[i];
+    const float4 b = p1[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    p1[i] = z;
+    if (p2) {
+      const float4 c = p2[i];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      p2[i] = z;
+    }
+    g[i] = a;
+  }
+}
 }  // namespace srgan
 
 using namespace srgan;
@@ -586,24 +604,6 @@ extern "C" int srgan_act_bwd(const float* dy, const float* y, float* dx, size_t 
   if (n == 0) return SRGAN_OK;
   act_bwd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(dy, y, dx, n, act, slope);
   SRGAN_RETURN_LAUNCH();
-}
-// g += p1 (+ p2), then p1 = p2 = 0: the later gradient contributions of a backward pass, parked in "pending" copies of
-// the optimizer's flat gradient buffer, are folded in ARRIVAL order - bit-identical to autograd's one-add-per-tensor
-// accumulation - and the parking buffers are left zero for the next pass.
-__global__ void grad_fold_kernel(float4* __restrict__ g, float4* __restrict__ p1, float4* __restrict__ p2, size_t n4) {
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 a = g[i];
-    const float4 b = p1[i];
-    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    p1[i] = z;
-    if (p2) {
-      const float4 c = p2[i];
-      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
-      p2[i] = z;
-    }
-    g[i] = a;
-  }
 }
 extern "C" int srgan_grad_fold(float* g, float* p1, float* p2, size_t n, void* stream) {
   SRGAN_CHECK_ARG(g && p1, "null pointer");

@@ -135,6 +135,11 @@ int srgan_conv2d_wgrad_bf16_plan(const srgan_conv_desc* d, int* splits, int* cta
  * gradient buffer instead of being added tensor by tensor; ref: autograd accumulation of `.grad` across the several
  * generator / encoder passes of one loss.backward(), pyfiles/util_notebook.py:664-665, 689) in arrival order. */
 int srgan_grad_fold(float* g, float* p1, float* p2, size_t n, void* stream);
+/* bf16 discriminator tower (engine bf16; ref: the LeakyReLU(0.2) after every tower convolution, pyfiles/model.py:
+ * 255-346): dz = dy * act'(y) on bf16 tensors (y = the activation OUTPUT, as in srgan_act_bwd), and the widening cast
+ * at the tower's fp32 boundary (the 1- / 4-logit heads read fp32). */
+int srgan_act_bwd_bf16(const void* dy, const void* y, void* dx, size_t n, int act, float slope, void* stream);
+int srgan_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream);
 /* dst[i] = bf16(src[i]) (round to nearest even), n elements; both 16-byte aligned */
 int srgan_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
 /* introspection (tests, tools): pixel splits and CTAs of the tcgen05 wgrad launch for this layer (host only) */

@@ -341,6 +341,48 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
+// bf16 forms for the bf16 discriminator tower: dz = dy * act'(y) on bf16 tensors (8 elements per thread and trip), and
+// the widening cast at the tower's fp32 boundary
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& q, float* o) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { o[2 * e] = __uint_as_float(w[e] << 16); o[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+}
+__global__ void act_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                    __nv_bfloat16* __restrict__ dx, size_t n, int act, float slope) {
+  const size_t n8 = n / 8;
+  const uint4* d4 = reinterpret_cast<const uint4*>(dy);
+  const uint4* y4 = reinterpret_cast<const uint4*>(y);
+  uint4* o4 = reinterpret_cast<uint4*>(dx);
+  GRID_STRIDE(i, n8) {
+    float a[8], b[8];
+    bf16x8_to_f32(__ldg(d4 + i), a);
+    bf16x8_to_f32(__ldg(y4 + i), b);
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * e] * act_grad_out(b[2 * e], act, slope),
+                                               a[2 * e + 1] * act_grad_out(b[2 * e + 1], act, slope));
+      w[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    o4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * act_grad_out(__bfloat162float(y[i]), act, slope));
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t n8 = n / 8;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  GRID_STRIDE(i, n8) {
+    float a[8];
+    bf16x8_to_f32(__ldg(s4 + i), a);
+    d4[2 * i] = make_float4(a[0], a[1], a[2], a[3]);
+    d4[2 * i + 1] = make_float4(a[4], a[5], a[6], a[7]);
+  }
+  for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
                            size_t n) {
   size_t n4 = n / 4;
@@ -603,6 +645,21 @@ extern "C" int srgan_act_bwd(const float* dy, const float* y, float* dx, size_t 
   SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) % 16 == 0, "pointers must be 16-byte aligned");
   if (n == 0) return SRGAN_OK;
   act_bwd_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST>>>(dy, y, dx, n, act, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_act_bwd_bf16(const void* dy, const void* y, void* dx, size_t n, int act, float slope, void* stream) {
+  SRGAN_CHECK_ARG(dy && y && dx, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) % 16 == 0, "pointers must be 16-byte aligned");
+  if (n == 0) return SRGAN_OK;
+  act_bwd_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                              (__nv_bfloat16*)dx, n, act, slope);
+  SRGAN_RETURN_LAUNCH();
+}
+extern "C" int srgan_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream) {
+  SRGAN_CHECK_ARG(src && dst, "null pointer");
+  SRGAN_CHECK_ARG(((uintptr_t)src | (uintptr_t)dst) % 16 == 0, "pointers must be 16-byte aligned");
+  if (n == 0) return SRGAN_OK;
+  cast_bf16_f32_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, ST>>>((const __nv_bfloat16*)src, dst, n);
   SRGAN_RETURN_LAUNCH();
 }
 extern "C" int srgan_grad_fold(float* g, float* p1, float* p2, size_t n, void* stream) {

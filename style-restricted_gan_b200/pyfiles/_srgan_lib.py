@@ -46,6 +46,8 @@ SIGNATURES = {
     "srgan_conv2d_wgrad_bf16_plan": (c_int, [DP, P, P]),
     "srgan_cast_f32_bf16": (c_int, [P, P, c_size_t, P]),
     "srgan_grad_fold": (c_int, [P, P, P, c_size_t, P]),
+    "srgan_act_bwd_bf16": (c_int, [P, P, P, c_size_t, c_int, c_float, P]),
+    "srgan_cast_bf16_f32": (c_int, [P, P, c_size_t, P]),
     "srgan_inorm_mixed_workspace": (c_size_t, [c_int, c_int, c_int]),
     "srgan_inorm_mixed_counters": (c_size_t, [c_int, c_int]),
     "srgan_inorm_fwd_mixed": (c_int, [P, c_int, P, c_int, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int,

@@ -358,21 +358,50 @@ class SingleGenerator(nn.Module):
 # --------------------------------------------------------------------------------------------
 # discriminators   (ref: pyfiles/model.py:255-346)
 # --------------------------------------------------------------------------------------------
+def _tower_bf16_ok(stack, x):
+    """Engine 'bf16': can this discriminator tower keep bf16 activations?  Its RGB stem must qualify for the thin16
+    kernels (fp32 image -> bf16, wgrad on the bf16 gradient) and every following activated convolution must be
+    bias-free with channel counts that are multiples of 64 (tcgen05 kind::f16 fprop / dgrad / wgrad); a trailing head
+    convolution (1 or 4 logits) reads an fp32 copy.  The narrow second tower of the multi-scale discriminators
+    (nch / 2 = 32) does not qualify and stays on the TF32 engine."""
+    if not ops.bf16_trunk_enabled() or x.dtype != torch.float32 or x.shape[0] == 0:
+        return False
+    convs = [m for m in stack if isinstance(m, nn.Conv2d)]
+    if len(convs) < 2 or convs[0].in_channels > 4:
+        return False
+    N, _, H, W = x.shape
+    if not convs[0].thin16_ok(N, H, W, need_dgrad=False) or convs[0].out_channels % 64:
+        return False
+    mods = list(stack)
+    for i, m in enumerate(mods):
+        if not isinstance(m, nn.Conv2d) or m is convs[0]:
+            continue
+        activated = i + 1 < len(mods) and not isinstance(mods[i + 1], nn.Conv2d)
+        if activated and (m.bias is not None or m.in_channels % 64 or m.out_channels % 64 or
+                          m.padding_mode != "zeros"):
+            return False
+    return True
+
+
 def _run_conv_stack(stack, x):
     """nn.Sequential of [conv, LeakyReLU, conv, LeakyReLU, ... (, conv)]: each activation is fused
-    into the epilogue of the convolution before it."""
+    into the epilogue of the convolution before it.  Returns fp32 (a bf16 tower converts at its end)."""
     mods = list(stack)
+    lo = torch.bfloat16 if _tower_bf16_ok(stack, x) else None
     i = 0
     while i < len(mods):
         nxt = mods[i + 1] if i + 1 < len(mods) else None
         if nxt is not None and not isinstance(nxt, nn.Conv2d):
             act, slope = _activation_of(nxt)
-            x = mods[i](x, act=act, slope=slope)
+            if lo is not None and i == 0:
+                x = mods[i](x, act=act, slope=slope, out_dtype=lo)      # thin16 stem: fp32 image -> bf16
+            else:
+                x = mods[i](x, act=act, slope=slope)
             i += 2
         else:
-            x = mods[i](x)
+            x = mods[i](ops.cast_f32(x))                                # un-activated head convolution: fp32
             i += 1
-    return x
+    return ops.cast_f32(x)
 
 
 def _patch_tower(nch_in, nch, reduce, num_cls, with_head):

@@ -643,11 +643,41 @@ def wgrad_plan(d):
 def _act_bwd(dy, y, act, slope):
     if act == ACT_NONE:
         return dy
-    if dy.dtype != torch.float32:
-        raise SrganKernelError("fused conv activations are fp32-only (the bf16 trunk activates in its norm kernels)")
+    if dy.dtype != y.dtype:
+        raise SrganKernelError("act_bwd: dy is %s, the activation output was %s" % (dy.dtype, y.dtype))
     dz = torch.empty_like(y)
-    _call("srgan_act_bwd", _p(dy), _p(y), _p(dz), y.numel(), act, slope, _stream())
+    if y.dtype == BF16:           # the bf16 discriminator tower (LeakyReLU fused into the conv epilogues)
+        _call("srgan_act_bwd_bf16", _p(dy), _p(y), _p(dz), y.numel(), act, slope, _stream())
+    else:
+        _call("srgan_act_bwd", _p(dy), _p(y), _p(dz), y.numel(), act, slope, _stream())
     return dz
+
+
+class _CastF32Fn(torch.autograd.Function):
+    """bf16 -> fp32 (values unchanged); the gradient comes back rounded to bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.empty_like(x, dtype=torch.float32)
+        if x.numel():
+            _call("srgan_cast_bf16_f32", _p(x), _p(y), x.numel(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _raw_to_nhwc(dy) if dy.dim() == 4 else dy.contiguous()
+        dx = torch.empty_like(dy, dtype=BF16)
+        if dy.numel():
+            cast_bf16(dy, dx)
+        return dx
+
+
+def cast_f32(x):
+    """A bf16 activation as fp32 (no-op for fp32 inputs): the boundary between a bf16 tower and fp32 heads."""
+    if x.dtype == torch.float32:
+        return x
+    _req(x)
+    return _CastF32Fn.apply(_raw_to_nhwc(x) if x.dim() == 4 else x.contiguous())
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -717,8 +747,6 @@ class _Conv2dThin16Fn(torch.autograd.Function):
         if lib.srgan_conv2d_thin16_supported(d, 0) != 1:
             raise SrganKernelError("thin16 conv: shape not supported (N=%d C=%d K=%d %dx%d stride %d)"
                                    % (N, C, K, R, S, stride))
-        if thin_in and act != ACT_NONE:
-            raise SrganKernelError("thin16 stem: no fused activation (the norm behind it activates)")
         y = _empty_nhwc(N, K, d.P, d.Q, x, dtype=BF16 if thin_in else torch.float32)
         if y.numel():
             nb = lib.srgan_conv2d_thin16_workspace(d, 0)
@@ -740,12 +768,19 @@ class _Conv2dThin16Fn(torch.autograd.Function):
         if d.N == 0:
             return (torch.zeros_like(x) if ctx.needs_input_grad[0] else None), None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
-            if lib.srgan_conv2d_thin16_supported(d, 1) != 1:
+            if lib.srgan_conv2d_thin16_supported(d, 1) == 1:
+                dx = torch.empty_like(x)
+                nb = lib.srgan_conv2d_thin16_workspace(d, 1)
+                ws = _workspace(x.device, nb) if nb else None
+                _call("srgan_conv2d_dgrad_thin16", d, _p(dz), _p(_krsc(ctx.weight)), _p(dx), _p(ws), nb, _stream())
+            elif d.C <= 4 and dz.dtype == BF16:
+                # strided stems (discriminator, encoder): the image gradient goes through an fp32 copy of dz and the
+                # fp32 engine's dgrad (rare: only passes that back-propagate into the image)
+                dz32 = torch.empty_like(dz, dtype=torch.float32)
+                _call("srgan_cast_bf16_f32", _p(dz), _p(dz32), dz.numel(), _stream())
+                dx = _dgrad(d, dz32, _krsc(ctx.weight), x)
+            else:
                 raise SrganKernelError("thin16 conv: no input-gradient kernel for this shape")
-            dx = torch.empty_like(x)
-            nb = lib.srgan_conv2d_thin16_workspace(d, 1)
-            ws = _workspace(x.device, nb) if nb else None
-            _call("srgan_conv2d_dgrad_thin16", d, _p(dz), _p(_krsc(ctx.weight)), _p(dx), _p(ws), nb, _stream())
         want_w = ctx.needs_input_grad[1]
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if want_w or want_b:

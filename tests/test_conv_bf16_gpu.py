@@ -458,3 +458,57 @@ def test_reflect_pad_and_pool_bf16(shape):
     ar = a.detach().float().requires_grad_(True)
     dar, = torch.autograd.grad(F.avg_pool2d(ar, 2), ar, gz)
     assert da.dtype == torch.bfloat16 and _rel(da, dar) < 4e-3 and torch.equal(db, gz)
+
+
+def test_act_bwd_bf16_and_cast_f32():
+    """LeakyReLU backward on bf16 tensors and the widening cast at a bf16 tower's fp32 boundary."""
+    torch.manual_seed(7)
+    y = torch.randn(3, 64, 9, 11, device=DEV).to(torch.bfloat16).contiguous(memory_format=CL)
+    dy = torch.randn(3, 64, 9, 11, device=DEV).to(torch.bfloat16).contiguous(memory_format=CL)
+    dz = ops._act_bwd(dy, y, ops.ACT_LRELU, 0.01)
+    ref = (dy.float() * torch.where(y.float() > 0, 1.0, 0.01)).to(torch.bfloat16)
+    assert dz.dtype == torch.bfloat16 and torch.equal(dz, ref)
+    x = y.clone().requires_grad_(True)
+    f = ops.cast_f32(x)
+    assert f.dtype == torch.float32 and torch.equal(f, y.float())
+    g, = torch.autograd.grad(f, x, dy.float())
+    assert g.dtype == torch.bfloat16 and torch.equal(g, dy)
+    z = torch.randn(5, 7, device=DEV)
+    assert ops.cast_f32(z) is z
+
+
+def test_discriminator_bf16_tower_against_fp32_engine():
+    """SingleDiscriminator_solo_multi (nb02 / 03 / 05) forward / backward with the wide tower in bf16 (thin16 stem with
+    fused LeakyReLU, three kind::f16 convolutions, fp32 heads; the narrow tower stays TF32) against the exact-fp32 engine
+    on the same weights; the TF32 engine's distance printed next to it.  ref pyfiles/model.py:294-346."""
+    import cases
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(0)
+    D = model.SingleDiscriminator_solo_multi(3, 64, 2, 4, "instance", 4).to(DEV)
+    x = (torch.rand(6, 3, 128, 128, device=DEV) * 2 - 1).requires_grad_(True)
+    out = {}
+    for eng in ("fp32", "auto", "bf16"):
+        ops.set_conv_engine(eng)
+        try:
+            for p in D.parameters():
+                p.grad = None
+            o, c = D(x)
+            assert all(t.dtype == torch.float32 for t in o + c)
+            loss = sum((t ** 2).mean() for t in o) + sum((t[:, 0]).mean() for t in c)
+            dx, = torch.autograd.grad(loss, x, retain_graph=True)
+            loss.backward()
+            out[eng] = ([t.detach().clone() for t in o + c], dx.clone(),
+                        {n: p.grad.detach().clone() for n, p in D.named_parameters()})
+        finally:
+            ops.set_conv_engine("auto")
+    y0, dx0, g0 = out["fp32"]
+    for eng in ("auto", "bf16"):
+        y, dx, g = out[eng]
+        ey = max(_rel(a, b) for a, b in zip(y, y0))
+        e = (ey, _rel(dx, dx0), _rel_dict(g, g0), _cos_dict(g, g0))
+        print("discriminator %s vs fp32 engine: outputs %.2e  dx %.2e  param grads %.2e (cos %.4f)" % ((eng,) + e))
+        # measured on B200: TF32 2.1e-3 / 3.3e-2 / 5.3e-3, bf16 tower 2.4e-3 / 7.4e-2 / 1.1e-2 (cos 0.9999); bounds = 3 x
+        if eng == "bf16":
+            assert e[0] < 8e-3 and e[1] < 2.5e-1 and e[2] < 4e-2 and e[3] > 0.999, e
+        else:
+            assert e[0] < 7e-3 and e[1] < 1e-1 and e[2] < 2e-2, e

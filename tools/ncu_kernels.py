@@ -41,7 +41,7 @@ def main():
             jobs.append((name + " wgrad", lambda: ops._wgrad(d, x, dy, True, False)))
         else:
             d = ops._desc(B, H, H, C, K, R, R, stride, pad)
-            thin = C <= 4 or K <= 4            # the RGB stem / head keep fp32 tensors on both sides (norms convert)
+            thin = C <= 4 or K <= 4            # fp32 on both sides: the TF32-engine kernels of the RGB layers / the E and D stems
             xd = torch.float32 if thin else act_dtype
             yd = torch.float32 if thin else act_dtype
             x = torch.randn(B, C, H, H, device=dev).to(xd).contiguous(memory_format=CL)
@@ -92,6 +92,56 @@ def main():
 
     a1, b1 = torch.rand(B, 3, 128, 128, device=dev), torch.rand(B, 3, 128, 128, device=dev)
     jobs.append(("L1 mean 3x128x128", lambda: ops.l1_mean(a1, b1)))
+
+    if a.engine == "bf16":
+        # thin16: the RGB stem / head with a bf16 fat side
+        BF = torch.bfloat16
+        img = (torch.rand(B, 3, 128, 128, device=dev) * 2 - 1).contiguous(memory_format=CL)
+        ws_ = torch.nn.Parameter((torch.randn(64, 3, 7, 7, device=dev) * 0.05).contiguous(memory_format=CL))
+        wh_ = torch.nn.Parameter((torch.randn(3, 64, 7, 7, device=dev) * 0.05).contiguous(memory_format=CL))
+        fat = torch.randn(B, 64, 128, 128, device=dev).to(BF).contiguous(memory_format=CL).requires_grad_(True)
+        imgg = img.clone().requires_grad_(True)
+        ys = ops.conv2d(imgg, ws_, None, 1, 3, out_dtype=BF)
+        yh = ops.conv2d(fat, wh_, None, 1, 3, act=ops.ACT_TANH)
+        gs, gh_ = torch.randn_like(ys), torch.randn_like(yh)
+        jobs.append(("thin16 stem fprop (fp32 image -> bf16)", lambda: ops.conv2d(img, ws_, None, 1, 3, out_dtype=BF)))
+        jobs.append(("thin16 stem dgrad + wgrad", lambda: torch.autograd.grad(ys, [imgg, ws_], gs, retain_graph=True)))
+        jobs.append(("thin16 head fprop (bf16 -> fp32 image, tanh)", lambda: ops.conv2d(fat.detach(), wh_, None, 1, 3, act=ops.ACT_TANH)))
+        jobs.append(("thin16 head dgrad + wgrad", lambda: torch.autograd.grad(yh, [fat, wh_], gh_, retain_graph=True)))
+
+        # the one-pass (cluster) instance norm, opt-in
+        xo = torch.randn(B, 256, 32, 32, device=dev).to(BF).contiguous(memory_format=CL).requires_grad_(True)
+        g1, b1_ = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+        cb1 = torch.randn(B, 256, device=dev)
+        lib = ops._lib()
+
+        def onepass(fn):
+            def run():
+                prev = lib.srgan_inorm_onepass_enable(1)
+                try:
+                    return fn()
+                finally:
+                    lib.srgan_inorm_onepass_enable(prev)
+            return run
+        prev = lib.srgan_inorm_onepass_enable(1)
+        yo = ops.instance_norm_act(xo, g1, b1_, cb1, None, 1e-5, ops.ACT_RELU, 0.0)
+        lib.srgan_inorm_onepass_enable(prev)
+        dyo = torch.randn_like(yo)
+        jobs.append(("IN 256@32 one-pass cluster fwd", onepass(
+            lambda: ops.instance_norm_act(xo.detach(), g1, b1_, cb1, None, 1e-5, ops.ACT_RELU, 0.0))))
+        jobs.append(("IN 256@32 one-pass cluster bwd", onepass(lambda: torch.autograd.grad(yo, xo, dyo, retain_graph=True))))
+
+    # f4: cross entropy of the notebook-04 job (batch 512) and PRDC on 2048 x 2048 features of 4096 dimensions
+    xe = torch.randn(512, 4, device=dev, requires_grad=True)
+    le = torch.randint(0, 4, (512,), device=dev)
+    jobs.append(("cross entropy 512x4 fwd + bwd", lambda: torch.autograd.grad(ops.cross_entropy(xe, le), xe)))
+    fr, ff = torch.randn(2048, 4096, device=dev), torch.randn(2048, 4096, device=dev) * 1.1
+    jobs.append(("PRDC 2048 x 2048 x 4096, k = 5", lambda: ops.prdc_counts(fr, ff, 5)))
+
+    # gradient fold of the generator's flat buffers (14 M parameters, two parked contributions)
+    gf = [torch.zeros(14_000_000, device=dev) for _ in range(3)]
+    jobs.append(("gradient fold, 14 M parameters, 2 parked contributions", lambda: ops._call(
+        "srgan_grad_fold", ops._p(gf[0]), ops._p(gf[1]), ops._p(gf[2]), gf[0].numel(), ops._stream())))
 
     jobs = [j for j in jobs if a.only in j[0]]
     for name, fn in jobs:

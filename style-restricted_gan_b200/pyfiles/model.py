@@ -441,7 +441,12 @@ class SingleDiscriminator_original_multi(nn.Module):
 
     def forward(self, x):
         x = ops.to_nhwc(x)
-        return [self.discriminator1(x), self.discriminator2(self.down(x))]
+        with ops.tower_streams(x) as ts:
+            with ts.side():
+                out2 = self.discriminator2(self.down(x))
+            out1 = self.discriminator1(x)
+            ts.join(out2)
+        return [out1, out2]
 
 
 class SingleDiscriminator_solo(nn.Module):
@@ -482,13 +487,16 @@ class SingleDiscriminator_solo_multi(nn.Module):
 
     def forward(self, x):
         x = ops.to_nhwc(x)
-        disout1 = self.discriminator1(x)
-        disout2 = self.discriminator2(self.down(x))
-        output1 = self.last_layer1(disout1)
-        output2 = self.last_layer2(disout2)
-        out_class1 = self._classify(self.classification_layer1, disout1)
-        out_class2 = self._classify(self.classification_layer2, disout2)
-        return [output1, output2], [out_class1.view(-1, self.n_class), out_class2.view(-1, self.n_class)]
+        with ops.tower_streams(x) as ts:
+            with ts.side():                      # the narrow tower and its heads: small kernels, second stream
+                disout2 = self.discriminator2(self.down(x))
+                output2 = self.last_layer2(disout2)
+                out_class2 = self._classify(self.classification_layer2, disout2).view(-1, self.n_class)
+            disout1 = self.discriminator1(x)
+            output1 = self.last_layer1(disout1)
+            out_class1 = self._classify(self.classification_layer1, disout1).view(-1, self.n_class)
+            ts.join(output2, out_class2)
+        return [output1, output2], [out_class1, out_class2]
 
 
 # --------------------------------------------------------------------------------------------

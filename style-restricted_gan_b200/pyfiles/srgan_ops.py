@@ -105,32 +105,38 @@ class _ScratchSet(object):
     def __init__(self):
         self.ws, self.red, self.ctr, self.keep = {}, {}, {}, []
 
+    # Every buffer is keyed by (device, stream): two streams that run kernels concurrently (the two towers of the
+    # multi-scale discriminators, see tower_streams) must not share scratch.
+
     def counters(self, dev, nbytes):
         """Zero-initialised int32 ticket counters of the norm kernels (they leave them zero, see
         srgan_inorm_fwd_mixed)."""
-        c = self.ctr.get(dev)
+        key = (dev, _stream())
+        c = self.ctr.get(key)
         if c is None or c.numel() * 4 < nbytes:
             c = torch.zeros(max(nbytes // 4 + 1, 1 << 16), dtype=torch.int32, device=dev)
-            self.ctr[dev] = c
+            self.ctr[key] = c
             if self is not _global_scratch:
                 self.keep.append(c)
         return c
 
     def workspace(self, dev, nbytes):
-        buf = self.ws.get(dev)
+        key = (dev, _stream())
+        buf = self.ws.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
-            self.ws[dev] = buf
+            self.ws[key] = buf
             if self is not _global_scratch:
                 self.keep.append(buf)          # addresses are baked into the graph: nothing is ever released
         return buf
 
     def red_scratch(self, dev):
-        s = self.red.get(dev)
+        key = (dev, _stream())
+        s = self.red.get(key)
         if s is None:
             # zero-initialised ticket counter; inside a capture this is a captured memset, replayed with the graph
             s = torch.zeros(_lib().srgan_reduce_scratch_bytes(0) // 4, dtype=torch.float32, device=dev)
-            self.red[dev] = s
+            self.red[key] = s
         return s
 
 
@@ -158,6 +164,49 @@ class private_scratch(object):
 
 def _workspace(dev, nbytes):
     return _scratch_set.workspace(dev, nbytes)
+
+
+# ---- two independent sub-networks on two streams (the towers of the multi-scale discriminators): the narrow tower's
+# kernels are small (8 - 64 CTAs, launch bound) and fit next to the wide tower's on other SMs.  Autograd runs every
+# backward node on the stream of its forward and synchronises across streams, so the split carries over to backward.
+# Measured (same box, ABAB, batch 64, CUDA graph): 51.9 / 51.3 ms with, 52.5 / 52.7 ms without; losses bit-identical.
+TOWER_STREAMS = os.environ.get("SRGAN_TOWER_STREAMS", "1") != "0"
+_tower_side = {}
+
+
+class tower_streams(object):
+    """with tower_streams(x) as ts: ... ; with ts.side(): y2 = f2(x) ; y1 = f1(x) ; ts.join(y2)"""
+
+    def __init__(self, *inputs):
+        self.inputs = [t for t in inputs if torch.is_tensor(t) and t.is_cuda]
+        self.enabled = TOWER_STREAMS and bool(self.inputs)
+
+    def __enter__(self):
+        if self.enabled:
+            dev = self.inputs[0].device
+            self.main = torch.cuda.current_stream(dev)
+            st = _tower_side.get(dev)
+            if st is None:
+                st = _tower_side[dev] = torch.cuda.Stream(dev)
+            self.side_stream = st
+            st.wait_stream(self.main)
+            for t in self.inputs:
+                t.record_stream(st)
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def side(self):
+        import contextlib
+        return torch.cuda.stream(self.side_stream) if self.enabled else contextlib.nullcontext()
+
+    def join(self, *outputs):
+        if self.enabled:
+            self.main.wait_stream(self.side_stream)
+            for t in outputs:
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(self.main)
 
 
 def _red_scratch(dev):

@@ -486,6 +486,9 @@ def _need16(d, p):
 # itself becomes one pass (fold + apply: 25.7 vs 33.0 us).  Kept for planes where the conv has smem headroom.
 _tile_stats = None
 _TILE_STATS = os.environ.get("SRGAN_TILE_STATS", "0") != "0"
+# SRGAN_TILE_STATS=2: only for convolutions with <= 128 output channels (64- / 128-wide tiles: tensor pipe 27 - 42 %
+# busy, i.e. with epilogue headroom - unlike the 256-wide residual trunk)
+_TILE_STATS_MAXK = 128 if os.environ.get("SRGAN_TILE_STATS", "0") == "2" else 1 << 30
 
 
 def set_tile_stats(on):
@@ -497,7 +500,7 @@ def set_tile_stats(on):
 
 def _tile_stats_buffer(d, p, out, plain):
     """fp32 [N, rows, K_out, 2] when the pass can deliver tile statistics for `out` (and the epilogue is plain)."""
-    if not _TILE_STATS or not plain:
+    if not _TILE_STATS or not plain or out.shape[1] > _TILE_STATS_MAXK:
         return None, 0
     rows = _lib().srgan_conv2d_bf16_stat_rows(d, p)
     if rows <= 0:

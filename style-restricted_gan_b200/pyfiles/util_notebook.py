@@ -47,6 +47,7 @@ _NO_BATCH_FAKES = os.environ.get("SRGAN_DBG_NO_BATCH_FAKES", "0") != "0"    # br
 _SPLIT_D = os.environ.get("SRGAN_DBG_SPLIT_D", "0") != "0"           # bring-up: D(real) and D(fake) as two passes, like the reference
 _REENCODE = os.environ.get("SRGAN_DBG_REENCODE", "0") != "0"     # bring-up: second encoder pass of phase 1, like the reference
 _SPLIT_BACKWARD = os.environ.get("SRGAN_DBG_SPLIT_BACKWARD", "0") != "0"     # bring-up: the reference's two calls
+_GEN_PIPELINE = os.environ.get("SRGAN_GEN_PIPELINE", "0") != "0"    # generator passes of the D updates on a second stream
 
 
 def _world():
@@ -360,6 +361,63 @@ class _UnrolledTrainer(object):
             images = self._nG(torch.cat([src] * n, 0), cond)
         return [(images[i * B:(i + 1) * B], styles[i]) for i in range(n)]
 
+    def _pipelined_fakes(self):
+        """The k generator passes of the k discriminator updates, issued up front on a second stream: the generator
+        does not change during `UnrolledUpdate`'s loop and the discriminator does not consume the CPU generator, so
+        pass i + 1 (full-GPU convolutions) can run next to discriminator update i, whose many small kernels leave SMs
+        idle.  Same kernels, same data, same noise order - results are bit-identical to the sequential schedule; under
+        CUDA-graph capture the two streams become parallel branches of the graph.  The LAST pass keeps its autograd
+        graph (phase 2 of `update_GandE` back-propagates through it - on this stream, autograd follows the forward).
+        Returns [(image, noise, event)] or None (CPU tensors, one discriminator per class, batch-coupled norms,
+        SRGAN_GEN_PIPELINE=0)."""
+        if not _GEN_PIPELINE or self.k < 2 or isinstance(self._nD, (list, tuple)) or self._coupled["G"]:
+            return None
+        src = self.source_image
+        if not (torch.is_tensor(src) and src.is_cuda):
+            return None
+        dev = src.device
+        main = torch.cuda.current_stream(dev)
+        gen = getattr(self, "_gen_stream", None)
+        if gen is None:
+            gen = self._gen_stream = torch.cuda.Stream(dev)
+        gen.wait_stream(main)
+        src.record_stream(gen)
+        out = []
+        with torch.cuda.stream(gen):
+            for i in range(self.k):
+                with torch.set_grad_enabled(i == self.k - 1):
+                    image, noise = self.G_transformation(self.label["target"], src, False)
+                ev = torch.cuda.Event()
+                ev.record(gen)
+                out.append((image, noise, ev))
+        return out
+
+    def _take_fake(self, item):
+        """Make the compute stream wait for a pipelined generator pass; returns (image, noise)."""
+        image, noise, ev = item
+        main = torch.cuda.current_stream(image.device)
+        main.wait_event(ev)
+        image.record_stream(main)
+        noise.record_stream(main)
+        return image, noise
+
+    def _unrolled_D(self):
+        """The k discriminator updates of `UnrolledUpdate`; returns the first update's loss."""
+        early = self._early_fakes()
+        piped = self._pipelined_fakes() if not early else None
+        errorD = None
+        for i in range(self.k):
+            if piped is not None:
+                fake = self._take_fake(piped[i])
+            else:
+                fake = early[i] if early and i < self.k - 1 else None
+            errD = self.update_D(keep_graph=(i == self.k - 1), fake=fake)
+            if i == 0:
+                errorD = errD
+                # (the reference snapshots D.state_dict() here and reloads it after the loop; the snapshot aliases the
+                #  live parameters, so nothing is rolled back -- reproduced by doing nothing)
+        return errorD
+
     def _solo_D_loss(self, fake):
         """LSGAN + class loss of the single (solo-multi) discriminator on the real batch and on `fake`
         (ref pyfiles/util_notebook.py:582-589).  The discriminator has no batch-coupled layer (convolutions, LeakyReLU,
@@ -670,13 +728,7 @@ class SingleGAN_training(_UnrolledTrainer):
         return ops.l1_mean(z, mu)
 
     def UnrolledUpdate(self):
-        early = self._early_fakes()
-        for i in range(self.k):
-            errD = self.update_D(keep_graph=(i == self.k - 1), fake=early[i] if early and i < self.k - 1 else None)
-            if i == 0:
-                errorD = errD
-                # (the reference snapshots D.state_dict() here and reloads it below; the snapshot aliases the
-                #  live parameters, so nothing is rolled back -- reproduced by doing nothing)
+        errorD = self._unrolled_D()
         self._errD_first = errorD.detach() if torch.is_tensor(errorD) else errorD    # value only: no graph is kept
         errorG, errorE = self.update_GandE()
         self._comm_join()
@@ -734,11 +786,7 @@ class SRGAN_training(_UnrolledTrainer):
         return ops.l1_mean(info[1], mu)
 
     def UnrolledUpdate(self):
-        early = self._early_fakes()
-        for i in range(self.k):
-            errD = self.update_D(keep_graph=(i == self.k - 1), fake=early[i] if early and i < self.k - 1 else None)
-            if i == 0:
-                errorD = errD       # (state_dict snapshot / reload of the reference is an aliasing no-op)
+        errorD = self._unrolled_D()
         self._errD_first = errorD.detach() if torch.is_tensor(errorD) else errorD    # value only: no graph is kept
         errorG, errorE = self.update_GandE()
         self._comm_join()

@@ -1288,12 +1288,20 @@ static int thin_pad_launch(const ThinPlan& t, const float* thin, float* tp, cuda
   SRGAN_RETURN_LAUNCH();
 }
 
+// direct form (below): the tensor core reads the im2col rows from one copy of the image row
+static bool thin_direct_plan(const srgan_conv_desc* d, int pass, ThinPlan* t);
+template <typename OT>
+static int conv_thin_direct_launch(const srgan_conv_desc* d, const ThinPlan& t, const float* thin, const float* w,
+                                   const float* bias, OT* out, int act, float slope, void* ws, size_t ws_bytes,
+                                   cudaStream_t st);
+
 // y = act(conv(x) + bias) with thin x (pass 0)  /  dx = conv_transpose(dy) with thin dy (pass 1)
 template <typename OT = float>
 static int conv_thin_fwdlike_launch(const srgan_conv_desc* d, int pass, const float* thin, const float* w,
                                     const float* bias, OT* out, int act, float slope, void* ws, size_t ws_bytes,
                                     cudaStream_t st) {
   ThinPlan t;
+  if (thin_direct_plan(d, pass, &t)) return conv_thin_direct_launch<OT>(d, t, thin, w, bias, out, act, slope, ws, ws_bytes, st);
   if (!thin_plan(d, pass, &t)) { set_error("thin conv: unsupported shape"); return SRGAN_E_UNSUPPORTED; }
   const size_t tpb = thin_tp_bytes(t), bpb = align256((size_t)t.fC * t.R * 32 * sizeof(float));
   if (!ws || ws_bytes < tpb + bpb) { set_error("thin conv: workspace %zu < %zu", ws_bytes, tpb + bpb); return SRGAN_E_WORKSPACE; }
@@ -1533,6 +1541,249 @@ int conv_dgrad_umma_launch(const srgan_conv_desc* d, const float* dy, const floa
   Problem pr = {};
   dgrad_problem(d, dy, wt, pr);
   return run_problem(pr, nullptr, dx, SRGAN_ACT_NONE, 0.f, st, nullptr, addend);
+}
+
+// ------------------------------------------------------------------------------------------ thin layers, direct form
+// Stride-1 convolutions with a <= 4-channel INPUT side and 64 output channels (RGB stem fprop; the head's input gradient
+// with the roles of dy / flipped filter) without materialising im2col rows.  The row-packed form above makes TMA
+// deliver, per filter row, 128 overlapping rows of 128 B (16 KB for 2 KB of distinct image data): 7.4 x expansion on
+// the L2 -> shared-memory path, which bounds that kernel (ncu: 1.1 GB of TMA reads for a 134 MB result).
+// Here ONE copy of every padded NHWC4 image row (Wp pixels x 16 B, contiguous) is bulk-copied into a ring of row slots
+// and the tensor core reads the overlapping im2col rows itself: without swizzle a K-major core matrix is 8 rows of 16
+// bytes that are 16 bytes apart - eight consecutive pixels - so
+//     A_r[m][j]  (pixel m of the output row, j = s*4 + c)  = slot(h + r)[(m + j/4) * 16 + (j%4) * 4]
+// is the canonical no-swizzle layout with LBO (next K core matrix) = 16 B and SBO (next 8 rows) = 128 B: overlapping
+// core matrices over the same bytes.  One output row (<= 128 pixels) = R x 4 MMAs (M 128, N 64, K 8 tf32) into a
+// four-deep ring of TMEM accumulators; consecutive output rows share R - 1 input rows, so a CTA walking down a band of rows
+// loads one new 2 KB row per 16 KB (bf16) of output.  The packed filter (R x 8 KB, no-swizzle K-major: chunk stride 1 KB,
+// 8-filter group stride 128 B) is loaded once per CTA.  Warp 0: bulk-copy producer, warp 1: MMA issuer (+ TMEM),
+// warps 2-5: epilogue (tcgen05.ld -> bias / activation -> 32-byte stores, fp32 or bf16 output).
+constexpr int kTDThreads = 192;
+constexpr int kTDRing = 16;                    // image-row slots
+constexpr int kTDSlotBytes = 2304;             // >= (128 + 8) pixels x 16 B, multiple of 128
+constexpr int kTDAcc = 4;                      // TMEM accumulators of 64 columns (one per output row in flight)
+struct ThinDirectP {
+  int N, Ho, Wo, K;          // output [N][Ho][Wo][K], Wo <= 128, K == 64
+  int Hp, Wp;                // padded thin tensor TP[N][Hp][Wp][4] (fp32)
+  int R;                     // filter rows (<= 8)
+  int bands, BH;             // row bands per image, rows per band
+  int row_bytes;             // bytes of a TP row that are copied (multiple of 16, <= kTDSlotBytes)
+  int act;
+  float slope;
+};
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo >> 4) << 16;                 // K-direction stride between core matrices
+  d |= (uint64_t)(sbo >> 4) << 32;                 // M / N-direction stride between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void bulk_g2s_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(kTDThreads, 1)
+conv_thin_direct_kernel(const __grid_constant__ ThinDirectP p, const float* __restrict__ tp, const float* __restrict__ bp,
+                        const float* __restrict__ bias, OT* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int b_bytes = p.R * 8192;
+  uint8_t* sb = smem;
+  uint8_t* ring = smem + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kTDRing * kTDSlotBytes);
+  uint64_t* empty = full + kTDRing;
+  uint64_t* t_full = empty + kTDRing;              // [kTDAcc]
+  uint64_t* t_empty = t_full + kTDAcc;             // [kTDAcc]
+  uint64_t* b_full = t_empty + kTDAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.N * p.bands;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTDRing; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kTDAcc; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4); }
+    mbar_init(b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // slots start as zeros: the MMAs read up to 16 bytes past a copied row (taps beyond S carry zero filter weights, but
+  // 0 x NaN garbage would still poison the accumulator)
+  for (int i = threadIdx.x; i < kTDRing * kTDSlotBytes / 16; i += kTDThreads)
+    reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) tmem_alloc(tmem_slot, kTDAcc * 64);
+  tc_fence_before();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, b_bytes);
+      bulk_g2s_1d(sb, bp, b_bytes, b_full);
+      int li = 0;                                  // image rows loaded so far by this CTA
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = item / p.bands, band = item - n * p.bands;
+        const int h0 = band * p.BH, h1 = min(p.Ho, h0 + p.BH);
+        for (int hp = h0; hp < h1 + p.R - 1; ++hp, ++li) {       // padded rows h0 .. h1 - 1 + R - 1
+          const int slot = li % kTDRing;
+          mbar_wait(empty + slot, (((uint32_t)(li / kTDRing)) & 1u) ^ 1u);
+          mbar_expect_tx(full + slot, p.row_bytes);
+          bulk_g2s_1d(ring + slot * kTDSlotBytes, tp + ((size_t)n * p.Hp + hp) * p.Wp * 4, p.row_bytes, full + slot);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = B = tf32, both K-major, N = 64, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      mbar_wait(b_full, 0);
+      const uint64_t adesc0 = smem_desc_nosw(smem_u32(ring), 16, 128);        // A: next K chunk + 16 B, next 8 pixels + 128 B
+      const uint64_t bdesc0 = smem_desc_nosw(smem_u32(sb), 1024, 128);        // B: next K chunk + 1 KB, next 8 filters + 128 B
+      int li = 0, waited = 0, ti = 0;              // first row of the current item, rows waited for, output rows done
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = item / p.bands, band = item - n * p.bands;
+        const int h0 = band * p.BH, h1 = min(p.Ho, h0 + p.BH);
+        (void)n;
+        for (int h = h0; h < h1; ++h, ++ti) {
+          const int first = li + (h - h0);          // load index of padded row h
+          for (; waited < first + p.R; ++waited)    // rows h .. h + R - 1 have landed
+            mbar_wait(full + waited % kTDRing, ((uint32_t)(waited / kTDRing)) & 1u);
+          const int buf = ti % kTDAcc;
+          mbar_wait(t_empty + buf, (((uint32_t)(ti / kTDAcc)) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + buf * 64;
+          // one thread issues all MMAs: keep its instruction count per MMA minimal (descriptors advance by adds: the
+          // first version rebuilt both descriptors per MMA and was bound by this thread, 3000 clk per output row)
+          int slot = first % kTDRing;
+          uint64_t bdesc = bdesc0;
+          for (int r = 0; r < p.R; ++r) {
+            const uint64_t adesc = adesc0 + (uint64_t)(slot * (kTDSlotBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)             // K step = 8 floats = 2 pixels of A (+32 B), 2 chunks of B (+2 KB)
+              umma_tf32(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc, (r | k) != 0);
+            bdesc += 8192 >> 4;
+            if (++slot == kTDRing) slot = 0;
+          }
+          umma_commit(empty + first % kTDRing);     // padded row h is not needed by later output rows
+          umma_commit(t_full + buf);
+        }
+        // the last R - 1 rows of the band are released once its last output row has read them
+        for (int r = 1; r < p.R; ++r) umma_commit(empty + (li + (h1 - h0) - 1 + r) % kTDRing);
+        li += (h1 - h0) + p.R - 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;                 // TMEM lane == output pixel of the row
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int V8 = 32 / (int)sizeof(OT);
+    const int vec = ((uintptr_t)y % 32 == 0 && p.K % V8 == 0 && (!bias || (uintptr_t)bias % 16 == 0)) ? 8 : 0;
+    int ti = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int n = item / p.bands, band = item - n * p.bands;
+      const int h0 = band * p.BH, h1 = min(p.Ho, h0 + p.BH);
+      for (int h = h0; h < h1; ++h, ++ti) {
+        const int buf = ti % kTDAcc;
+        mbar_wait(t_full + buf, ((uint32_t)(ti / kTDAcc)) & 1u);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(taddr + buf * 64, ra);
+        tmem_ld32_issue(taddr + buf * 64 + 32, rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + buf);  // the accumulator is in registers
+        if (m < p.Wo) {
+          OT* yrow = y + (((size_t)n * p.Ho + h) * p.Wo + m) * p.K;
+          float v[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(half ? rb[j] : ra[j]);
+            if (vec) {
+              epi_row_chunk_any<32>(v, yrow + half * 32, bias ? bias + half * 32 : nullptr, p.act, p.slope, 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                st_from_float(yrow + half * 32 + j,
+                              apply_act(v[j] + (bias ? __ldg(bias + half * 32 + j) : 0.f), p.act, p.slope));
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTDAcc * 64);
+  }
+}
+
+// packed filter of the direct form, per filter row r: [chunk c = s (4 floats)][8-filter group g][filter f % 8][4 floats]
+// mode 0: value = w[f][r][s][e] ; mode 1 (input gradient of a thin-output layer): = w[e][R-1-r][S-1-s][f]   (e < tc)
+__global__ void thin_direct_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ bp, int K, int C, int R,
+                                               int S, int mode) {
+  const int total = R * 8 * 64 * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 3, f8 = (i >> 2) & 7, g = (i >> 5) & 7, c = (i >> 8) & 7, r = i >> 11;
+    const int f = g * 8 + f8, s = c;
+    float v = 0.f;
+    if (s < S) {
+      if (mode == 0) { if (e < C && f < K) v = w[(((size_t)f * R + r) * S + s) * C + e]; }
+      else           { if (e < K && f < C) v = w[(((size_t)e * R + (R - 1 - r)) * S + (S - 1 - s)) * C + f]; }
+    }
+    bp[i] = v;
+  }
+}
+
+static bool thin_direct_plan(const srgan_conv_desc* d, int pass, ThinPlan* t) {
+  static const bool off = getenv("SRGAN_THIN_DIRECT") && atoi(getenv("SRGAN_THIN_DIRECT")) == 0;
+  if (off || (pass != 0 && pass != 1) || !thin_plan(d, pass, t)) return false;
+  return t->st == 1 && t->fC == 64 && t->fW <= 128 && t->S * 4 <= 32 && t->R <= 8 && t->Wp * 16 <= kTDSlotBytes &&
+         t->Wp >= t->fW + t->S - 1;
+}
+static size_t thin_direct_workspace(const ThinPlan& t) { return thin_tp_bytes(t) + align256((size_t)t.R * 8192); }
+
+template <typename OT>
+static int conv_thin_direct_launch(const srgan_conv_desc* d, const ThinPlan& t, const float* thin, const float* w,
+                                   const float* bias, OT* out, int act, float slope, void* ws, size_t ws_bytes,
+                                   cudaStream_t st) {
+  const size_t tpb = thin_tp_bytes(t), need = thin_direct_workspace(t);
+  if (!ws || ws_bytes < need) { set_error("thin direct conv: workspace %zu < %zu", ws_bytes, need); return SRGAN_E_WORKSPACE; }
+  if (((uintptr_t)thin | (uintptr_t)ws | (uintptr_t)out) % 16) { set_error("thin direct conv: tensors must be 16-byte aligned"); return SRGAN_E_BADARG; }
+  float* tp = (float*)ws;
+  float* bp = (float*)((uint8_t*)ws + tpb);
+  if (int e = thin_pad_launch(t, thin, tp, st)) return e;
+  thin_direct_pack_filter_kernel<<<ceil_div(t.R * 8192 / 4, 256), 256, 0, st>>>(w, bp, d->K, d->C, d->R, d->S, t.mode);
+  ThinDirectP p = {};
+  p.N = t.N; p.Ho = t.fH; p.Wo = t.fW; p.K = t.fC; p.Hp = t.Hp; p.Wp = t.Wp; p.R = t.R;
+  p.act = act; p.slope = slope;
+  p.row_bytes = t.Wp * 16;
+  // rows per band: whole waves of one CTA per SM; every band re-reads R - 1 halo rows (cheap: 2 KB each)
+  long best = -1;
+  for (int b = 1; b <= p.Ho; ++b) {
+    const int bh = ceil_div(p.Ho, b);
+    if (ceil_div(p.Ho, bh) != b) continue;
+    const long waves = ((long)p.N * b + kNumSMs - 1) / kNumSMs;
+    const long cost = waves * (4 * bh + t.R - 1 + 8);
+    if (best < 0 || cost < best) { best = cost; p.bands = b; p.BH = bh; }
+  }
+  const size_t smem = 1024 + (size_t)t.R * 8192 + (size_t)kTDRing * kTDSlotBytes + 512;
+  static unsigned long long attr = 0;
+  {
+    cudaError_t e = ensure_dyn_smem(conv_thin_direct_kernel<OT>, 227 * 1024, &attr);
+    if (e != cudaSuccess) { set_error("conv_thin_direct smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const long items = (long)p.N * p.bands;
+  const unsigned ctas = (unsigned)(items < kNumSMs ? items : kNumSMs);
+  conv_thin_direct_kernel<OT><<<ctas, kTDThreads, smem, st>>>(p, tp, bp, bias, out);
+  SRGAN_RETURN_LAUNCH();
 }
 
 // ------------------------------------------------------------------------------------------ thin layers, bf16 fat side

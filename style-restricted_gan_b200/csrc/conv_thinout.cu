@@ -245,6 +245,10 @@ conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
   const int box_bytes = (128 + p.S - 1) * 128;
 
   if (warp == 0) {
+    // (measured: one producer warp per stage - three warps - does not change the time; neither does keeping the
+    //  partial output rows in registers, below.  What sets the pace is the MMA itself: ~146 clk per N = 32 MMA whose A
+    //  start is shifted by s pixel rows inside the 128-byte-swizzled buffer, against 16 clk of math: 28 MMAs = 4100 clk
+    //  per image row with bf16 input, 56 x 107 = 6000 clk with fp32 input - the same constant per MMA in both.)
     if (lane == 0) {
       mbar_expect_tx(b_full, b_bytes);
       for (int j = 0; j < p.S * p.nchunks; ++j) tma_load_2d(&map_b, b_full, sb + j * 4096, 0, j * 32);
@@ -305,8 +309,23 @@ conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
     float bv[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) bv[t] = (bias && t < p.tc) ? __ldg(bias + t) : 0.f;
+    // Partial output rows live in REGISTERS: part[a] is output row hp + padH - a (a = filter row that input row hp
+    // contributes to it); every step the window shifts by one row and row a = R - 1 is complete.  (The first version
+    // kept them in a shared-memory ring: 21 dependent load-add-store triples per input row made the four epilogue
+    // warps, not the tensor pipe, set the pace - ncu: 14 % of all stall samples on that one line.)
+    float part[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) part[a][t] = 0.f;
     int i = 0;
     for (int hp = hp_beg; hp <= hp_end; ++hp) {
+#pragma unroll
+      for (int a = 7; a > 0; --a)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) part[a][t] = part[a - 1][t];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) part[0][t] = 0.f;
       if (hp >= 0 && hp < p.Hi) {
         const int buf = i & 1;
         mbar_wait(t_full + buf, (i >> 1) & 1);
@@ -317,27 +336,24 @@ conv_thinout2_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty + buf);      // accumulator is in registers: release it right away
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int h = hp - r + p.padH;
-          if (r < p.R && h >= h0 && h < h1) {
-            float* ar = accs + (h & 7) * 4 * 128 + qq;
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (t < p.tc) ar[t * 128] += v[r * 4 + t];
-          }
-        }
+          for (int t = 0; t < 4; ++t) part[a][t] += v[a * 4 + t];      // columns of filter rows >= R are zero
         ++i;
       }
       const int hd = hp + p.padH - (p.R - 1);
-      if (hd >= h0 && hd < h1) {
-        float* ar = accs + (hd & 7) * 4 * 128 + qq;
+      if (hd >= h0 && hd < h1 && qq < p.Wo) {
+        float done[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          if (a == p.R - 1) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) done[t] = part[a][t];
+          }
         float* o = out + (((size_t)n * p.Ho + hd) * p.Wo + qq) * p.tc;
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          if (t < p.tc) {
-            if (qq < p.Wo) o[t] = apply_act(ar[t * 128] + bv[t], p.act, p.slope);
-            ar[t * 128] = 0.f;
-          }
+          if (t < p.tc) o[t] = apply_act(done[t] + bv[t], p.act, p.slope);
       }
     }
   }

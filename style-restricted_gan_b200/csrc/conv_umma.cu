@@ -1658,7 +1658,10 @@ conv_thin_direct_kernel(const __grid_constant__ ThinDirectP p, const float* __re
           tc_fence_after();
           const uint32_t acc = tmem_base + buf * 64;
           // one thread issues all MMAs: keep its instruction count per MMA minimal (descriptors advance by adds: the
-          // first version rebuilt both descriptors per MMA and was bound by this thread, 3000 clk per output row)
+          // first version rebuilt both descriptors per MMA and was bound by this thread, 3000 clk per output row).
+          // Measured and not kept: four output rows interleaved on four accumulators (so that consecutive MMAs are
+          // independent): 130 instead of 105 us - the pace is set by the operand fetch (80 shared-memory wavefronts per
+          // MMA: 128 pixel rows x 32 B through core matrices that straddle 128-byte lines), not by the dependent chain.
           int slot = first % kTDRing;
           uint64_t bdesc = bdesc0;
           for (int r = 0; r < p.R; ++r) {

@@ -166,14 +166,17 @@ __global__ void __launch_bounds__(256) prdc_rows_kernel(const double* __restrict
   }
   if (threadIdx.x == 0) { row_hits_fake[i] = sc[0]; row_min_in[i] = sv[0] < r_real[i]; }
 }
-// per fake column j:  col_hits_real[j] = #{i : d2[i][j] < r_real[i]}   (threads of a warp read consecutive j: coalesced)
+// per fake column j:  col_hits_real[j] = #{i : d2[i][j] < r_real[i]}.  Threads of a warp read consecutive j (coalesced);
+// the rows are cut into gridDim.y slabs whose integer counts are added with atomicAdd (integers: order-independent,
+// bit-exact) into the zeroed result - the first, column-serial version took 0.46 ms for 2048 x 2048 (73 GB/s).
 __global__ void prdc_cols_kernel(const double* __restrict__ d2, const double* __restrict__ r_real, int* __restrict__ col_hits_real,
-                                 int N, int M) {
+                                 int N, int M, int rows_per_slab) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
+  const int i0 = blockIdx.y * rows_per_slab, i1 = min(N, i0 + rows_per_slab);
   int c = 0;
-  for (int i = 0; i < N; ++i) c += d2[(size_t)i * M + j] < __ldg(r_real + i);
-  col_hits_real[j] = c;
+  for (int i = i0; i < i1; ++i) c += d2[(size_t)i * M + j] < __ldg(r_real + i);
+  if (c) atomicAdd(col_hits_real + j, c);
 }
 
 }  // namespace srgan
@@ -216,6 +219,8 @@ extern "C" int srgan_prdc_counts(const double* d2_real_fake, const double* r_rea
   SRGAN_CHECK_ARG(N > 0 && M > 0, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   prdc_rows_kernel<<<N, 256, 0, st>>>(d2_real_fake, r_real, r_fake, row_hits_fake, row_min_in, N, M);
-  prdc_cols_kernel<<<ceil_div(M, 128), 128, 0, st>>>(d2_real_fake, r_real, col_hits_real, N, M);
+  if (cudaMemsetAsync(col_hits_real, 0, (size_t)M * sizeof(int), st) != cudaSuccess) { set_error("prdc_counts: memset failed"); return SRGAN_E_BADARG; }
+  const int slabs = N < 64 ? 1 : (N + 63) / 64;
+  prdc_cols_kernel<<<dim3(ceil_div(M, 128), slabs), 128, 0, st>>>(d2_real_fake, r_real, col_hits_real, N, M, ceil_div(N, slabs));
   SRGAN_RETURN_LAUNCH();
 }

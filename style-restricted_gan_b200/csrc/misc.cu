@@ -494,7 +494,25 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
 // accumulation - and the parking buffers are left zero for the next pass.
 __global__ void grad_fold_kernel(float4* __restrict__ g, float4* __restrict__ p1, float4* __restrict__ p2, size_t n4) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // two elements per trip: six independent 16-byte loads in flight per thread (the one-element form reached 1.1 TB/s)
+  for (; i + stride < n4; i += 2 * stride) {
+    float4 a0 = g[i], a1 = g[i + stride];
+    const float4 b0 = p1[i], b1 = p1[i + stride];
+    float4 c0 = z, c1 = z;
+    if (p2) { c0 = p2[i]; c1 = p2[i + stride]; }
+    a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+    a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+    if (p2) {
+      a0.x += c0.x; a0.y += c0.y; a0.z += c0.z; a0.w += c0.w;
+      a1.x += c1.x; a1.y += c1.y; a1.z += c1.z; a1.w += c1.w;
+      p2[i] = z; p2[i + stride] = z;
+    }
+    p1[i] = z; p1[i + stride] = z;
+    g[i] = a0; g[i + stride] = a1;
+  }
+  for (; i < n4; i += stride) {
     float4 a = g[i];
     const float4 b = p1[i];
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;

@@ -512,3 +512,34 @@ def test_discriminator_bf16_tower_against_fp32_engine():
             assert e[0] < 8e-3 and e[1] < 2.5e-1 and e[2] < 4e-2 and e[3] > 0.999, e
         else:
             assert e[0] < 7e-3 and e[1] < 1e-1 and e[2] < 2e-2, e
+
+
+def test_discriminator_original_multi_bf16_tower_against_fp32_engine():
+    """SingleDiscriminator_original_multi (notebook 01: the patch head is the last convolution of the tower's stack):
+    the wide tower in bf16 up to the head, which reads an fp32 copy; against the exact-fp32 engine on the same weights.
+    ref pyfiles/model.py:255-292."""
+    import cases
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(1)
+    D = model.SingleDiscriminator_original_multi(3, 64, 2, 4, "instance").to(DEV)
+    x = (torch.rand(4, 3, 128, 128, device=DEV) * 2 - 1).requires_grad_(True)
+    out = {}
+    for eng in ("fp32", "bf16"):
+        ops.set_conv_engine(eng)
+        try:
+            for p in D.parameters():
+                p.grad = None
+            o = D(x)
+            assert all(t.dtype == torch.float32 for t in o) and o[0].shape == (4, 1, 7, 7)
+            loss = sum((t ** 2).mean() for t in o)
+            dx, = torch.autograd.grad(loss, x, retain_graph=True)
+            loss.backward()
+            out[eng] = ([t.detach().clone() for t in o], dx.clone(),
+                        {n: p.grad.detach().clone() for n, p in D.named_parameters()})
+        finally:
+            ops.set_conv_engine("auto")
+    y0, dx0, g0 = out["fp32"]
+    y, dx, g = out["bf16"]
+    e = (max(_rel(a, b) for a, b in zip(y, y0)), _rel(dx, dx0), _rel_dict(g, g0), _cos_dict(g, g0))
+    print("discriminator (original, multi) bf16 vs fp32 engine: outputs %.2e  dx %.2e  param grads %.2e (cos %.4f)" % e)
+    assert e[0] < 1e-2 and e[1] < 2.5e-1 and e[2] < 5e-2 and e[3] > 0.998, e

@@ -65,3 +65,34 @@ def test_train_notebooks_resolve_every_name_against_this_surface():
     for nb in NOTEBOOKS:
         missing = sorted(_free_names(os.path.join(ref_harness.REF_ROOT, "notebook", nb + ".ipynb")) - exported)
         assert missing == [], (nb, missing)
+
+
+_PROBE04 = r'''
+import sys, types, json
+sys.path.insert(0, sys.argv[1])
+for n in ("matplotlib", "matplotlib.pyplot", "torchvision", "torchvision.transforms", "tqdm"):
+    try:
+        __import__(n)
+    except Exception:
+        sys.modules[n] = types.ModuleType(n)
+ns = {}
+# cell 1 of notebook 04, verbatim, plus the modules behind the names it uses without importing them
+exec("from util import image_from_output, cuda2numpy, cuda2cpu, weights_init, plot_confusion_matrix\n"
+     "from dataset import get_class_label, FaceDataset\nfrom model import MinMax\n"
+     "from model import Encoder_classifier\nfrom util import pickle_load\n"
+     "import evaluation\nfrom util_notebook import Classifier_training, do_test", ns)
+print(json.dumps(sorted(k for k in ns if not k.startswith("__")) + sorted(dir(ns["evaluation"]))))
+'''
+
+
+def test_notebook_04_and_06_imports_resolve():
+    """Cell 1 of notebooks 04 / 06 (`from util import ...`, `from dataset import ...`, `from model import MinMax`,
+    `from util import pickle_load`) and the f4 additions (Encoder_classifier, the evaluation module, the classifier job)."""
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "style-restricted_gan_b200", "pyfiles")
+    r = subprocess.run([sys.executable, "-c", _PROBE04, here], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    names = set(json.loads(r.stdout.strip().splitlines()[-1]))
+    for k in ("image_from_output", "cuda2numpy", "cuda2cpu", "weights_init", "plot_confusion_matrix", "get_class_label",
+              "FaceDataset", "MinMax", "Encoder_classifier", "pickle_load", "Classifier_training", "do_test",
+              "GAN_evaluation", "evaluation_init", "compute_prdc", "vgg_model"):
+        assert k in names, k

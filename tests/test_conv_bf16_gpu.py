@@ -543,3 +543,41 @@ def test_discriminator_original_multi_bf16_tower_against_fp32_engine():
     e = (max(_rel(a, b) for a, b in zip(y, y0)), _rel(dx, dx0), _rel_dict(g, g0), _cos_dict(g, g0))
     print("discriminator (original, multi) bf16 vs fp32 engine: outputs %.2e  dx %.2e  param grads %.2e (cos %.4f)" % e)
     assert e[0] < 1e-2 and e[1] < 2.5e-1 and e[2] < 5e-2 and e[3] > 0.998, e
+
+
+def test_discriminator_two_streams_is_bit_identical():
+    """The two towers of the multi-scale discriminators on two streams (srgan_ops.tower_streams) against the
+    single-stream schedule: same kernels on the same data - outputs, input gradient and every parameter gradient must be
+    bit-identical (per-stream scratch, autograd's cross-stream synchronisation)."""
+    import cases
+    model, util, nb = cases.use_product_modules()
+    torch.manual_seed(2)
+    D = model.SingleDiscriminator_solo_multi(3, 64, 2, 4, "instance", 4).to(DEV)
+    x = (torch.rand(8, 3, 128, 128, device=DEV) * 2 - 1).requires_grad_(True)
+    res = {}
+    prev = ops.TOWER_STREAMS
+    try:
+        for eng in ("auto", "bf16"):
+            ops.set_conv_engine(eng)
+            for on in (True, False, True):
+                ops.TOWER_STREAMS = on
+                for p in D.parameters():
+                    p.grad = None
+                o, c = D(x)
+                loss = sum((t ** 2).mean() for t in o) + sum((t[:, 1]).mean() for t in c)
+                dx, = torch.autograd.grad(loss, x, retain_graph=True)
+                loss.backward()
+                torch.cuda.synchronize()
+                cur = ([t.detach().clone() for t in o + c], dx.clone(), [p.grad.detach().clone() for p in D.parameters()])
+                key = eng
+                if key in res:
+                    for a, b in zip(cur[0], res[key][0]):
+                        assert torch.equal(a, b), (eng, on)
+                    assert torch.equal(cur[1], res[key][1]), (eng, on)
+                    for a, b in zip(cur[2], res[key][2]):
+                        assert torch.equal(a, b), (eng, on)
+                else:
+                    res[key] = cur
+    finally:
+        ops.TOWER_STREAMS = prev
+        ops.set_conv_engine("auto")
